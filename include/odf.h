@@ -1,0 +1,144 @@
+/* libodf — C ABI of the B200-native FALKON hot path (online-detection on-line learners).
+ *
+ * The reference (hsp-iit/online-detection) has no FFI of its own: its seam is the Python duck
+ * type between first-party code and the third-party `falkon` package
+ * (github.com/FalkonML/falkon @ 0d96c685, INSTALLATION_GUIDE.md:67-77).  Every entry point below
+ * names the reference interface it stands in for.  All pointers are DEVICE pointers to
+ * caller-owned, row-major fp32 buffers (16-byte aligned); `stream` is a cudaStream_t passed as
+ * void*; every call is asynchronous on that stream unless stated; return 0 = OK, negative =
+ * error (text via odf_last_error()).  No torch types cross this boundary; no internal threads;
+ * one process per GPU.  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with ODF_ERR_CUDA.
+ */
+#ifndef ODF_H_
+#define ODF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODF_OK 0
+#define ODF_ERR_ARG (-1)
+#define ODF_ERR_CUDA (-2)
+#define ODF_ERR_WORKSPACE (-3)
+#define ODF_ERR_LINALG (-4)
+
+/* which triangular solve odf_precond_solve applies (FalkonPreconditioner.invT / invTt / invA /
+ * invAt) */
+#define ODF_SOLVE_T 0   /* B <- T^-1  B */
+#define ODF_SOLVE_TT 1  /* B <- T^-T  B */
+#define ODF_SOLVE_A 2   /* B <- A^-1  B */
+#define ODF_SOLVE_AT 3  /* B <- A^-T  B */
+
+const char* odf_last_error(void);
+int odf_version(void);
+
+/* ---- layout helpers ------------------------------------------------------------------------ */
+int64_t odf_pad_dim(int64_t d);   /* feature pitch of prepared operands: round_up(d, 32)        */
+int64_t odf_pad_rows(int64_t n);  /* length of norm vectors / pitch of V^T: round_up(n, 128)    */
+int odf_tpad(int64_t T);          /* padded RHS count: 16 if T<=16, 32 if T<=32, else -1        */
+/* Number of column splits the tile launcher wants for this shape (size of the partial slab). */
+int odf_tile_splits(int64_t n_rows, int64_t n_cols, int64_t d);
+
+/* ---- operand preparation ------------------------------------------------------------------- */
+/* Fused z-score + 3xTF32 split + squared norms.
+ * Replaces OnlineRegionClassifier.zScores (src/modules/region-classifier/
+ * OnlineRegionClassifier.py:224-227) and the norm pre-pass of falkon GaussianKernel.
+ *   x' = (X[r,:] - mean) * scale      (mean may be NULL -> 0)
+ *   hi = tf32(x'), lo = tf32(x' - hi) -> [n x odf_pad_dim(d)], zero padded
+ *   sqnorm[r] = |x'|^2                -> odf_pad_rows(n) floats, zero padded                    */
+int odf_prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean,
+                       float scale, float* hi, float* lo, float* sqnorm, void* stream);
+/* In-place z-score only (same reference lines). */
+int odf_zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
+               void* stream);
+/* V [m x T] (pitch ldv) -> V^T split: vt_hi, vt_lo [T_pad x ldvt] = split(scale * V^T), zero
+ * padded (ldvt = odf_pad_rows(m)). */
+int odf_split_rhs(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, float* vt_hi,
+                  float* vt_lo, int64_t ldvt, int T_pad, void* stream);
+
+/* ---- fused Gaussian-kernel tile (tcgen05 / TMEM / TMA) -------------------------------------- */
+/* partial[s][r][0..T_pad) = sum over the columns of split s of K(row r, col q) * V[q, :]
+ * with K = exp(-|r-q|^2 / (2 sigma^2)).  Stands in for falkon GaussianKernel.mmv
+ * (call sites: FALKONWrapper_with_centers_selection_incore.py:75-82, roi_box_predictors.py:158,
+ * roi_mask_predictors.py:90, rpn.py:225) and for each half of GaussianKernel.dmmv.
+ * n_splits must come from odf_tile_splits(n_rows, n_cols, d).                                   */
+int odf_gauss_mmv_prepared(const float* r_hi, const float* r_lo, const float* r_sqnorm,
+                           int64_t n_rows, const float* q_hi, const float* q_lo,
+                           const float* q_sqnorm, int64_t n_cols, int64_t d_pad,
+                           const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad,
+                           int n_splits, float sigma, float* partial, void* stream);
+/* out[r, t] = scale * sum_s partial[s][r][t] + addend[r, t]   (addend may be NULL) */
+int odf_finish_rows(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T,
+                    float scale, const float* addend, int64_t ld_add, float* out, int64_t ldo,
+                    void* stream);
+/* same reduction, written as the split transposed right-hand side of a following pass */
+int odf_finish_split(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T,
+                     float scale, const float* addend, int64_t ld_add, float* wt_hi, float* wt_lo,
+                     int64_t ldwt, void* stream);
+/* K[i, j] = exp(-|c_i - c_j|^2 / (2 sigma^2)), M x M, pitch ldk.  falkon Kernel.__call__ (K_MM
+ * for FalkonPreconditioner.init, reached through InCoreFalkon.fit, ...incore.py:68).            */
+int odf_gauss_kmm_prepared(const float* c_hi, const float* c_lo, const float* c_sqnorm, int64_t M,
+                           int64_t d_pad, float sigma, float* K, int64_t ldk, void* stream);
+
+/* ---- convenience entry points on plain fp32 operands (prepare internally in `ws`) ----------- */
+#define ODF_OP_MMV 0
+#define ODF_OP_DMMV 1
+#define ODF_OP_KMM 2
+#define ODF_OP_PRECOND 3
+size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T);
+/* out[n x T] = K(X, C) V          — kernel.mmv(X1, X2, v, out) */
+int odf_gauss_mmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_t M, int64_t ldc,
+                  int64_t d, const float* V, int64_t T, int64_t ldv, float sigma, float* out,
+                  int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+/* out[M x T] = K(X,C)^T (K(X,C) V + W); V or W may be NULL — kernel.dmmv(X1, X2, v, w) */
+int odf_gauss_dmmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_t M, int64_t ldc,
+                   int64_t d, const float* V, int64_t ldv, const float* W, int64_t ldw, int64_t T,
+                   float sigma, float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+int odf_gauss_kmm(const float* C, int64_t M, int64_t ldc, int64_t d, float sigma, float* K,
+                  int64_t ldk, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- preconditioner: FalkonPreconditioner.init / invT / invTt / invA / invAt ---------------- */
+/* In: Tm = K_MM (M x M, pitch M).  Out: Tm = T (upper, K_MM + eps*M*I = T^T T, strict lower
+ * zeroed), Am = A (upper, T T^T / M + lam*I = A^T A).  cuSOLVER potrf + cuBLAS syrk.
+ * SYNCHRONOUS (reads the factorisation status); ODF_ERR_LINALG if a pivot fails.               */
+int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void* ws,
+                     size_t ws_bytes, void* stream);
+/* B [M x T] (pitch ldb) <- op(Tri)^-1 B with Tri upper triangular (pitch M), op by `which`.   */
+int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t ldb, int which,
+                      void* stream);
+
+/* ---- conjugate-gradient vector kernels on M x T blocks (per-column scalars) ------------------ */
+/* FalkonConjugateGradient / ConjugateGradient.solve.  `state` is a device
+ * array of 4*T+4 floats owned by the caller: rs_old[T], a[T], b[T], rs_new[T], then flags:
+ * state[4T] = 1.0 once converged (every later update becomes a no-op, which freezes the
+ * iterate exactly where the reference's `break` leaves it).                                    */
+int odf_cg_init(const float* R, int64_t M, int64_t T, int64_t ld, float* state, void* ws,
+                size_t ws_bytes, void* stream);           /* rs_old = colsum(R^2), flag = 0      */
+int odf_cg_alpha(const float* P, const float* AP, int64_t M, int64_t T, int64_t ld, float eps,
+                 float* state, void* ws, size_t ws_bytes, void* stream); /* a = rs_old/(P.AP+eps)*/
+/* Y[:, t] += sign * a[t] * X[:, t]  with a = state[T..2T) */
+int odf_cg_axpy_a(float* Y, const float* X, int64_t M, int64_t T, int64_t ld, float sign,
+                  const float* state, void* stream);
+/* R = Bm - H   (full-gradient restart), skipped when converged */
+int odf_cg_residual(float* R, const float* Bm, const float* H, int64_t M, int64_t T, int64_t ld,
+                    const float* state, void* stream);
+/* rs_new = colsum(R^2); converged |= sqrt(max rs_new) < tol; b = rs_new/(rs_old+eps);
+ * rs_old = rs_new */
+int odf_cg_beta(const float* R, int64_t M, int64_t T, int64_t ld, float eps, float tol,
+                float* state, void* ws, size_t ws_bytes, void* stream);
+/* P[:, t] = R[:, t] + b[t] * P[:, t] */
+int odf_cg_xpby_b(float* P, const float* R, int64_t M, int64_t T, int64_t ld, const float* state,
+                  void* stream);
+/* out = alpha * A + beta * Bm (elementwise on M x T; A/Bm may alias out; Bm may be NULL) */
+int odf_axpby(float* out, float alpha, const float* A, float beta, const float* Bm, int64_t M,
+              int64_t T, int64_t ld, void* stream);
+size_t odf_cg_workspace_bytes(int64_t M, int64_t T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODF_H_ */

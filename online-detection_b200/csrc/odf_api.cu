@@ -1,0 +1,347 @@
+// extern "C" surface of libodf (declared in include/odf.h) + the cuSOLVER/cuBLAS-backed
+// preconditioner.  Everything here is thin: argument checks, workspace carving, launches.
+#include <cstring>
+#include <string>
+
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include "odf_internal.h"
+
+namespace odf {
+
+// ---- implemented in odf_vec.cu
+int prepare_points(const float*, int64_t, int64_t, int64_t, const float*, float, float*, float*, float*, cudaStream_t);
+int zscore(float*, int64_t, int64_t, int64_t, const float*, float, cudaStream_t);
+int split_rhs(const float*, int64_t, int64_t, int64_t, float, float*, float*, int64_t, int, cudaStream_t);
+int finish_rows(const float*, int, int64_t, int, int64_t, float, const float*, int64_t, float*, int64_t, cudaStream_t);
+int finish_split(const float*, int, int64_t, int, int64_t, float, const float*, int64_t, float*, float*, int64_t, cudaStream_t);
+size_t cg_workspace_bytes(int64_t, int64_t);
+int cg_init(const float*, int64_t, int64_t, int64_t, float*, void*, size_t, cudaStream_t);
+int cg_alpha(const float*, const float*, int64_t, int64_t, int64_t, float, float*, void*, size_t, cudaStream_t);
+int cg_beta(const float*, int64_t, int64_t, int64_t, float, float, float*, void*, size_t, cudaStream_t);
+int cg_axpy_a(float*, const float*, int64_t, int64_t, int64_t, float, const float*, cudaStream_t);
+int cg_xpby_b(float*, const float*, int64_t, int64_t, int64_t, const float*, cudaStream_t);
+int cg_residual(float*, const float*, const float*, int64_t, int64_t, int64_t, const float*, cudaStream_t);
+int axpby(float*, float, const float*, float, const float*, int64_t, int64_t, int64_t, cudaStream_t);
+int add_diag(float*, int64_t, float, cudaStream_t);
+int zero_lower(float*, int64_t, cudaStream_t);
+
+namespace {
+thread_local std::string g_err = "";
+}
+
+int set_error(int code, const char* msg) {
+  g_err = msg ? msg : "";
+  return code;
+}
+int set_cuda_error(cudaError_t e, const char* where) {
+  g_err = std::string(where ? where : "cuda") + ": " + cudaGetErrorString(e);
+  return ODF_ERR_CUDA;
+}
+
+namespace {
+
+// bump allocator over the caller's workspace (256-byte granules)
+struct Arena {
+  uint8_t* base;
+  size_t cap, off;
+  Arena(void* p, size_t n) : base(static_cast<uint8_t*>(p)), cap(n), off(0) {}
+  template <class T>
+  T* take(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) & ~static_cast<size_t>(255);
+    if (base == nullptr || off + bytes > cap) { off = cap + 1; return nullptr; }
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+inline size_t al(size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); }
+
+struct Prepared {
+  float *hi, *lo, *sqn;
+};
+size_t prepared_bytes(int64_t n, int64_t d) {
+  return 2 * al(sizeof(float) * n * round_up(d, 32)) + al(sizeof(float) * round_up(n, 128));
+}
+bool take_prepared(Arena& a, int64_t n, int64_t d, Prepared* p) {
+  p->hi = a.take<float>(n * round_up(d, 32));
+  p->lo = a.take<float>(n * round_up(d, 32));
+  p->sqn = a.take<float>(round_up(n, 128));
+  return a.ok();
+}
+
+int tpad_of(int64_t T) { return T <= 16 ? 16 : (T <= 32 ? 32 : -1); }
+
+cublasHandle_t g_cublas = nullptr;
+cusolverDnHandle_t g_cusolver = nullptr;
+int ensure_handles(cudaStream_t st) {
+  if (!g_cublas) {
+    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "cublasCreate failed");
+    // triangular solves / syrk of the preconditioner stay in true fp32
+    cublasSetMathMode(g_cublas, CUBLAS_DEFAULT_MATH);  // fp32 routines stay true fp32 (no TF32)
+  }
+  if (!g_cusolver) {
+    if (cusolverDnCreate(&g_cusolver) != CUSOLVER_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "cusolverDnCreate failed");
+  }
+  cublasSetStream(g_cublas, st);
+  cusolverDnSetStream(g_cusolver, st);
+  return ODF_OK;
+}
+
+}  // namespace
+}  // namespace odf
+
+using namespace odf;
+
+extern "C" {
+
+const char* odf_last_error(void) { return g_err.c_str(); }
+int odf_version(void) { return 100; }
+
+int64_t odf_pad_dim(int64_t d) { return round_up(d, 32); }
+int64_t odf_pad_rows(int64_t n) { return round_up(n, 128); }
+int odf_tpad(int64_t T) { return tpad_of(T); }
+int odf_tile_splits(int64_t n_rows, int64_t n_cols, int64_t d) {
+  return tile_default_splits(n_rows, n_cols, round_up(d, 32));
+}
+
+int odf_prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
+                       float* hi, float* lo, float* sqnorm, void* stream) {
+  return prepare_points(X, n, d, ldx, mean, scale, hi, lo, sqnorm, static_cast<cudaStream_t>(stream));
+}
+int odf_zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale, void* stream) {
+  return zscore(X, n, d, ldx, mean, scale, static_cast<cudaStream_t>(stream));
+}
+int odf_split_rhs(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, float* vt_hi, float* vt_lo,
+                  int64_t ldvt, int T_pad, void* stream) {
+  return split_rhs(V, m, T, ldv, scale, vt_hi, vt_lo, ldvt, T_pad, static_cast<cudaStream_t>(stream));
+}
+
+int odf_gauss_mmv_prepared(const float* r_hi, const float* r_lo, const float* r_sqnorm, int64_t n_rows,
+                           const float* q_hi, const float* q_lo, const float* q_sqnorm, int64_t n_cols,
+                           int64_t d_pad, const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad,
+                           int n_splits, float sigma, float* partial, void* stream) {
+  if (!(sigma > 0.f)) return set_error(ODF_ERR_ARG, "sigma must be positive");
+  TileLaunch L{};
+  L.r_hi = r_hi; L.r_lo = r_lo; L.r_norm = r_sqnorm; L.n_rows = n_rows;
+  L.q_hi = q_hi; L.q_lo = q_lo; L.q_norm = q_sqnorm; L.n_cols = n_cols;
+  L.d_pad = d_pad; L.vt_hi = vt_hi; L.vt_lo = vt_lo; L.ldvt = ldvt; L.T_pad = T_pad;
+  L.mode = MODE_MMV; L.n_splits = n_splits; L.sigma = sigma;
+  L.out = partial; L.ldo = T_pad; L.split_stride = n_rows * T_pad;
+  return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
+}
+
+int odf_finish_rows(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T, float scale,
+                    const float* addend, int64_t ld_add, float* out, int64_t ldo, void* stream) {
+  return finish_rows(partial, n_splits, n_rows, T_pad, T, scale, addend, ld_add, out, ldo, static_cast<cudaStream_t>(stream));
+}
+int odf_finish_split(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T, float scale,
+                     const float* addend, int64_t ld_add, float* wt_hi, float* wt_lo, int64_t ldwt, void* stream) {
+  return finish_split(partial, n_splits, n_rows, T_pad, T, scale, addend, ld_add, wt_hi, wt_lo, ldwt, static_cast<cudaStream_t>(stream));
+}
+
+int odf_gauss_kmm_prepared(const float* c_hi, const float* c_lo, const float* c_sqnorm, int64_t M, int64_t d_pad,
+                           float sigma, float* K, int64_t ldk, void* stream) {
+  if (!(sigma > 0.f)) return set_error(ODF_ERR_ARG, "sigma must be positive");
+  TileLaunch L{};
+  L.r_hi = c_hi; L.r_lo = c_lo; L.r_norm = c_sqnorm; L.n_rows = M;
+  L.q_hi = c_hi; L.q_lo = c_lo; L.q_norm = c_sqnorm; L.n_cols = M;
+  L.d_pad = d_pad; L.T_pad = 16; L.mode = MODE_STORE;
+  L.n_splits = tile_default_splits(M, M, d_pad); L.sigma = sigma;
+  L.out = K; L.ldo = ldk; L.split_stride = 0;
+  return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------- convenience (plain fp32 in)
+size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T) {
+  const int T_pad = tpad_of(T > 0 ? T : 1);
+  const int64_t dp = round_up(d, 32);
+  switch (op) {
+    case ODF_OP_MMV: {
+      const int S = tile_default_splits(n, M, dp);
+      return prepared_bytes(n, d) + prepared_bytes(M, d) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
+             al(sizeof(float) * S * n * T_pad);
+    }
+    case ODF_OP_DMMV: {
+      const int S1 = tile_default_splits(n, M, dp);
+      const int S2 = tile_default_splits(M, n, dp);
+      return prepared_bytes(n, d) + prepared_bytes(M, d) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
+             2 * al(sizeof(float) * T_pad * round_up(n, 128)) + al(sizeof(float) * S1 * n * T_pad) +
+             al(sizeof(float) * S2 * M * T_pad);
+    }
+    case ODF_OP_KMM:
+      return prepared_bytes(M, d);
+    case ODF_OP_PRECOND: {
+      // potrf scratch: query needs a handle + device; use a generous closed form instead
+      return al(sizeof(float) * (static_cast<size_t>(M) * 256 + (1u << 20))) + 256;
+    }
+    default:
+      return 0;
+  }
+}
+
+int odf_gauss_mmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_t M, int64_t ldc, int64_t d,
+                  const float* V, int64_t T, int64_t ldv, float sigma, float* out, int64_t ldo, void* ws,
+                  size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T_pad = tpad_of(T);
+  if (T_pad < 0) return set_error(ODF_ERR_ARG, "T must be <= 32 per call");
+  const int64_t dp = round_up(d, 32), ldvt = round_up(M, 128);
+  Arena a(ws, ws_bytes);
+  Prepared px, pc;
+  take_prepared(a, n, d, &px);
+  take_prepared(a, M, d, &pc);
+  float* vth = a.take<float>(T_pad * ldvt);
+  float* vtl = a.take<float>(T_pad * ldvt);
+  const int S = tile_default_splits(n, M, dp);
+  float* partial = a.take<float>(static_cast<size_t>(S) * n * T_pad);
+  if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_mmv: workspace too small");
+  int rc;
+  if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, px.hi, px.lo, px.sqn, st))) return rc;
+  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, pc.hi, pc.lo, pc.sqn, st))) return rc;
+  if ((rc = split_rhs(V, M, T, ldv, 1.f, vth, vtl, ldvt, T_pad, st))) return rc;
+  if ((rc = odf_gauss_mmv_prepared(px.hi, px.lo, px.sqn, n, pc.hi, pc.lo, pc.sqn, M, dp, vth, vtl, ldvt, T_pad, S,
+                                   sigma, partial, stream)))
+    return rc;
+  return finish_rows(partial, S, n, T_pad, T, 1.f, nullptr, 0, out, ldo, st);
+}
+
+int odf_gauss_dmmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_t M, int64_t ldc, int64_t d,
+                   const float* V, int64_t ldv, const float* W, int64_t ldw, int64_t T, float sigma, float* out,
+                   int64_t ldo, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T_pad = tpad_of(T);
+  if (T_pad < 0) return set_error(ODF_ERR_ARG, "T must be <= 32 per call");
+  if (!V && !W) return set_error(ODF_ERR_ARG, "dmmv needs V or W");
+  const int64_t dp = round_up(d, 32), ldvt = round_up(M, 128), ldwt = round_up(n, 128);
+  Arena a(ws, ws_bytes);
+  Prepared px, pc;
+  take_prepared(a, n, d, &px);
+  take_prepared(a, M, d, &pc);
+  float* vth = a.take<float>(T_pad * ldvt);
+  float* vtl = a.take<float>(T_pad * ldvt);
+  float* wth = a.take<float>(T_pad * ldwt);
+  float* wtl = a.take<float>(T_pad * ldwt);
+  const int S1 = tile_default_splits(n, M, dp);
+  const int S2 = tile_default_splits(M, n, dp);
+  float* part1 = a.take<float>(static_cast<size_t>(S1) * n * T_pad);
+  float* part2 = a.take<float>(static_cast<size_t>(S2) * M * T_pad);
+  if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_dmmv: workspace too small");
+  int rc;
+  if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, px.hi, px.lo, px.sqn, st))) return rc;
+  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, pc.hi, pc.lo, pc.sqn, st))) return rc;
+  if (V) {
+    if ((rc = split_rhs(V, M, T, ldv, 1.f, vth, vtl, ldvt, T_pad, st))) return rc;
+    if ((rc = odf_gauss_mmv_prepared(px.hi, px.lo, px.sqn, n, pc.hi, pc.lo, pc.sqn, M, dp, vth, vtl, ldvt, T_pad, S1,
+                                     sigma, part1, stream)))
+      return rc;
+    if ((rc = finish_split(part1, S1, n, T_pad, T, 1.f, W, ldw, wth, wtl, ldwt, st))) return rc;
+  } else {
+    if ((rc = split_rhs(W, n, T, ldw, 1.f, wth, wtl, ldwt, T_pad, st))) return rc;
+  }
+  if ((rc = odf_gauss_mmv_prepared(pc.hi, pc.lo, pc.sqn, M, px.hi, px.lo, px.sqn, n, dp, wth, wtl, ldwt, T_pad, S2,
+                                   sigma, part2, stream)))
+    return rc;
+  return finish_rows(part2, S2, M, T_pad, T, 1.f, nullptr, 0, out, ldo, st);
+}
+
+int odf_gauss_kmm(const float* C, int64_t M, int64_t ldc, int64_t d, float sigma, float* K, int64_t ldk, void* ws,
+                  size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(ws, ws_bytes);
+  Prepared pc;
+  if (!take_prepared(a, M, d, &pc)) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_kmm: workspace too small");
+  int rc;
+  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, pc.hi, pc.lo, pc.sqn, st))) return rc;
+  return odf_gauss_kmm_prepared(pc.hi, pc.lo, pc.sqn, M, round_up(d, 32), sigma, K, ldk, stream);
+}
+
+// ---------------------------------------------------------------- preconditioner
+// Row-major upper U  ==  column-major lower L = U^T, so cuSOLVER/cuBLAS run with uplo = LOWER.
+int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void* ws, size_t ws_bytes,
+                     void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= 0 || M > 0x7fffffff) return set_error(ODF_ERR_ARG, "precond_init: bad M");
+  int rc;
+  if ((rc = ensure_handles(st))) return rc;
+  const int m = static_cast<int>(M);
+  int lwork = 0;
+  if (cusolverDnSpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_LOWER, m, Tm, m, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf_bufferSize failed");
+  Arena a(ws, ws_bytes);
+  int* info = a.take<int>(2);
+  float* work = a.take<float>(static_cast<size_t>(lwork));
+  if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "precond_init: workspace too small");
+
+  // T: K_MM + eps*M*I = L L^T
+  if ((rc = add_diag(Tm, M, eps * static_cast<float>(M), st))) return rc;
+  if (cusolverDnSpotrf(g_cusolver, CUBLAS_FILL_MODE_LOWER, m, Tm, m, work, lwork, info) != CUSOLVER_STATUS_SUCCESS)
+    return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf (T) failed to launch");
+  if ((rc = zero_lower(Tm, M, st))) return rc;  // row-major strict lower == the triangle potrf left untouched
+  // A: (1/M) T T^T + lam I = (1/M) L^T L + lam I
+  const float alpha = 1.f / static_cast<float>(M), beta = 0.f;
+  if (cublasSsyrk(g_cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, m, m, &alpha, Tm, m, &beta, Am, m) != CUBLAS_STATUS_SUCCESS)
+    return set_error(ODF_ERR_CUDA, "cublasSsyrk failed");
+  if ((rc = add_diag(Am, M, lam, st))) return rc;
+  if (cusolverDnSpotrf(g_cusolver, CUBLAS_FILL_MODE_LOWER, m, Am, m, work, lwork, info + 1) != CUSOLVER_STATUS_SUCCESS)
+    return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf (A) failed to launch");
+  if ((rc = zero_lower(Am, M, st))) return rc;
+  int hinfo[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_cuda_error(e, "precond_init");
+  if (hinfo[0] != 0 || hinfo[1] != 0) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "Cholesky failed: info(T)=%d info(A)=%d (matrix not positive definite)", hinfo[0], hinfo[1]);
+    return set_error(ODF_ERR_LINALG, buf);
+  }
+  return ODF_OK;
+}
+
+int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t ldb, int which, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = ensure_handles(st))) return rc;
+  if (which < 0 || which > 3) return set_error(ODF_ERR_ARG, "precond_solve: bad `which`");
+  // Row-major B (M x T) is column-major B' = B^T (T x M).  X = U^-1 B  <=>  X' L = B' (L = U^T col-major lower);
+  // X = U^-T B  <=>  X' L^T = B'.
+  const bool transposed = (which == ODF_SOLVE_TT || which == ODF_SOLVE_AT);
+  const float one = 1.f;
+  cublasStatus_t s = cublasStrsm(g_cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER,
+                                 transposed ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, static_cast<int>(T),
+                                 static_cast<int>(M), &one, Tri, static_cast<int>(M), B, static_cast<int>(ldb));
+  if (s != CUBLAS_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "cublasStrsm failed");
+  return ODF_OK;
+}
+
+// ---------------------------------------------------------------- CG vector kernels
+size_t odf_cg_workspace_bytes(int64_t M, int64_t T) { return cg_workspace_bytes(M, T); }
+int odf_cg_init(const float* R, int64_t M, int64_t T, int64_t ld, float* state, void* ws, size_t ws_bytes, void* stream) {
+  return cg_init(R, M, T, ld, state, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int odf_cg_alpha(const float* P, const float* AP, int64_t M, int64_t T, int64_t ld, float eps, float* state, void* ws,
+                 size_t ws_bytes, void* stream) {
+  return cg_alpha(P, AP, M, T, ld, eps, state, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int odf_cg_axpy_a(float* Y, const float* X, int64_t M, int64_t T, int64_t ld, float sign, const float* state, void* stream) {
+  return cg_axpy_a(Y, X, M, T, ld, sign, state, static_cast<cudaStream_t>(stream));
+}
+int odf_cg_residual(float* R, const float* Bm, const float* H, int64_t M, int64_t T, int64_t ld, const float* state,
+                    void* stream) {
+  return cg_residual(R, Bm, H, M, T, ld, state, static_cast<cudaStream_t>(stream));
+}
+int odf_cg_beta(const float* R, int64_t M, int64_t T, int64_t ld, float eps, float tol, float* state, void* ws,
+                size_t ws_bytes, void* stream) {
+  return cg_beta(R, M, T, ld, eps, tol, state, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int odf_cg_xpby_b(float* P, const float* R, int64_t M, int64_t T, int64_t ld, const float* state, void* stream) {
+  return cg_xpby_b(P, R, M, T, ld, state, static_cast<cudaStream_t>(stream));
+}
+int odf_axpby(float* out, float alpha, const float* A, float beta, const float* Bm, int64_t M, int64_t T, int64_t ld,
+              void* stream) {
+  return axpby(out, alpha, A, beta, Bm, M, T, ld, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

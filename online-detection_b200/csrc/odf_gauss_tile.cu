@@ -1,0 +1,501 @@
+// Fused Gaussian-kernel tile for sm_100a (tcgen05 + TMEM + TMA).
+//
+// One persistent, warp-specialised kernel evaluates tiles of
+//     K[r, q] = exp(-(|x_r|^2 + |c_q|^2 - 2 x_r.c_q) / (2 sigma^2))
+// for a block of 128 "row" points against a stream of 128-wide "column" point tiles and, without
+// ever writing K to memory, contracts each tile with a block of right-hand sides:
+//     W[r, :] += K[r, tile] . V[tile, :]
+// This is the operator behind every hot call of the reference path:
+//   * predict / minibootstrap scoring  falkon `GaussianKernel.mmv`  (reference call sites:
+//     src/modules/region-classifier/FALKONWrapper_with_centers_selection_incore.py:75-82,
+//     .../box_head/roi_box_predictors.py:136,158, .../mask_head/roi_mask_predictors.py:61,90,
+//     .../rpn/rpn.py:197,225)
+//   * the CG operator K_nm^T (K_nm V) of `GaussianKernel.dmmv` (via FALKONWrapper.train ->
+//     InCoreFalkon.fit, same file :58-68): first pass rows = data, columns = centres; second pass
+//     rows = centres, columns = data (the Gaussian kernel is symmetric, K(X,C)^T = K(C,X)).
+//   * K_MM for the preconditioner (store epilogue, MODE_STORE).
+//
+// x.c runs on the tensor cores as a 3xTF32 product: operands are pre-split (odf_vec.cu) into
+// hi = tf32(x), lo = tf32(x - hi) and the tile accumulates hi.hi + lo.hi + hi.lo in fp32 TMEM,
+// which restores fp32-grade distances.  The epilogue adds the norms, clamps at 0, applies exp2
+// and splits K the same way; K_hi overwrites the S accumulator in place and together with K_lo
+// feeds the second tensor-core contraction straight from TMEM (A operand in TMEM, V^T tiles
+// from shared memory), again as a 3xTF32 product.
+//
+// Warp roles (256 threads, 1 CTA / SM):
+//   warp 0  lane 0 : TMA producer for the operand pipeline (R_hi, R_lo, Q_hi, Q_lo k-blocks)
+//   warp 1  lane 0 : tcgen05.mma issuer (S tiles and the K.V contraction)
+//   warp 2         : TMEM allocator
+//   warp 3  lane 0 : TMA producer for the V^T tiles
+//   warps 4..7     : epilogue (one TMEM lane == one row per thread)
+#include "odf_ptx.cuh"
+#include "odf_internal.h"
+
+namespace odf {
+
+namespace {
+
+constexpr int BM = 128;                    // rows per tile (TMEM lanes)
+constexpr int BN = 128;                    // columns per tile
+constexpr int BK = 32;                     // fp32 elements per k-block (= one 128B swizzle atom)
+constexpr int NS = 3;                      // operand pipeline depth
+constexpr int TILE_BYTES = BM * BK * 4;    // 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // R_hi, R_lo, Q_hi, Q_lo
+constexpr int MAX_TPAD = 32;
+constexpr int V_ATOM_BYTES_MAX = MAX_TPAD * 128;         // one [T_pad x 32] box
+constexpr int V_BYTES = 2 * 4 * V_ATOM_BYTES_MAX;        // hi+lo, 4 atoms each
+constexpr int NUM_BARS = 2 * NS + 8;
+constexpr int SMEM_BYTES = NS * STAGE_BYTES + V_BYTES + NUM_BARS * 8 + 16 + 1024;
+
+// TMEM column map (512 columns allocated)
+constexpr uint32_t TM_S0 = 0;      // S / K_hi buffer 0
+constexpr uint32_t TM_S1 = 128;    // S / K_hi buffer 1
+constexpr uint32_t TM_PLO = 256;   // K_lo
+constexpr uint32_t TM_W = 384;     // W accumulator (T_pad columns)
+constexpr uint32_t TM_COLS = 512;
+
+struct WorkItem {
+  int row0;     // first row of the block
+  int jt0;      // first column tile
+  int jt1;      // one past the last column tile
+  int split;    // split index (selects the partial output slab)
+};
+
+__device__ __forceinline__ WorkItem decode_item(const TileParams& p, int idx) {
+  // Items are ordered so that CTAs running side by side share operand tiles in L2:
+  // groups of `group_rows` row blocks x all splits; inside a group split-major.
+  const int per_full = p.group_rows * p.n_splits;
+  const int n_full = p.n_rowblocks / p.group_rows;
+  int g = idx / per_full;
+  int rem, gsize;
+  if (g < n_full) {
+    rem = idx - g * per_full;
+    gsize = p.group_rows;
+  } else {
+    g = n_full;
+    rem = idx - n_full * per_full;
+    gsize = p.n_rowblocks - n_full * p.group_rows;
+  }
+  const int split = rem / gsize;
+  const int r = rem - split * gsize;
+  WorkItem w;
+  w.row0 = (g * p.group_rows + r) * BM;
+  w.split = split;
+  w.jt0 = split * p.tiles_per_split;
+  w.jt1 = min(w.jt0 + p.tiles_per_split, p.n_coltiles);
+  return w;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256, 1)
+gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
+                  const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                  const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+                  const TileParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* v_base = smem + NS * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_base + V_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // barrier indices
+  const int B_FULL = 0, B_EMPTY = NS, B_SFULL = 2 * NS, B_PREADY = 2 * NS + 2,
+            B_PVDONE = 2 * NS + 3, B_VFULL = 2 * NS + 4, B_VEMPTY = 2 * NS + 5,
+            B_WFULL = 2 * NS + 6, B_WEMPTY = 2 * NS + 7;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool mode_mmv = (p.mode == MODE_MMV);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmRh);
+    tma_prefetch_desc(&tmRl);
+    tma_prefetch_desc(&tmQh);
+    tma_prefetch_desc(&tmQl);
+    if (mode_mmv) {
+      tma_prefetch_desc(&tmVh);
+      tma_prefetch_desc(&tmVl);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(BAR(B_FULL + s), 1);
+      mbar_init(BAR(B_EMPTY + s), 1);
+    }
+    mbar_init(BAR(B_SFULL + 0), 1);
+    mbar_init(BAR(B_SFULL + 1), 1);
+    mbar_init(BAR(B_PREADY), 128);
+    mbar_init(BAR(B_PVDONE), 1);
+    mbar_init(BAR(B_VFULL), 1);
+    mbar_init(BAR(B_VEMPTY), 1);
+    mbar_init(BAR(B_WFULL), 1);
+    mbar_init(BAR(B_WEMPTY), 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), TM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = p.n_rowblocks * p.n_splits;
+  const int KB = p.kblocks;
+  const int T_pad = p.T_pad;
+
+  if (warp == 0 && lane == 0) {
+    // ======================= operand TMA producer =======================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem w = decode_item(p, it);
+      for (int j = w.jt0; j < w.jt1; ++j) {
+        const int col0 = j * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
+          const uint32_t full = BAR(B_FULL + stage);
+          const uint32_t dst = smem_u32(stage_base + stage * STAGE_BYTES);
+          mbar_arrive_expect_tx(full, STAGE_BYTES);
+          tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, kb * BK, w.row0);
+          tma_load_2d(dst + 1 * TILE_BYTES, &tmRl, full, kb * BK, w.row0);
+          tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, kb * BK, col0);
+          tma_load_2d(dst + 3 * TILE_BYTES, &tmQl, full, kb * BK, col0);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3 && lane == 0 && mode_mmv) {
+    // ======================= V^T tile TMA producer =======================
+    uint32_t n = 0;  // tile counter
+    const uint32_t atom_bytes = T_pad * 128;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem w = decode_item(p, it);
+      for (int j = w.jt0; j < w.jt1; ++j, ++n) {
+        mbar_wait(BAR(B_VEMPTY), (n & 1) ^ 1);
+        const uint32_t full = BAR(B_VFULL);
+        mbar_arrive_expect_tx(full, 8 * atom_bytes);
+        const uint32_t dst = smem_u32(v_base);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          tma_load_2d(dst + a * atom_bytes, &tmVh, full, j * BN + a * 32, 0);
+          tma_load_2d(dst + (4 + a) * atom_bytes, &tmVl, full, j * BN + a * 32, 0);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc_s = make_idesc_tf32(BM, BN);
+    const uint32_t idesc_pv = make_idesc_tf32(BM, T_pad);
+    const uint32_t atom_bytes = T_pad * 128;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t n = 0;         // tiles whose S-MMAs have been issued
+    uint32_t item_cnt = 0;  // items whose first PV has been issued
+    bool pend = false, pend_first = false, pend_last = false;
+
+    // second contraction (or, in MODE_STORE, just the hand-back of the S buffer) for tile n-1
+    auto finish_prev = [&](uint32_t tile) {
+      mbar_wait(BAR(B_PREADY), tile & 1);
+      if (mode_mmv) {
+        mbar_wait(BAR(B_VFULL), tile & 1);
+        if (pend_first) {
+          mbar_wait(BAR(B_WEMPTY), (item_cnt & 1) ^ 1);
+          ++item_cnt;
+        }
+        tc_fence_after();
+        const uint32_t t_hi = tmem_base + ((tile & 1) ? TM_S1 : TM_S0);
+        const uint32_t t_lo = tmem_base + TM_PLO;
+        const uint32_t t_w = tmem_base + TM_W;
+        const uint32_t vb = smem_u32(v_base);
+#pragma unroll
+        for (int ks = 0; ks < BN / 8; ++ks) {
+          const uint32_t off = (ks >> 2) * atom_bytes + (ks & 3) * 32;
+          const uint64_t b_hi = make_sdesc_sw128(vb + off);
+          const uint64_t b_lo = make_sdesc_sw128(vb + 4 * atom_bytes + off);
+          mma_tf32_ts(t_w, t_hi + ks * 8, b_hi, idesc_pv, (pend_first && ks == 0) ? 0u : 1u);
+          mma_tf32_ts(t_w, t_lo + ks * 8, b_hi, idesc_pv, 1u);
+          mma_tf32_ts(t_w, t_hi + ks * 8, b_lo, idesc_pv, 1u);
+        }
+        tc_commit(BAR(B_VEMPTY));
+        tc_commit(BAR(B_PVDONE));
+        if (pend_last) tc_commit(BAR(B_WFULL));
+      }
+    };
+
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem w = decode_item(p, it);
+      for (int j = w.jt0; j < w.jt1; ++j) {
+        const uint32_t t_s = tmem_base + ((n & 1) ? TM_S1 : TM_S0);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(BAR(B_FULL + stage), phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(stage_base + stage * STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t a_hi = make_sdesc_sw128(sb + 0 * TILE_BYTES + ks * 32);
+            const uint64_t a_lo = make_sdesc_sw128(sb + 1 * TILE_BYTES + ks * 32);
+            const uint64_t b_hi = make_sdesc_sw128(sb + 2 * TILE_BYTES + ks * 32);
+            const uint64_t b_lo = make_sdesc_sw128(sb + 3 * TILE_BYTES + ks * 32);
+            mma_tf32_ss(t_s, a_hi, b_hi, idesc_s, (kb | ks) ? 1u : 0u);
+            mma_tf32_ss(t_s, a_lo, b_hi, idesc_s, 1u);
+            mma_tf32_ss(t_s, a_hi, b_lo, idesc_s, 1u);
+          }
+          tc_commit(BAR(B_EMPTY + stage));
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(BAR(B_SFULL + (n & 1)));
+        if (pend) finish_prev(n - 1);
+        pend = true;
+        pend_first = (j == w.jt0);
+        pend_last = (j == w.jt1 - 1);
+        ++n;
+      }
+    }
+    if (pend) finish_prev(n - 1);
+  } else if (warp >= 4) {
+    // ======================= epilogue =======================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;          // row inside the block
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float nsl2 = p.neg_scale_log2;
+    uint32_t n = 0;
+    uint32_t item_cnt = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_cnt) {
+      const WorkItem w = decode_item(p, it);
+      const int grow = w.row0 + row;
+      const float rn = (grow < p.n_rows) ? __ldg(p.rnorm + grow) : 0.f;
+      for (int j = w.jt0; j < w.jt1; ++j, ++n) {
+        const uint32_t b = n & 1;
+        mbar_wait(BAR(B_SFULL + b), (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_s = tmem_base + lane_off + (b ? TM_S1 : TM_S0);
+        const uint32_t t_lo = tmem_base + lane_off + TM_PLO;
+        const int col0 = j * BN;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t s[32];
+          __syncwarp();
+          tmem_ld32(t_s + ch * 32, s);
+          float qn[32];
+          const float4* qp = reinterpret_cast<const float4*>(p.qnorm + col0 + ch * 32);
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const float4 t = __ldg(qp + v);
+            qn[4 * v + 0] = t.x; qn[4 * v + 1] = t.y; qn[4 * v + 2] = t.z; qn[4 * v + 3] = t.w;
+          }
+          tc_wait_ld();
+          if (mode_mmv) {
+            uint32_t lo[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float d2 = fmaf(-2.f, __uint_as_float(s[c]), rn + qn[c]);
+              d2 = fmaxf(d2, 0.f);
+              const float kv = ex2_approx(d2 * nsl2);
+              const float hi = tf32_rn(kv);
+              s[c] = __float_as_uint(hi);
+              lo[c] = __float_as_uint(tf32_rn(kv - hi));
+            }
+            if (ch == 0 && n > 0) mbar_wait(BAR(B_PVDONE), (n - 1) & 1);  // K_lo buffer free
+            tmem_st32(t_s + ch * 32, s);
+            tmem_st32(t_lo + ch * 32, lo);
+          } else {
+            // MODE_STORE: write K straight to global (row-major, ld = ldo)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float d2 = fmaf(-2.f, __uint_as_float(s[c]), rn + qn[c]);
+              d2 = fmaxf(d2, 0.f);
+              s[c] = __float_as_uint(ex2_approx(d2 * nsl2));
+            }
+            if (grow < p.n_rows) {
+              float* orow = p.out + static_cast<int64_t>(grow) * p.ldo;
+              const int c0 = col0 + ch * 32;
+              if (p.store_vec4 && c0 + 32 <= p.n_cols) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                  float4 t;
+                  t.x = __uint_as_float(s[4 * v + 0]); t.y = __uint_as_float(s[4 * v + 1]);
+                  t.z = __uint_as_float(s[4 * v + 2]); t.w = __uint_as_float(s[4 * v + 3]);
+                  *reinterpret_cast<float4*>(orow + c0 + 4 * v) = t;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c0 + c < p.n_cols) orow[c0 + c] = __uint_as_float(s[c]);
+              }
+            }
+          }
+        }
+        if (mode_mmv) tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(BAR(B_PREADY));
+      }
+      if (mode_mmv) {
+        // W for this item is complete once the last tile's contraction has retired.
+        mbar_wait(BAR(B_WFULL), item_cnt & 1);
+        tc_fence_after();
+        const uint32_t t_w = tmem_base + lane_off + TM_W;
+        float* orow = p.out + static_cast<int64_t>(w.split) * p.split_stride +
+                      static_cast<int64_t>(grow) * T_pad;
+        for (int c0 = 0; c0 < T_pad; c0 += 16) {
+          uint32_t r[16];
+          __syncwarp();
+          tmem_ld16(t_w + c0, r);
+          tc_wait_ld();
+          if (grow < p.n_rows) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              float4 t;
+              t.x = __uint_as_float(r[4 * v + 0]); t.y = __uint_as_float(r[4 * v + 1]);
+              t.z = __uint_as_float(r[4 * v + 2]); t.w = __uint_as_float(r[4 * v + 3]);
+              *reinterpret_cast<float4*>(orow + c0 + 4 * v) = t;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(B_WEMPTY));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TM_COLS);
+}
+
+// ----------------------------------------------------------------------------- host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// 2-D fp32 tensor [rows x cols] with row pitch ld (elements); box = [box_rows x 32], 128B swizzle.
+int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld,
+             int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld",
+             static_cast<int>(r), (long long)rows, (long long)cols, (long long)ld);
+    return set_error(ODF_ERR_CUDA, buf);
+  }
+  return ODF_OK;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace
+
+int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t d_pad) {
+  const int sms = num_sms();
+  const int64_t n_rb = (n_rows + BM - 1) / BM;
+  const int64_t n_ct = (n_cols + BN - 1) / BN;
+  int64_t splits = 1;
+  // (a) not enough row blocks to fill the machine a few times over: split the column range
+  if (n_rb < 8 * sms) splits = (8 * sms + n_rb - 1) / n_rb;
+  // (b) row blocks too fat for L2 when every SM streams its own: make ~12 CTAs share one
+  const int64_t rb_bytes = static_cast<int64_t>(BM) * d_pad * 8;
+  if (rb_bytes * sms > (48ll << 20) && splits < 12) splits = 12;
+  // keep at least 4 column tiles per item so the pipeline fill/drain stays amortised
+  const int64_t max_splits = n_ct >= 4 ? n_ct / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  // normalise so that no split is empty (the launcher insists on it)
+  const int64_t tps = (n_ct + splits - 1) / splits;
+  splits = (n_ct + tps - 1) / tps;
+  return static_cast<int>(splits);
+}
+
+int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
+  if (L.d_pad % BK != 0 || L.d_pad <= 0) return set_error(ODF_ERR_ARG, "d_pad must be a positive multiple of 32");
+  if (L.n_rows <= 0 || L.n_cols <= 0) return set_error(ODF_ERR_ARG, "empty operand");
+  if (L.mode == MODE_MMV && !(L.T_pad == 16 || L.T_pad == 32))
+    return set_error(ODF_ERR_ARG, "T_pad must be 16 or 32");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gauss_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gauss_tile_kernel)");
+    attr_set = true;
+  }
+  CUtensorMap mRh, mRl, mQh, mQl, mVh, mVl;
+  int rc;
+  if ((rc = make_map(&mRh, L.r_hi, L.n_rows, L.d_pad, L.d_pad, BM))) return rc;
+  if ((rc = make_map(&mRl, L.r_lo, L.n_rows, L.d_pad, L.d_pad, BM))) return rc;
+  if ((rc = make_map(&mQh, L.q_hi, L.n_cols, L.d_pad, L.d_pad, BN))) return rc;
+  if ((rc = make_map(&mQl, L.q_lo, L.n_cols, L.d_pad, L.d_pad, BN))) return rc;
+  if (L.mode == MODE_MMV) {
+    if ((rc = make_map(&mVh, L.vt_hi, L.T_pad, L.ldvt, L.ldvt, L.T_pad))) return rc;
+    if ((rc = make_map(&mVl, L.vt_lo, L.T_pad, L.ldvt, L.ldvt, L.T_pad))) return rc;
+  } else {
+    mVh = mRh;
+    mVl = mRl;
+  }
+  TileParams p;
+  p.n_rows = static_cast<int>(L.n_rows);
+  p.n_cols = static_cast<int>(L.n_cols);
+  p.kblocks = static_cast<int>(L.d_pad / BK);
+  p.T_pad = L.T_pad;
+  p.mode = L.mode;
+  p.n_rowblocks = static_cast<int>((L.n_rows + BM - 1) / BM);
+  p.n_coltiles = static_cast<int>((L.n_cols + BN - 1) / BN);
+  int splits = L.n_splits > 0 ? L.n_splits : 1;
+  if (splits > p.n_coltiles) splits = p.n_coltiles;
+  p.tiles_per_split = (p.n_coltiles + splits - 1) / splits;
+  p.n_splits = (p.n_coltiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  if (L.mode == MODE_MMV && p.n_splits != L.n_splits)
+    return set_error(ODF_ERR_ARG, "n_splits must divide the column tiles without empty splits (use odf_tile_splits)");
+  const int sms = num_sms();
+  p.group_rows = sms / p.n_splits;
+  if (p.group_rows < 1) p.group_rows = 1;
+  p.neg_scale_log2 = static_cast<float>(-1.4426950408889634 / (2.0 * double(L.sigma) * double(L.sigma)));
+  p.rnorm = L.r_norm;
+  p.qnorm = L.q_norm;
+  p.out = L.out;
+  p.ldo = L.ldo;
+  p.split_stride = L.split_stride;
+  p.store_vec4 = (L.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) ? 1 : 0;
+  const int n_items = p.n_rowblocks * p.n_splits;
+  const int grid = n_items < sms ? n_items : sms;
+  gauss_tile_kernel<<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "gauss_tile_kernel launch");
+  return ODF_OK;
+}
+
+}  // namespace odf

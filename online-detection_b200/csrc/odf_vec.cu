@@ -1,0 +1,451 @@
+// HBM-bound helper kernels around the fused Gaussian tile: operand preparation (z-score +
+// 3xTF32 split + norms), right-hand-side split/transposition, split-slab reduction and the
+// per-column conjugate-gradient vector updates.  All are coalesced, vectorised where the layout
+// allows it and reduction-order deterministic (no floating-point atomics).
+#include "odf_ptx.cuh"
+#include "odf_internal.h"
+
+namespace odf {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ prepare_points
+// One warp per row.  Reads X once (4 B/elem), writes hi and lo (8 B/elem) and one norm.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+prepare_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx,
+               const float* __restrict__ mean, float scale, float* __restrict__ hi,
+               float* __restrict__ lo, int d_pad, float* __restrict__ sqn, int64_t n_pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  if (row >= n) {
+    if (lane == 0) sqn[row] = 0.f;
+    return;
+  }
+  const float* xr = X + row * ldx;
+  float* hr = hi + row * d_pad;
+  float* lr = lo + row * d_pad;
+  double acc = 0.0;
+  for (int c = lane * 4; c < d_pad; c += 128) {
+    float v[4];
+    if (VEC && c + 3 < d) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (c + k < d) ? __ldg(xr + c + k) : 0.f;
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x = v[k];
+      if (c + k < d) {
+        if (mean) x -= __ldg(mean + c + k);
+        x *= scale;
+      } else {
+        x = 0.f;
+      }
+      h[k] = tf32_rn(x);
+      l[k] = tf32_rn(x - h[k]);
+      acc += static_cast<double>(x) * static_cast<double>(x);
+    }
+    *reinterpret_cast<float4*>(hr + c) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lr + c) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) sqn[row] = static_cast<float>(acc);
+}
+
+__global__ void __launch_bounds__(256)
+zscore_kernel(float* __restrict__ X, int64_t n, int d, int64_t ldx, const float* __restrict__ mean,
+              float scale) {
+  const int64_t total = n * static_cast<int64_t>(d);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = static_cast<int>(i - r * d);
+    float x = X[r * ldx + c];
+    if (mean) x -= __ldg(mean + c);
+    X[r * ldx + c] = x * scale;
+  }
+}
+
+// ------------------------------------------------------------------ split_rhs
+// V [m x T] -> vt_hi/vt_lo [T_pad x ldvt]; one block per 128 rows of V, transposed through smem.
+__global__ void __launch_bounds__(128)
+split_rhs_kernel(const float* __restrict__ V, int64_t m, int T, int64_t ldv, float scale,
+                 float* __restrict__ vt_hi, float* __restrict__ vt_lo, int64_t ldvt, int T_pad) {
+  __shared__ float tile[32][129];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 128;
+  // coalesced-ish load: consecutive threads walk along a row of V
+  for (int idx = threadIdx.x; idx < 128 * T_pad; idx += 128) {
+    const int r = idx / T_pad, t = idx - r * T_pad;
+    float v = 0.f;
+    if (t < T && r0 + r < m) v = __ldg(V + (r0 + r) * ldv + t) * scale;
+    tile[t][r] = v;
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r0 + r < ldvt) {
+    for (int t = 0; t < T_pad; ++t) {
+      const float v = tile[t][r];
+      const float h = tf32_rn(v);
+      vt_hi[t * ldvt + r0 + r] = h;
+      vt_lo[t * ldvt + r0 + r] = tf32_rn(v - h);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ finish (split-slab reduce)
+// partial [S][n][T_pad] -> out[n x T]: each thread owns one row (a full 64/128-byte line per
+// slab), sums the slabs in index order.
+__global__ void __launch_bounds__(128)
+finish_rows_kernel(const float* __restrict__ partial, int S, int64_t n, int T_pad, int T,
+                   float scale, const float* __restrict__ addend, int64_t ld_add,
+                   float* __restrict__ out, int64_t ldo) {
+  __shared__ float tile[128][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 128;
+  const int64_t r = r0 + threadIdx.x;
+  float acc[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) acc[t] = 0.f;
+  if (r < n) {
+    for (int s = 0; s < S; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(partial + (static_cast<int64_t>(s) * n + r) * T_pad);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        if (4 * v < T_pad) {
+          const float4 t4 = __ldg(src + v);
+          acc[4 * v + 0] += t4.x; acc[4 * v + 1] += t4.y; acc[4 * v + 2] += t4.z; acc[4 * v + 3] += t4.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 32; ++t) tile[threadIdx.x][t] = acc[t] * scale;
+  __syncthreads();
+  // coalesced store along rows of out
+  for (int idx = threadIdx.x; idx < 128 * T; idx += 128) {
+    const int rr = idx / T, t = idx - rr * T;
+    if (r0 + rr < n) {
+      float v = tile[rr][t];
+      if (addend) v += __ldg(addend + (r0 + rr) * ld_add + t);
+      out[(r0 + rr) * ldo + t] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+finish_split_kernel(const float* __restrict__ partial, int S, int64_t n, int T_pad, int T,
+                    float scale, const float* __restrict__ addend, int64_t ld_add,
+                    float* __restrict__ wt_hi, float* __restrict__ wt_lo, int64_t ldwt) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
+  if (r >= ldwt) return;
+  float acc[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) acc[t] = 0.f;
+  if (r < n) {
+    for (int s = 0; s < S; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(partial + (static_cast<int64_t>(s) * n + r) * T_pad);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        if (4 * v < T_pad) {
+          const float4 t4 = __ldg(src + v);
+          acc[4 * v + 0] += t4.x; acc[4 * v + 1] += t4.y; acc[4 * v + 2] += t4.z; acc[4 * v + 3] += t4.w;
+        }
+      }
+    }
+  }
+  // consecutive threads -> consecutive columns of the transposed output: coalesced
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    if (t < T_pad) {
+      float v = 0.f;
+      if (r < n && t < T) {
+        v = acc[t] * scale;
+        if (addend) v += __ldg(addend + r * ld_add + t);
+      }
+      const float h = tf32_rn(v);
+      wt_hi[t * ldwt + r] = h;
+      wt_lo[t * ldwt + r] = tf32_rn(v - h);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CG column reductions
+// Block (32 x 8): x walks the columns of a row (coalesced), y/blocks walk the rows.
+// Stage 1 writes one double per (block, column); stage 2 sums the blocks in index order and
+// applies the scalar recurrence.  Deterministic.
+constexpr int RED_BLOCKS = 64;
+
+template <int OP>  // 0: sum A*A   1: sum A*B
+__global__ void __launch_bounds__(256)
+colreduce_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t M, int T,
+                 int64_t ld, double* __restrict__ part) {
+  __shared__ double sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + tx;
+    double acc = 0.0;
+    if (t < T) {
+      for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + ty; r < M; r += static_cast<int64_t>(gridDim.x) * 8) {
+        const float a = __ldg(A + r * ld + t);
+        const float b = OP == 0 ? a : __ldg(B + r * ld + t);
+        acc += static_cast<double>(a) * static_cast<double>(b);
+      }
+    }
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && t < T) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += sm[k][tx];
+      part[static_cast<int64_t>(blockIdx.x) * T + t] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// state layout: rs_old[T] | a[T] | b[T] | rs_new[T] | flag, pad[3]
+__global__ void cg_init_final(const double* __restrict__ part, int nb, int T, float* state) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) {
+    double s = 0.0;
+    for (int k = 0; k < nb; ++k) s += part[static_cast<int64_t>(k) * T + t];
+    state[t] = static_cast<float>(s);
+    state[T + t] = 0.f;
+    state[2 * T + t] = 0.f;
+    state[3 * T + t] = static_cast<float>(s);
+  }
+  if (t == 0) {
+    state[4 * T] = 0.f; state[4 * T + 1] = 0.f; state[4 * T + 2] = 0.f; state[4 * T + 3] = 0.f;
+  }
+}
+
+__global__ void cg_alpha_final(const double* __restrict__ part, int nb, int T, float eps, float* state) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) {
+    double s = 0.0;
+    for (int k = 0; k < nb; ++k) s += part[static_cast<int64_t>(k) * T + t];
+    const bool frozen = state[4 * T] != 0.f;
+    const float pap = static_cast<float>(s);
+    state[T + t] = frozen ? 0.f : state[t] / (pap + eps);
+  }
+}
+
+// Single block: needs the max over columns before any column may update.
+__global__ void cg_beta_final(const double* __restrict__ part, int nb, int T, float eps, float tol,
+                              float* state) {
+  __shared__ float smax[32];
+  const bool frozen = state[4 * T] != 0.f;
+  float mymax = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < nb; ++k) s += part[static_cast<int64_t>(k) * T + t];
+    const float rs_new = static_cast<float>(s);
+    if (!frozen) state[3 * T + t] = rs_new;
+    mymax = fmaxf(mymax, fabsf(rs_new));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mymax = fmaxf(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mymax;
+  __syncthreads();
+  float m = 0.f;
+  for (int k = 0; k < (blockDim.x >> 5); ++k) m = fmaxf(m, smax[k]);
+  const bool conv = sqrtf(m) < tol;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    if (frozen || conv) {
+      state[2 * T + t] = 0.f;
+    } else {
+      const float rs_new = state[3 * T + t];
+      state[2 * T + t] = rs_new / (state[t] + eps);
+      state[t] = rs_new;
+    }
+  }
+  if (threadIdx.x == 0 && conv && !frozen) state[4 * T] = 1.f;
+}
+
+// ------------------------------------------------------------------ CG elementwise updates
+// mode 0: Y += sign * s[t] * X      (s = state + T: a)
+// mode 1: Y  = X + s[t] * Y         (s = state + 2T: b)         [P = R + b P]
+// mode 2: Y  = X - Z (unless frozen)                              [R = B - H]
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cg_elem_kernel(float* __restrict__ Y, const float* __restrict__ X, const float* __restrict__ Z,
+               int64_t M, int T, int64_t ld, float sign, const float* __restrict__ state) {
+  const bool frozen = state[4 * T] != 0.f;
+  if (frozen) return;
+  const int64_t total = M * static_cast<int64_t>(T);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / T;
+    const int t = static_cast<int>(i - r * T);
+    const int64_t o = r * ld + t;
+    if (MODE == 0) {
+      Y[o] = fmaf(sign * __ldg(state + T + t), __ldg(X + o), Y[o]);
+    } else if (MODE == 1) {
+      Y[o] = fmaf(__ldg(state + 2 * T + t), Y[o], __ldg(X + o));
+    } else {
+      Y[o] = __ldg(X + o) - __ldg(Z + o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+axpby_kernel(float* __restrict__ out, float alpha, const float* __restrict__ A, float beta,
+             const float* __restrict__ Bm, int64_t M, int T, int64_t ld) {
+  const int64_t total = M * static_cast<int64_t>(T);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / T;
+    const int64_t o = r * ld + (i - r * T);
+    float v = alpha * A[o];
+    if (Bm) v = fmaf(beta, Bm[o], v);
+    out[o] = v;
+  }
+}
+
+// ------------------------------------------------------------------ preconditioner helpers
+__global__ void add_diag_kernel(float* __restrict__ A, int64_t M, float v) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < M) A[i * M + i] += v;
+}
+// Zero the strict lower triangle in row-major terms (== strict upper in cuBLAS column-major terms).
+__global__ void __launch_bounds__(256)
+zero_lower_kernel(float* __restrict__ A, int64_t M) {
+  const int64_t r = blockIdx.y;
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < r;
+       c += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    A[r * M + c] = 0.f;
+}
+
+int grid_for(int64_t total, int block, int cap = 148 * 8) {
+  int64_t g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, what);
+  return ODF_OK;
+}
+
+}  // namespace
+
+// ---- internal C++ entry points used by odf_api.cu ------------------------------------------
+int prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
+                   float* hi, float* lo, float* sqn, cudaStream_t st) {
+  if (n <= 0 || d <= 0 || ldx < d) return set_error(ODF_ERR_ARG, "prepare_points: bad shape");
+  const int64_t n_pad = round_up(n, 128);
+  const int d_pad = static_cast<int>(round_up(d, 32));
+  const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const unsigned grid = static_cast<unsigned>((n_pad + 7) / 8);
+  if (vec)
+    prepare_kernel<true><<<grid, 256, 0, st>>>(X, n, static_cast<int>(d), ldx, mean, scale, hi, lo, d_pad, sqn, n_pad);
+  else
+    prepare_kernel<false><<<grid, 256, 0, st>>>(X, n, static_cast<int>(d), ldx, mean, scale, hi, lo, d_pad, sqn, n_pad);
+  return check_launch("prepare_kernel");
+}
+
+int zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale, cudaStream_t st) {
+  if (n <= 0 || d <= 0) return set_error(ODF_ERR_ARG, "zscore: bad shape");
+  zscore_kernel<<<grid_for(n * d, 256), 256, 0, st>>>(X, n, static_cast<int>(d), ldx, mean, scale);
+  return check_launch("zscore_kernel");
+}
+
+int split_rhs(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, float* vt_hi,
+              float* vt_lo, int64_t ldvt, int T_pad, cudaStream_t st) {
+  if (m <= 0 || T <= 0 || T > T_pad || T_pad > 32 || ldvt < m || ldvt % 128 != 0)
+    return set_error(ODF_ERR_ARG, "split_rhs: bad shape");
+  split_rhs_kernel<<<static_cast<unsigned>(ldvt / 128), 128, 0, st>>>(V, m, static_cast<int>(T), ldv, scale, vt_hi, vt_lo, ldvt, T_pad);
+  return check_launch("split_rhs_kernel");
+}
+
+int finish_rows(const float* partial, int S, int64_t n, int T_pad, int64_t T, float scale,
+                const float* addend, int64_t ld_add, float* out, int64_t ldo, cudaStream_t st) {
+  if (S <= 0 || n <= 0 || T <= 0 || T > T_pad || T_pad > 32) return set_error(ODF_ERR_ARG, "finish_rows: bad shape");
+  finish_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(partial, S, n, T_pad, static_cast<int>(T), scale, addend, ld_add, out, ldo);
+  return check_launch("finish_rows_kernel");
+}
+
+int finish_split(const float* partial, int S, int64_t n, int T_pad, int64_t T, float scale,
+                 const float* addend, int64_t ld_add, float* wt_hi, float* wt_lo, int64_t ldwt,
+                 cudaStream_t st) {
+  if (S <= 0 || n <= 0 || T <= 0 || T > T_pad || T_pad > 32 || ldwt < n || ldwt % 128 != 0)
+    return set_error(ODF_ERR_ARG, "finish_split: bad shape");
+  finish_split_kernel<<<static_cast<unsigned>(ldwt / 128), 128, 0, st>>>(partial, S, n, T_pad, static_cast<int>(T), scale, addend, ld_add, wt_hi, wt_lo, ldwt);
+  return check_launch("finish_split_kernel");
+}
+
+size_t cg_workspace_bytes(int64_t /*M*/, int64_t T) { return sizeof(double) * RED_BLOCKS * static_cast<size_t>(T); }
+
+static int red_blocks(int64_t M) {
+  int64_t b = (M + 7) / 8;
+  if (b > RED_BLOCKS) b = RED_BLOCKS;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+int cg_init(const float* R, int64_t M, int64_t T, int64_t ld, float* state, void* ws, size_t wsb, cudaStream_t st) {
+  if (wsb < cg_workspace_bytes(M, T)) return set_error(ODF_ERR_WORKSPACE, "cg_init: workspace too small");
+  const int nb = red_blocks(M);
+  colreduce_kernel<0><<<nb, 256, 0, st>>>(R, nullptr, M, static_cast<int>(T), ld, static_cast<double*>(ws));
+  cg_init_final<<<static_cast<unsigned>((T + 127) / 128), 128, 0, st>>>(static_cast<double*>(ws), nb, static_cast<int>(T), state);
+  return check_launch("cg_init");
+}
+
+int cg_alpha(const float* P, const float* AP, int64_t M, int64_t T, int64_t ld, float eps, float* state,
+             void* ws, size_t wsb, cudaStream_t st) {
+  if (wsb < cg_workspace_bytes(M, T)) return set_error(ODF_ERR_WORKSPACE, "cg_alpha: workspace too small");
+  const int nb = red_blocks(M);
+  colreduce_kernel<1><<<nb, 256, 0, st>>>(P, AP, M, static_cast<int>(T), ld, static_cast<double*>(ws));
+  cg_alpha_final<<<static_cast<unsigned>((T + 127) / 128), 128, 0, st>>>(static_cast<double*>(ws), nb, static_cast<int>(T), eps, state);
+  return check_launch("cg_alpha");
+}
+
+int cg_beta(const float* R, int64_t M, int64_t T, int64_t ld, float eps, float tol, float* state,
+            void* ws, size_t wsb, cudaStream_t st) {
+  if (wsb < cg_workspace_bytes(M, T)) return set_error(ODF_ERR_WORKSPACE, "cg_beta: workspace too small");
+  const int nb = red_blocks(M);
+  colreduce_kernel<0><<<nb, 256, 0, st>>>(R, nullptr, M, static_cast<int>(T), ld, static_cast<double*>(ws));
+  cg_beta_final<<<1, 128, 0, st>>>(static_cast<double*>(ws), nb, static_cast<int>(T), eps, tol, state);
+  return check_launch("cg_beta");
+}
+
+int cg_axpy_a(float* Y, const float* X, int64_t M, int64_t T, int64_t ld, float sign, const float* state, cudaStream_t st) {
+  cg_elem_kernel<0><<<grid_for(M * T, 256), 256, 0, st>>>(Y, X, nullptr, M, static_cast<int>(T), ld, sign, state);
+  return check_launch("cg_axpy_a");
+}
+int cg_xpby_b(float* P, const float* R, int64_t M, int64_t T, int64_t ld, const float* state, cudaStream_t st) {
+  cg_elem_kernel<1><<<grid_for(M * T, 256), 256, 0, st>>>(P, R, nullptr, M, static_cast<int>(T), ld, 1.f, state);
+  return check_launch("cg_xpby_b");
+}
+int cg_residual(float* R, const float* Bm, const float* H, int64_t M, int64_t T, int64_t ld, const float* state, cudaStream_t st) {
+  cg_elem_kernel<2><<<grid_for(M * T, 256), 256, 0, st>>>(R, Bm, H, M, static_cast<int>(T), ld, 1.f, state);
+  return check_launch("cg_residual");
+}
+int axpby(float* out, float alpha, const float* A, float beta, const float* Bm, int64_t M, int64_t T, int64_t ld, cudaStream_t st) {
+  axpby_kernel<<<grid_for(M * T, 256), 256, 0, st>>>(out, alpha, A, beta, Bm, M, static_cast<int>(T), ld);
+  return check_launch("axpby");
+}
+int add_diag(float* A, int64_t M, float v, cudaStream_t st) {
+  add_diag_kernel<<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(A, M, v);
+  return check_launch("add_diag");
+}
+int zero_lower(float* A, int64_t M, cudaStream_t st) {
+  dim3 grid(8, static_cast<unsigned>(M));
+  zero_lower_kernel<<<grid, 256, 0, st>>>(A, M);
+  return check_launch("zero_lower");
+}
+
+}  // namespace odf

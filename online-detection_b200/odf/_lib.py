@@ -1,0 +1,87 @@
+"""ctypes binding of libodf.so (include/odf.h).  The CUDA extension is mandatory: if the shared
+object is missing or a call fails, this module raises — there is no eager/PyTorch fallback."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libodf.so")
+
+c_fp = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f = ctypes.c_float
+c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/odf.h declaration by declaration
+SIGNATURES = {
+    "odf_last_error": (ctypes.c_char_p, []),
+    "odf_version": (c_int, []),
+    "odf_pad_dim": (c_i64, [c_i64]),
+    "odf_pad_rows": (c_i64, [c_i64]),
+    "odf_tpad": (c_int, [c_i64]),
+    "odf_tile_splits": (c_int, [c_i64, c_i64, c_i64]),
+    "odf_prepare_points": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_f, c_fp, c_fp, c_fp, c_fp]),
+    "odf_zscore": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_f, c_fp]),
+    "odf_split_rhs": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_i64, c_int, c_fp]),
+    "odf_gauss_mmv_prepared": (c_int, [c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_i64, c_i64,
+                                       c_fp, c_fp, c_i64, c_int, c_int, c_f, c_fp, c_fp]),
+    "odf_finish_rows": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_i64, c_fp]),
+    "odf_finish_split": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_fp,
+                                 c_i64, c_fp]),
+    "odf_gauss_kmm_prepared": (c_int, [c_fp, c_fp, c_fp, c_i64, c_i64, c_f, c_fp, c_i64, c_fp]),
+    "odf_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_i64, c_i64]),
+    "odf_gauss_mmv": (c_int, [c_fp, c_i64, c_i64, c_fp, c_i64, c_i64, c_i64, c_fp, c_i64, c_i64, c_f,
+                              c_fp, c_i64, c_fp, c_sz, c_fp]),
+    "odf_gauss_dmmv": (c_int, [c_fp, c_i64, c_i64, c_fp, c_i64, c_i64, c_i64, c_fp, c_i64, c_fp, c_i64,
+                               c_i64, c_f, c_fp, c_i64, c_fp, c_sz, c_fp]),
+    "odf_gauss_kmm": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_i64, c_fp, c_sz, c_fp]),
+    "odf_precond_init": (c_int, [c_fp, c_fp, c_i64, c_f, c_f, c_fp, c_sz, c_fp]),
+    "odf_precond_solve": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_fp]),
+    "odf_cg_init": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_sz, c_fp]),
+    "odf_cg_alpha": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_sz, c_fp]),
+    "odf_cg_axpy_a": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp]),
+    "odf_cg_residual": (c_int, [c_fp, c_fp, c_fp, c_i64, c_i64, c_i64, c_fp, c_fp]),
+    "odf_cg_beta": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_f, c_fp, c_fp, c_sz, c_fp]),
+    "odf_cg_xpby_b": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_fp, c_fp]),
+    "odf_axpby": (c_int, [c_fp, c_f, c_fp, c_f, c_fp, c_i64, c_i64, c_i64, c_fp]),
+    "odf_cg_workspace_bytes": (c_sz, [c_i64, c_i64]),
+}
+
+ODF_OP_MMV, ODF_OP_DMMV, ODF_OP_KMM, ODF_OP_PRECOND = 0, 1, 2, 3
+ODF_SOLVE_T, ODF_SOLVE_TT, ODF_SOLVE_A, ODF_SOLVE_AT = 0, 1, 2, 3
+
+
+class OdfError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libodf.so (once).  Raises OdfError when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OdfError(
+            "libodf.so not found at %s — build it with `python online-detection_b200/build_lib.py` "
+            "(there is no CPU/PyTorch fallback for the FALKON hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().odf_last_error()
+        raise OdfError("%s failed (%d): %s" % (what or "libodf call", rc, (msg or b"").decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

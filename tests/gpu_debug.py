@@ -1,0 +1,228 @@
+"""Bring-up script for the GPU box: runs each check in its own process (a device-side trap kills
+the CUDA context) and prints compact PASS/FAIL lines.  Not collected by pytest.
+
+    python tests/gpu_debug.py            # all stages
+    python tests/gpu_debug.py kmm mmv    # selected stages
+"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "online-detection_b200"))
+
+STAGES = ["prepare", "kmm_small", "kmm", "mmv_small", "mmv", "dmmv", "precond", "cg", "perf"]
+
+
+def _ref_kernel(X, C, sigma):
+    import torch
+    X64, C64 = X.double(), C.double()
+    D = (X64 * X64).sum(1)[:, None] + (C64 * C64).sum(1)[None, :] - 2.0 * X64 @ C64.T
+    return torch.exp(-D.clamp_min(0) / (2 * sigma * sigma))
+
+
+def _data(n, d, seed, norm=20.0):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    X = torch.randn(n, d, generator=g)
+    X = X * (norm / X.norm(dim=1).mean())
+    return X.cuda()
+
+
+def run_stage(stage):
+    import torch
+    from odf import _lib
+    L = _lib.load()
+    st = ctypes_stream()
+    torch.manual_seed(0)
+    ok = True
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+    if stage == "prepare":
+        for (n, d) in [(100, 40), (1000, 1024), (257, 256)]:
+            X = _data(n, d, 1)
+            mean = torch.randn(d, device="cuda") * 0.1
+            dp = L.odf_pad_dim(d); npad = L.odf_pad_rows(n)
+            hi = torch.full((n, dp), 7.0, device="cuda"); lo = torch.full((n, dp), 7.0, device="cuda")
+            sq = torch.full((npad,), 7.0, device="cuda")
+            _lib.check(L.odf_prepare_points(_lib.ptr(X), n, d, d, _lib.ptr(mean), 1.5, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(sq), st))
+            torch.cuda.synchronize()
+            xr = (X - mean) * 1.5
+            e1 = float(((hi + lo)[:, :d].double() - xr.double()).abs().max() / xr.abs().max())
+            e2 = float((sq[:n].double() - (xr.double() ** 2).sum(1)).abs().max() / 400)
+            padok = bool((hi[:, d:] == 0).all() and (lo[:, d:] == 0).all() and (sq[n:] == 0).all())
+            lowbits = int((hi.view(torch.int32) & 0x1FFF).abs().max())
+            print(f"prepare n={n} d={d}: split_err={e1:.2e} norm_err={e2:.2e} pad_ok={padok} hi_lowbits={lowbits}")
+            ok &= e1 < 1e-6 and e2 < 1e-6 and padok and lowbits == 0
+    elif stage in ("kmm_small", "kmm"):
+        shapes = [(128, 32), (128, 64), (256, 32), (200, 40)] if stage == "kmm_small" else [(1000, 1024), (1500, 256), (333, 100)]
+        for (M, d) in shapes:
+            for sigma in (5.0, 20.0):
+                C = _data(M, d, 2)
+                K = torch.full((M, M), -1.0, device="cuda")
+                ws_b = L.odf_workspace_bytes(_lib.ODF_OP_KMM, 0, M, d, 1)
+                ws = torch.empty(ws_b, dtype=torch.uint8, device="cuda")
+                _lib.check(L.odf_gauss_kmm(_lib.ptr(C), M, d, d, sigma, _lib.ptr(K), M, _lib.ptr(ws), ws_b, st), "kmm")
+                torch.cuda.synchronize()
+                Kr = _ref_kernel(C, C, sigma)
+                err = float((K.double() - Kr).abs().max())
+                print(f"kmm M={M} d={d} sigma={sigma}: max_abs_err={err:.3e} diag_min={float(K.diag().min()):.6f}")
+                if err > 1e-4:
+                    bad = (K.double() - Kr).abs() > 1e-4
+                    idx = bad.nonzero()[:5].tolist()
+                    print("   first bad idx", idx, "count", int(bad.sum()), "K", [float(K[i, j]) for i, j in idx], "ref", [float(Kr[i, j]) for i, j in idx])
+                ok &= err < 2e-5
+    elif stage in ("mmv_small", "mmv"):
+        shapes = [(128, 128, 32, 16), (128, 128, 32, 30), (256, 256, 64, 5), (300, 200, 40, 21)] if stage == "mmv_small" else \
+                 [(5000, 1000, 1024, 21), (2000, 3000, 256, 30), (20000, 1000, 1024, 1), (777, 4500, 512, 15)]
+        for (n, M, d, T) in shapes:
+            sigma = 15.0
+            X = _data(n, d, 3); C = _data(M, d, 4)
+            V = torch.randn(M, T, device="cuda")
+            out = torch.full((n, T), -7.0, device="cuda")
+            ws_b = L.odf_workspace_bytes(_lib.ODF_OP_MMV, n, M, d, T)
+            ws = torch.empty(ws_b, dtype=torch.uint8, device="cuda")
+            _lib.check(L.odf_gauss_mmv(_lib.ptr(X), n, d, _lib.ptr(C), M, d, d, _lib.ptr(V), T, T, sigma, _lib.ptr(out), T, _lib.ptr(ws), ws_b, st), "mmv")
+            torch.cuda.synchronize()
+            ref = _ref_kernel(X, C, sigma) @ V.double()
+            e = rel(out, ref)
+            print(f"mmv n={n} M={M} d={d} T={T}: rel_err={e:.3e} splits={L.odf_tile_splits(n, M, d)}")
+            if e > 1e-4:
+                dd = (out.double() - ref).abs()
+                print("   worst rows", dd.max(1).values.topk(5).indices.tolist(), "worst cols", dd.max(0).values.topk(min(5, T)).indices.tolist())
+                print("   out[0,:4]", out[0, :4].tolist(), "ref[0,:4]", ref[0, :4].tolist())
+            ok &= e < 2e-5
+    elif stage == "dmmv":
+        for (n, M, d, T) in [(3000, 500, 256, 21), (20000, 1000, 1024, 30)]:
+            sigma = 15.0
+            X = _data(n, d, 5); C = _data(M, d, 6)
+            V = torch.randn(M, T, device="cuda"); W = torch.randn(n, T, device="cuda")
+            out = torch.empty(M, T, device="cuda")
+            ws_b = L.odf_workspace_bytes(_lib.ODF_OP_DMMV, n, M, d, T)
+            ws = torch.empty(ws_b, dtype=torch.uint8, device="cuda")
+            Kr = _ref_kernel(X, C, sigma)
+            for (v, w, tag) in [(V, None, "v"), (None, W, "w"), (V, W, "vw")]:
+                _lib.check(L.odf_gauss_dmmv(_lib.ptr(X), n, d, _lib.ptr(C), M, d, d, _lib.ptr(v), T, _lib.ptr(w), T, T, sigma, _lib.ptr(out), T, _lib.ptr(ws), ws_b, st), "dmmv")
+                torch.cuda.synchronize()
+                inner = torch.zeros(n, T, dtype=torch.float64, device="cuda")
+                if v is not None: inner += Kr @ v.double()
+                if w is not None: inner += w.double()
+                ref = Kr.T @ inner
+                e = rel(out, ref)
+                print(f"dmmv[{tag}] n={n} M={M} d={d} T={T}: rel_err={e:.3e}")
+                ok &= e < 2e-5
+    elif stage == "precond":
+        for M in (300, 2000):
+            d, sigma, lam, eps = 64, 5.0, 1e-4, 1e-5
+            C = _data(M, d, 7)
+            Kr = _ref_kernel(C, C, sigma)
+            Tm = Kr.float().contiguous(); Am = torch.empty(M, M, device="cuda")
+            ws_b = L.odf_workspace_bytes(_lib.ODF_OP_PRECOND, 0, M, d, 1)
+            ws = torch.empty(ws_b, dtype=torch.uint8, device="cuda")
+            _lib.check(L.odf_precond_init(_lib.ptr(Tm), _lib.ptr(Am), M, lam, eps, _lib.ptr(ws), ws_b, st), "precond_init")
+            Tr = torch.linalg.cholesky(Kr + eps * M * torch.eye(M, device="cuda", dtype=torch.float64), upper=True)
+            Ar = torch.linalg.cholesky(Tr @ Tr.T / M + lam * torch.eye(M, device="cuda", dtype=torch.float64), upper=True)
+            eT, eA = rel(Tm, Tr), rel(Am, Ar)
+            B = torch.randn(M, 21, device="cuda")
+            errs = []
+            for which, mat, tr in [(0, Tr, False), (1, Tr, True), (2, Ar, False), (3, Ar, True)]:
+                Bc = B.clone()
+                _lib.check(L.odf_precond_solve(_lib.ptr(Tm if which < 2 else Am), M, _lib.ptr(Bc), 21, 21, which, st), "solve")
+                torch.cuda.synchronize()
+                refs = torch.linalg.solve_triangular(mat.T if tr else mat, B.double(), upper=not tr)
+                errs.append(rel(Bc, refs))
+            print(f"precond M={M}: T_err={eT:.2e} A_err={eA:.2e} solve_errs={['%.1e' % e for e in errs]}")
+            ok &= eT < 1e-3 and eA < 1e-3 and max(errs) < 5e-2
+    elif stage == "cg":
+        M, T = 1234, 21
+        R = torch.randn(M, T, device="cuda"); P = torch.randn(M, T, device="cuda"); AP = torch.randn(M, T, device="cuda")
+        Bv = torch.randn(M, T, device="cuda")
+        state = torch.zeros(4 * T + 4, device="cuda")
+        wsb = L.odf_cg_workspace_bytes(M, T); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        _lib.check(L.odf_cg_init(_lib.ptr(R), M, T, T, _lib.ptr(state), _lib.ptr(ws), wsb, st))
+        e0 = rel(state[:T], (R.double() ** 2).sum(0))
+        _lib.check(L.odf_cg_alpha(_lib.ptr(P), _lib.ptr(AP), M, T, T, 1e-7, _lib.ptr(state), _lib.ptr(ws), wsb, st))
+        a_ref = (R.double() ** 2).sum(0) / ((P.double() * AP.double()).sum(0) + 1e-7)
+        e1 = rel(state[T:2 * T], a_ref)
+        Y = Bv.clone()
+        _lib.check(L.odf_cg_axpy_a(_lib.ptr(Y), _lib.ptr(P), M, T, T, -1.0, _lib.ptr(state), st))
+        e2 = rel(Y, Bv.double() - P.double() * a_ref)
+        R2 = torch.randn(M, T, device="cuda")
+        _lib.check(L.odf_cg_beta(_lib.ptr(R2), M, T, T, 1e-7, 1e-7, _lib.ptr(state), _lib.ptr(ws), wsb, st))
+        b_ref = (R2.double() ** 2).sum(0) / ((R.double() ** 2).sum(0) + 1e-7)
+        e3 = rel(state[2 * T:3 * T], b_ref)
+        e3b = rel(state[:T], (R2.double() ** 2).sum(0))
+        P2 = P.clone()
+        _lib.check(L.odf_cg_xpby_b(_lib.ptr(P2), _lib.ptr(R2), M, T, T, _lib.ptr(state), st))
+        e4 = rel(P2, R2.double() + P.double() * b_ref)
+        R3 = torch.empty(M, T, device="cuda")
+        _lib.check(L.odf_cg_residual(_lib.ptr(R3), _lib.ptr(Bv), _lib.ptr(AP), M, T, T, _lib.ptr(state), st))
+        e5 = rel(R3, Bv.double() - AP.double())
+        O = torch.empty(M, T, device="cuda")
+        _lib.check(L.odf_axpby(_lib.ptr(O), 0.5, _lib.ptr(R), 2.0, _lib.ptr(P), M, T, T, st))
+        e6 = rel(O, 0.5 * R.double() + 2 * P.double())
+        torch.cuda.synchronize()
+        print("cg errs", ["%.1e" % e for e in (e0, e1, e2, e3, e3b, e4, e5, e6)], "flag", float(state[4 * T]))
+        ok &= max(e0, e1, e2, e3, e3b, e4, e5, e6) < 1e-5
+    elif stage == "perf":
+        for (n, M, d, T) in [(131072, 10000, 1024, 30), (262144, 5000, 256, 15), (10000, 131072, 1024, 30)]:
+            sigma = 15.0
+            X = _data(n, d, 8); C = _data(M, d, 9)
+            V = torch.randn(M, T, device="cuda")
+            dp = L.odf_pad_dim(d); Tp = L.odf_tpad(T)
+            def prep(A, m):
+                hi = torch.empty(m, dp, device="cuda"); lo = torch.empty(m, dp, device="cuda"); sq = torch.empty(L.odf_pad_rows(m), device="cuda")
+                _lib.check(L.odf_prepare_points(_lib.ptr(A), m, d, d, None, 1.0, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(sq), st))
+                return hi, lo, sq
+            xh, xl, xs = prep(X, n); ch, cl, cs = prep(C, M)
+            ldvt = L.odf_pad_rows(M)
+            vth = torch.empty(Tp, ldvt, device="cuda"); vtl = torch.empty(Tp, ldvt, device="cuda")
+            _lib.check(L.odf_split_rhs(_lib.ptr(V), M, T, T, 1.0, _lib.ptr(vth), _lib.ptr(vtl), ldvt, Tp, st))
+            for S in sorted(set([L.odf_tile_splits(n, M, d), 1, 4, 12])):
+                if S > (M + 127) // 128 // 1: continue
+                # launcher requires no empty splits
+                tiles = (M + 127) // 128; tps = (tiles + S - 1) // S
+                if (tiles + tps - 1) // tps != S: continue
+                part = torch.empty(S, n, Tp, device="cuda")
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                for it in range(3):
+                    if it == 1: e0.record()
+                    _lib.check(L.odf_gauss_mmv_prepared(_lib.ptr(xh), _lib.ptr(xl), _lib.ptr(xs), n, _lib.ptr(ch), _lib.ptr(cl), _lib.ptr(cs), M, dp,
+                                                        _lib.ptr(vth), _lib.ptr(vtl), ldvt, Tp, S, sigma, _lib.ptr(part), st), "mmv_prepared")
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 2
+                fl = 2.0 * n * M * (d + T)
+                print(f"perf mmv n={n} M={M} d={d} T={T} S={S}: {ms:.2f} ms  alg={fl / ms / 1e9:.1f} TFLOP/s  exec_tensor={(6.0 * n * M * d + 6.0 * n * M * Tp) / ms / 1e9:.1f} TFLOP/s")
+    print(("STAGE_PASS " if ok else "STAGE_FAIL ") + stage, flush=True)
+    return ok
+
+
+def ctypes_stream():
+    import ctypes
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--stage":
+        import torch  # noqa
+        sys.exit(0 if run_stage(sys.argv[2]) else 1)
+    stages = sys.argv[1:] or STAGES
+    summary = []
+    for s in stages:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--stage", s], timeout=300,
+                               capture_output=True, text=True)
+            out = r.stdout + ("\n[stderr]\n" + r.stderr[-3000:] if r.returncode != 0 else "")
+            rc = r.returncode
+        except subprocess.TimeoutExpired as e:
+            out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+            out += "\n[TIMEOUT]"
+            rc = -9
+        print(f"===== {s} rc={rc} ({time.time() - t0:.1f}s)\n{out}", flush=True)
+        summary.append((s, rc))
+    print("SUMMARY", summary)
