@@ -1,0 +1,359 @@
+"""B200-native stand-ins for the `falkon` objects the reference's wrappers use:
+
+    falkon.kernels.GaussianKernel  -> GaussianKernel      (mmv / dmmv / __call__)
+    falkon.InCoreFalkon / Falkon   -> InCoreFalkon / Falkon (fit / predict, ny_points_, alpha_)
+    falkon.options.FalkonOptions   -> FalkonOptions        (accepted, options that only select
+                                                            CPU/GPU placement upstream are ignored)
+
+Call sites in the reference: src/modules/region-classifier/
+FALKONWrapper_with_centers_selection_incore.py:50-82 and ..._selection.py:47-78; inference heads
+roi_box_predictors.py:127-160, roi_mask_predictors.py:52-99, rpn.py:189-227.
+
+Algorithm: SURVEY.md Appendix A (FALKON: Nystrom centres, Cholesky preconditioner T/A,
+preconditioned CG with per-column step sizes and a full-gradient restart every 10 iterations).
+Every arithmetic step runs in libodf (hand-written sm_100a kernels + cuSOLVER/cuBLAS for the
+M x M factorisation); rows of X may be sharded over the ranks of a torch.distributed process
+group, in which case each application of K_nm^T(K_nm .) ends in one all-reduce of the M x T
+partial (NCCL over NVLink on a B200 box, gloo in CPU tests of the host logic).
+"""
+import math
+
+import torch
+
+from . import ops
+from ._lib import ODF_SOLVE_A as SOLVE_A, ODF_SOLVE_AT as SOLVE_AT, ODF_SOLVE_T as SOLVE_T, ODF_SOLVE_TT as SOLVE_TT
+
+
+class FalkonOptions:
+    """Subset of falkon.options.FalkonOptions the reference sets (…incore.py:56)."""
+
+    def __init__(self, cg_tolerance=1e-7, cg_full_gradient_every=10, cg_epsilon_32=1e-7, pc_epsilon_32=1e-5,
+                 debug=False, **ignored):
+        # ignored upstream knobs: keops_active, min_cuda_iter_size_32/64, min_cuda_pc_size_32/64,
+        # store_kernel_d_threshold, use_cpu, no_single_kernel … (placement / caching choices that
+        # have no meaning here: everything runs on the GPU and K_nm is never materialised)
+        self.cg_tolerance = cg_tolerance
+        self.cg_full_gradient_every = cg_full_gradient_every
+        self.cg_epsilon_32 = cg_epsilon_32
+        self.pc_epsilon_32 = pc_epsilon_32
+        self.debug = debug
+        self.ignored = dict(ignored)
+
+
+class GaussianKernel:
+    """k(x, c) = exp(-|x - c|^2 / (2 sigma^2)) evaluated by the fused tcgen05 tile."""
+
+    kernel_name = "gaussian"
+
+    def __init__(self, sigma, opt=None):
+        self.sigma = float(sigma)
+        self.opt = opt
+
+    def __repr__(self):
+        return "GaussianKernel(sigma=%g)" % self.sigma
+
+    # K(X1, X2) @ v
+    def mmv(self, X1, X2, v, out=None, opt=None):
+        squeeze = v.dim() == 1
+        if squeeze:
+            v = v[:, None]
+        n = X1.n if isinstance(X1, ops.Prepared) else X1.shape[0]
+        T = v.shape[1]
+        if out is None:
+            out = torch.empty((n, T), dtype=torch.float32, device=v.device)
+        if n == 0:
+            return out[:, 0] if squeeze else out
+        rows = X1 if isinstance(X1, ops.Prepared) else ops.Prepared(X1)
+        cols = X2 if isinstance(X2, ops.Prepared) else ops.Prepared(X2)
+        ops.mmv_into(rows, cols, v, self.sigma, out)
+        return out[:, 0] if squeeze else out
+
+    # K(X1, X2)^T (K(X1, X2) v + w)
+    def dmmv(self, X1, X2, v, w, out=None, opt=None):
+        if v is None and w is None:
+            raise ValueError("dmmv needs v or w")
+        T = (v if v is not None else w).shape[1]
+        M = X2.shape[0] if not isinstance(X2, ops.Prepared) else X2.n
+        dev = (v if v is not None else w).device
+        if out is None:
+            out = torch.empty((M, T), dtype=torch.float32, device=dev)
+        rows = X1 if isinstance(X1, ops.Prepared) else ops.Prepared(X1)
+        cols = X2 if isinstance(X2, ops.Prepared) else ops.Prepared(X2)
+        sw = ops.Sweeper(rows, cols, self.sigma, min(T, 32))
+        for t0 in range(0, T, 32):
+            t1 = min(T, t0 + 32)
+            if t1 - t0 != sw.T:
+                sw = ops.Sweeper(rows, cols, self.sigma, t1 - t0)
+            sw.dmmv(None if v is None else v[:, t0:t1], None if w is None else w[:, t0:t1], out[:, t0:t1])
+        return out
+
+    def __call__(self, X1, X2=None, out=None, opt=None):
+        if X2 is not None and X2 is not X1:
+            raise NotImplementedError("only the symmetric K(X, X) block is on the hot path")
+        prep = X1 if isinstance(X1, ops.Prepared) else ops.Prepared(X1)
+        return ops.kmm(prep, self.sigma, out)
+
+
+def _dist_info(group):
+    import torch.distributed as dist
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    if group is False:
+        return None, 1
+    return dist, dist.get_world_size(group)
+
+
+class _Timer:
+    """CUDA-event timer on the current stream (wall clock when the tensors are not on a GPU,
+    which only happens in the host-logic tests that inject a CPU backend)."""
+
+    def __init__(self, dev):
+        self.cuda = dev.type == "cuda"
+        self.marks = []
+
+    def mark(self):
+        if self.cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+        else:
+            import time
+            e = time.perf_counter()
+        self.marks.append(e)
+
+    def ms(self, i, j):
+        if self.cuda:
+            return self.marks[i].elapsed_time(self.marks[j])
+        return (self.marks[j] - self.marks[i]) * 1e3
+
+
+class Falkon:
+    """fit / predict with the surface of falkon.Falkon as the reference uses it."""
+
+    def __init__(self, kernel, penalty, M, center_selection=None, maxiter=20, seed=None, options=None,
+                 error_fn=None, error_every=None, weight_fn=None, process_group=False, _ops=None):
+        self.kernel = kernel
+        self.penalty = float(penalty)
+        self.M = int(M)
+        self.center_selection = center_selection
+        self.maxiter = int(maxiter)
+        self.seed = seed
+        self.options = options if options is not None else FalkonOptions()
+        # process_group=False: single device (the reference's mode).  None: the default group if
+        # torch.distributed is initialised.  A group object: that group.
+        self.process_group = process_group
+        self.ny_points_ = None
+        self.alpha_ = None
+        self.fit_times_ = {}
+        self._prep_cache = None
+        # Device-operator table.  Always libodf (odf.ops) in the product; the N>1 host-logic
+        # tests inject a CPU stand-in with the same names to exercise sharding + all-reduce.
+        self._ops = _ops
+
+    @property
+    def _be(self):
+        return self._ops if self._ops is not None else ops
+
+    # ---- pickling / deepcopy: tensors and scalars only (reference: copy.deepcopy(self.model),
+    # torch.save(models)); device-side caches, process groups and operator tables are dropped
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_prep_cache"] = None
+        st["process_group"] = False
+        st["_ops"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+
+    def __setattr__(self, k, v):
+        if k == "ny_points_":
+            object.__setattr__(self, "_prep_cache", None)
+        object.__setattr__(self, k, v)
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, X, Y, Xts=None, Yts=None, centres=None, zscore=None):
+        """X (N x d) fp32 on the GPU [this rank's rows], Y (N,) or (N x T).  `centres` (M x d)
+        overrides center_selection (rank 0's choice is broadcast in the row-sharded mode).
+        `zscore=(mean, scale)` fuses OnlineRegionClassifier.zScores into the operand pre-pass:
+        X and the centres are taken as RAW features and (x - mean) * scale is applied on the fly."""
+        be = self._be
+        if Y.dim() == 1:
+            Y = Y[:, None]
+        Y = Y.to(torch.float32)
+        dist, world = _dist_info(self.process_group)
+        group = None if self.process_group in (None, False) else self.process_group
+        dev = X.device
+        opt = self.options
+        tm = _Timer(dev)
+        tm.mark()
+
+        if centres is None:
+            if self.center_selection is None:
+                g = torch.Generator().manual_seed(0 if self.seed is None else int(self.seed))
+                idx = torch.randperm(X.shape[0], generator=g)[:self.M].to(dev)
+                centres = X[idx]
+            else:
+                centres = self.center_selection.select(X, None)
+            if world > 1:
+                centres = centres.contiguous()
+                src = dist.get_global_rank(group, 0) if group is not None else 0
+                dist.broadcast(centres, src=src, group=group)
+        centres = centres.to(torch.float32).contiguous()
+        M, T = centres.shape[0], Y.shape[1]
+        self.M = M
+        sigma, lam = self.kernel.sigma, self.penalty
+
+        n_local = X.shape[0]
+        if world > 1:
+            n_t = torch.tensor([float(n_local)], device=dev, dtype=torch.float64)
+            dist.all_reduce(n_t, group=group)
+            N = int(n_t.item())
+        else:
+            N = n_local
+        if N == 0:
+            raise ValueError("fit needs at least one row")
+
+        zs = () if zscore is None else (zscore[0], float(zscore[1]))
+        pc = be.Prepared(centres, *zs)
+        px = be.Prepared(X, *zs) if n_local > 0 else None
+        if zs:
+            centres = be.zscore_(centres.clone(), zs[0], zs[1])     # ny_points_ live in normalised space
+        tm.mark()
+
+        # ---- preconditioner (built once per fit, replicated on every rank) --------------------
+        Kmm = be.kmm(pc, sigma)
+        Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
+        tm.mark()
+
+        alpha = torch.empty((M, T), dtype=torch.float32, device=dev)
+        iters = 0
+        for t0 in range(0, T, 32):
+            t1 = min(T, t0 + 32)
+            it = self._solve_block(px, pc, Y[:, t0:t1].contiguous(), Tm, Am, N, sigma, lam, alpha[:, t0:t1],
+                                   dist if world > 1 else None, group)
+            iters = max(iters, it)
+        tm.mark()
+        self.ny_points_ = centres
+        self.alpha_ = alpha
+        object.__setattr__(self, "_prep_cache", pc)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        self.fit_times_ = {"prepare_ms": tm.ms(0, 1), "precond_ms": tm.ms(1, 2), "cg_ms": tm.ms(2, 3),
+                           "cg_iters": iters, "sweeps": self._sweeps, "N": N, "M": M, "T": T}
+        return self
+
+    def _solve_block(self, px, pc, Yb, Tm, Am, N, sigma, lam, alpha_out, dist, group):
+        be = self._be
+        opt = self.options
+        dev = pc.hi.device
+        M, T = pc.n, Yb.shape[1]
+        eps, tol = opt.cg_epsilon_32, opt.cg_tolerance
+        sw = be.Sweeper(px, pc, sigma, T) if px is not None else None
+        new = lambda: torch.empty((M, T), dtype=torch.float32, device=dev)  # noqa: E731
+        B, R, P, AP, beta, v, u, c, H = new(), new(), new(), new(), new(), new(), new(), new(), new()
+        self._sweeps = 0
+
+        def sweep(vv, ww, out, w_scale=1.0):
+            # local rows only, then ONE all-reduce of the M x T partial
+            if sw is not None:
+                sw.dmmv(vv, ww, out, 1.0, w_scale)
+            else:
+                out.zero_()
+            if dist is not None:
+                dist.all_reduce(out, group=group)
+            self._sweeps += 1
+            return out
+
+        # B = apply_t(K_nm^T (Y / N))
+        sweep(None, Yb, B, 1.0 / N)
+        be.precond_solve_(Tm, B, SOLVE_TT)
+        be.precond_solve_(Am, B, SOLVE_AT)
+
+        def op(s, out):
+            v.copy_(s)
+            be.precond_solve_(Am, v, SOLVE_A)        # v = A^-1 s
+            u.copy_(v)
+            be.precond_solve_(Tm, u, SOLVE_T)        # u = T^-1 v
+            sweep(u, None, c)                        # c = K_nm^T K_nm u  (all ranks)
+            be.precond_solve_(Tm, c, SOLVE_TT)       # T^-T c
+            be.axpby(out, 1.0 / N, c, lam, v)        # c / N + lam v
+            be.precond_solve_(Am, out, SOLVE_AT)
+            return out
+
+        beta.zero_()
+        R.copy_(B)
+        P.copy_(B)
+        cg = be.CgState(M, T, dev)
+        cg.init(R)
+        on_gpu = dev.type == "cuda"
+        flag_host = torch.zeros(1, dtype=torch.float32)
+        if on_gpu:
+            flag_host = flag_host.pin_memory()
+        flag_ev = None
+        done = 0
+        for i in range(self.maxiter):
+            # Converged at an earlier iteration?  The device-side flag has already frozen every
+            # update, so leaving late costs sweeps, never correctness; the poll never blocks.
+            if on_gpu:
+                if flag_ev is not None and flag_ev.query() and float(flag_host[0]) != 0.0:
+                    break
+            elif float(cg.converged_flag[0]) != 0.0:
+                break
+            op(P, AP)
+            cg.alpha(P, AP, eps)                     # a = rs_old / (P.AP + eps)   per column
+            cg.axpy_a(beta, P, +1.0)                 # beta += a P
+            if (i + 1) % opt.cg_full_gradient_every == 0:
+                op(beta, H)
+                cg.residual(R, B, H)                 # R = B - op(beta)
+            else:
+                cg.axpy_a(R, AP, -1.0)               # R -= a AP
+            cg.beta(R, eps, tol)                     # rs_new, convergence flag, b = rs_new/(rs_old+eps)
+            cg.xpby_b(P, R)                          # P = R + b P
+            if on_gpu:
+                flag_host.copy_(cg.converged_flag, non_blocking=True)
+                flag_ev = torch.cuda.Event()
+                flag_ev.record()
+            done = i + 1
+        # alpha = T^-1 A^-1 beta
+        be.precond_solve_(Am, beta, SOLVE_A)
+        be.precond_solve_(Tm, beta, SOLVE_T)
+        alpha_out.copy_(beta)
+        return done
+
+    # ------------------------------------------------------------------ predict
+    def _centres_prepared(self):
+        be = self._be
+        if self._prep_cache is None or self._prep_cache.hi.device != self.ny_points_.device:
+            object.__setattr__(self, "_prep_cache", be.Prepared(self.ny_points_.to(torch.float32)))
+        return self._prep_cache
+
+    def predict(self, X, y=None):
+        if self.alpha_ is None or self.ny_points_ is None:
+            raise RuntimeError("Falkon model is not fitted")
+        be = self._be
+        alpha = self.alpha_ if self.alpha_.dim() == 2 else self.alpha_[:, None]
+        out = torch.empty((X.shape[0], alpha.shape[1]), dtype=torch.float32, device=X.device)
+        if X.shape[0] == 0:
+            return out
+        be.mmv_into(be.Prepared(X.to(torch.float32)), self._centres_prepared(), alpha.to(torch.float32),
+                    self.kernel.sigma, out)
+        return out
+
+    def __repr__(self):
+        return "%s(M=%d, penalty=%g, kernel=%r, maxiter=%d)" % (type(self).__name__, self.M, self.penalty,
+                                                                self.kernel, self.maxiter)
+
+
+class InCoreFalkon(Falkon):
+    """falkon.InCoreFalkon: identical here — data always lives in HBM."""
+    pass
+
+
+def sweep_flops(N, M, d, T):
+    """Algorithmic flops of one CG operator application: 2NMd + 4NMT."""
+    return 2.0 * N * M * d + 4.0 * N * M * T
+
+
+def fit_flops(N, M, d, T, maxiter=20, every=10):
+    f_mmv = 2.0 * N * M * (d + T)
+    return f_mmv + (maxiter + maxiter // every) * sweep_flops(N, M, d, T)

@@ -1,0 +1,287 @@
+"""Tensor-level wrappers over the libodf C ABI.  torch is used only for device memory and
+streams; every arithmetic step is a libodf call.  All functions require CUDA fp32 tensors and
+raise (OdfError / ValueError) otherwise — no fallback path exists."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+
+# Book-keeping for bench.py: number of libodf kernels launched and (optionally) CUDA-event pairs
+# around every launch of the fused tile.
+LAUNCHES = 0
+TILE_EVENTS = None      # set to a list to record (start, stop, flops) per tile launch
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s must be a torch tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must live on a CUDA device (the FALKON hot path has no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s must be float32, got %s" % (name, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must be %d-D" % (name, ndim))
+    return t
+
+
+def _rowmajor(t):
+    """Return a tensor with unit inner stride (copying only if needed) and its row pitch."""
+    if t.stride(-1) != 1 or (t.dim() == 2 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t, (t.stride(0) if t.dim() == 2 else t.shape[-1])
+
+
+class Prepared:
+    """3xTF32 operand form of a point set: hi/lo [n x d_pad] and squared norms (odf_prepare_points)."""
+
+    __slots__ = ("hi", "lo", "sqn", "n", "d", "d_pad")
+
+    def __init__(self, X, mean=None, scale=1.0):
+        L = _lib.load()
+        X = _req(X, "X", 2)
+        X, ldx = _rowmajor(X)
+        self.n, self.d = int(X.shape[0]), int(X.shape[1])
+        if self.n == 0:
+            raise ValueError("empty point set")
+        self.d_pad = int(L.odf_pad_dim(self.d))
+        dev = X.device
+        self.hi = torch.empty((self.n, self.d_pad), dtype=torch.float32, device=dev)
+        self.lo = torch.empty((self.n, self.d_pad), dtype=torch.float32, device=dev)
+        self.sqn = torch.empty((int(L.odf_pad_rows(self.n)),), dtype=torch.float32, device=dev)
+        if mean is not None:
+            mean = _req(mean, "mean").contiguous()
+        check(L.odf_prepare_points(ptr(X), self.n, self.d, ldx, ptr(mean), float(scale), ptr(self.hi),
+                                   ptr(self.lo), ptr(self.sqn), _stream()), "odf_prepare_points")
+        _count(1)
+
+
+class SplitRhs:
+    """Transposed, split right-hand side block [T_pad x pad_rows(m)] (odf_split_rhs)."""
+
+    __slots__ = ("hi", "lo", "ld", "T", "T_pad", "m")
+
+    def __init__(self, m, T, device):
+        L = _lib.load()
+        self.m, self.T = int(m), int(T)
+        self.T_pad = int(L.odf_tpad(T))
+        if self.T_pad < 0:
+            raise ValueError("at most 32 right-hand sides per block")
+        self.ld = int(L.odf_pad_rows(m))
+        self.hi = torch.empty((self.T_pad, self.ld), dtype=torch.float32, device=device)
+        self.lo = torch.empty((self.T_pad, self.ld), dtype=torch.float32, device=device)
+
+    def fill(self, V, scale=1.0):
+        L = _lib.load()
+        V, ldv = _rowmajor(_req(V, "V", 2))
+        assert V.shape[0] == self.m and V.shape[1] == self.T
+        check(L.odf_split_rhs(ptr(V), self.m, self.T, ldv, float(scale), ptr(self.hi), ptr(self.lo), self.ld,
+                              self.T_pad, _stream()), "odf_split_rhs")
+        _count(1)
+        return self
+
+
+def tile_splits(n_rows, n_cols, d):
+    return int(_lib.load().odf_tile_splits(n_rows, n_cols, d))
+
+
+def alloc_partial(rows, cols, T_pad, device):
+    """Partial-slab buffer for mmv_partial(rows, cols, ...)."""
+    S = tile_splits(rows.n, cols.n, rows.d)
+    return torch.empty((S, rows.n, T_pad), dtype=torch.float32, device=device)
+
+
+def mmv_partial(rows, cols, rhs, sigma, partial):
+    """partial[s] = K(rows, cols restricted to split s) @ rhs  — the fused tcgen05 tile."""
+    L = _lib.load()
+    assert rows.d_pad == cols.d_pad and rhs.m == cols.n
+    S = int(partial.shape[0])
+    ev = None
+    if TILE_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(L.odf_gauss_mmv_prepared(ptr(rows.hi), ptr(rows.lo), ptr(rows.sqn), rows.n, ptr(cols.hi), ptr(cols.lo),
+                                   ptr(cols.sqn), cols.n, rows.d_pad, ptr(rhs.hi), ptr(rhs.lo), rhs.ld, rhs.T_pad,
+                                   S, float(sigma), ptr(partial), _stream()), "odf_gauss_mmv_prepared")
+    if ev is not None:
+        ev[1].record()
+        TILE_EVENTS.append((ev[0], ev[1], rows.n, cols.n, rows.d, rhs.T))
+    _count(1)
+
+
+def finish_rows(partial, T, out, scale=1.0, addend=None):
+    L = _lib.load()
+    S, n, T_pad = partial.shape
+    assert out.stride(1) == 1
+    ld_add = 0
+    if addend is not None:
+        addend, ld_add = _rowmajor(_req(addend, "addend", 2))
+    check(L.odf_finish_rows(ptr(partial), S, n, T_pad, T, float(scale), ptr(addend), ld_add, ptr(out),
+                            out.stride(0), _stream()), "odf_finish_rows")
+    _count(1)
+    return out
+
+
+def finish_split(partial, T, rhs_out, scale=1.0, addend=None):
+    L = _lib.load()
+    S, n, T_pad = partial.shape
+    assert rhs_out.m == n and rhs_out.T_pad == T_pad
+    ld_add = 0
+    if addend is not None:
+        addend, ld_add = _rowmajor(_req(addend, "addend", 2))
+    check(L.odf_finish_split(ptr(partial), S, n, T_pad, T, float(scale), ptr(addend), ld_add, ptr(rhs_out.hi),
+                             ptr(rhs_out.lo), rhs_out.ld, _stream()), "odf_finish_split")
+    _count(1)
+    return rhs_out
+
+
+def kmm(prep, sigma, out=None):
+    L = _lib.load()
+    M = prep.n
+    if out is None:
+        out = torch.empty((M, M), dtype=torch.float32, device=prep.hi.device)
+    check(L.odf_gauss_kmm_prepared(ptr(prep.hi), ptr(prep.lo), ptr(prep.sqn), M, prep.d_pad, float(sigma), ptr(out),
+                                   out.stride(0), _stream()), "odf_gauss_kmm_prepared")
+    _count(1)
+    return out
+
+
+def zscore_(X, mean, scale):
+    L = _lib.load()
+    X = _req(X, "X", 2)
+    assert X.stride(1) == 1
+    mean = None if mean is None else _req(mean, "mean").contiguous()
+    check(L.odf_zscore(ptr(X), X.shape[0], X.shape[1], X.stride(0), ptr(mean), float(scale), _stream()), "odf_zscore")
+    _count(1)
+    return X
+
+
+# ---- preconditioner ---------------------------------------------------------------------------
+def precond_init(Tm, lam, eps):
+    """Tm: K_MM (M x M, contiguous) -> overwritten with T; returns (T, A)."""
+    L = _lib.load()
+    M = Tm.shape[0]
+    assert Tm.is_contiguous()
+    Am = torch.empty_like(Tm)
+    wsb = int(L.odf_workspace_bytes(_lib.ODF_OP_PRECOND, 0, M, 0, 1))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=Tm.device)
+    check(L.odf_precond_init(ptr(Tm), ptr(Am), M, float(lam), float(eps), ptr(ws), wsb, _stream()), "odf_precond_init")
+    _count(4)       # own kernels only (diag shifts, triangle clears); potrf/syrk are library launches
+    return Tm, Am
+
+
+def precond_solve_(Tri, B, which):
+    L = _lib.load()
+    assert B.stride(1) == 1
+    check(L.odf_precond_solve(ptr(Tri), Tri.shape[0], ptr(B), B.shape[1], B.stride(0), int(which), _stream()),
+          "odf_precond_solve")
+    return B
+
+
+# ---- CG vector kernels ------------------------------------------------------------------------
+class CgState:
+    def __init__(self, M, T, device):
+        L = _lib.load()
+        self.M, self.T = int(M), int(T)
+        self.state = torch.zeros((4 * T + 4,), dtype=torch.float32, device=device)
+        self.wsb = int(L.odf_cg_workspace_bytes(M, T))
+        self.ws = torch.empty((max(self.wsb, 8),), dtype=torch.uint8, device=device)
+
+    def init(self, R):
+        check(_lib.load().odf_cg_init(ptr(R), self.M, self.T, R.stride(0), ptr(self.state), ptr(self.ws), self.wsb,
+                                      _stream()), "odf_cg_init")
+        _count(2)
+
+    def alpha(self, P, AP, eps):
+        check(_lib.load().odf_cg_alpha(ptr(P), ptr(AP), self.M, self.T, P.stride(0), float(eps), ptr(self.state),
+                                       ptr(self.ws), self.wsb, _stream()), "odf_cg_alpha")
+        _count(2)
+
+    def axpy_a(self, Y, X, sign):
+        check(_lib.load().odf_cg_axpy_a(ptr(Y), ptr(X), self.M, self.T, Y.stride(0), float(sign), ptr(self.state),
+                                        _stream()), "odf_cg_axpy_a")
+        _count(1)
+
+    def residual(self, R, Bm, H):
+        check(_lib.load().odf_cg_residual(ptr(R), ptr(Bm), ptr(H), self.M, self.T, R.stride(0), ptr(self.state),
+                                          _stream()), "odf_cg_residual")
+        _count(1)
+
+    def beta(self, R, eps, tol):
+        check(_lib.load().odf_cg_beta(ptr(R), self.M, self.T, R.stride(0), float(eps), float(tol), ptr(self.state),
+                                      ptr(self.ws), self.wsb, _stream()), "odf_cg_beta")
+        _count(2)
+
+    def xpby_b(self, P, R):
+        check(_lib.load().odf_cg_xpby_b(ptr(P), ptr(R), self.M, self.T, P.stride(0), ptr(self.state), _stream()),
+              "odf_cg_xpby_b")
+        _count(1)
+
+    @property
+    def converged_flag(self):
+        return self.state[4 * self.T:4 * self.T + 1]
+
+
+def axpby(out, alpha, A, beta=0.0, B=None):
+    check(_lib.load().odf_axpby(ptr(out), float(alpha), ptr(A), float(beta), ptr(B), out.shape[0], out.shape[1],
+                                out.stride(0), _stream()), "odf_axpby")
+    _count(1)
+    return out
+
+
+# ---- composite operators ----------------------------------------------------------------------
+def mmv_into(rows, cols, v, sigma, out):
+    T = v.shape[1]
+    dev = out.device
+    for t0 in range(0, T, 32):
+        t1 = min(T, t0 + 32)
+        rhs = SplitRhs(cols.n, t1 - t0, dev).fill(v[:, t0:t1])
+        part = alloc_partial(rows, cols, rhs.T_pad, dev)
+        mmv_partial(rows, cols, rhs, sigma, part)
+        if out.stride(1) == 1:
+            finish_rows(part, t1 - t0, out[:, t0:t1])
+        else:
+            tmp = torch.empty((rows.n, t1 - t0), dtype=torch.float32, device=dev)
+            finish_rows(part, t1 - t0, tmp)
+            out[:, t0:t1].copy_(tmp)
+
+
+class Sweeper:
+    """Pre-allocated buffers for repeated K_nm^T (K_nm V + W) sweeps with T <= 32 columns."""
+
+    def __init__(self, rows, cols, sigma, T):
+        dev = rows.hi.device
+        self.rows, self.cols, self.sigma, self.T = rows, cols, sigma, int(T)
+        self.v_rhs = SplitRhs(cols.n, T, dev)       # V^T  (T_pad x M)
+        self.w_rhs = SplitRhs(rows.n, T, dev)       # W^T  (T_pad x n)
+        self.part1 = alloc_partial(rows, cols, self.v_rhs.T_pad, dev)   # rows = data
+        self.part2 = alloc_partial(cols, rows, self.v_rhs.T_pad, dev)   # rows = centres
+
+    def dmmv(self, v, w, out, scale=1.0, w_scale=1.0):
+        """out = scale * K^T (K v + w_scale * w)   (local rows only; caller all-reduces)."""
+        if v is not None:
+            self.v_rhs.fill(v)
+            mmv_partial(self.rows, self.cols, self.v_rhs, self.sigma, self.part1)
+            if w is not None and w_scale != 1.0:
+                w = w * w_scale
+            finish_split(self.part1, self.T, self.w_rhs, 1.0, w)
+        else:
+            self.w_rhs.fill(w, w_scale)
+        mmv_partial(self.cols, self.rows, self.w_rhs, self.sigma, self.part2)
+        finish_rows(self.part2, self.T, out, scale)
+        return out
+
+

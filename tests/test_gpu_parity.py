@@ -1,0 +1,304 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(ctypes -> libodf.so), against the CPU oracle on identical seeded inputs.  Tolerances follow
+BASELINE.json's north_star: decision scores within 1e-3 relative, identical argmax class and NMS
+keep indices, mAP within 0.1.  Nothing here reads /root/reference."""
+import copy
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import falkon_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SCORE_RTOL = 1e-3          # north_star: "decision scores within 1e-3 relative"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def odf(lib):
+    import odf as _odf
+    return _odf
+
+
+# ----------------------------------------------------------------------------- kernel level
+@pytest.mark.parametrize("n,M,d,T", [(1, 1, 1, 1), (128, 128, 32, 16), (300, 200, 40, 21), (129, 257, 33, 1),
+                                     (2000, 1500, 256, 30), (4096, 1000, 1024, 21), (777, 130, 2048, 15),
+                                     (50, 3000, 100, 32)])
+def test_mmv_matches_oracle(odf, n, M, d, T):
+    X, _, _ = orc.make_synthetic(max(n, 2), d, 2, seed=3)
+    C, _, _ = orc.make_synthetic(max(M, 2), d, 2, seed=4)
+    X, C = X[:n], C[:M]
+    v = torch.randn(M, T, generator=torch.Generator().manual_seed(5))
+    k = odf.GaussianKernel(15.0)
+    out = k.mmv(X.cuda(), C.cuda(), v.cuda())
+    assert out.shape == (n, T)
+    assert rel(out, orc.mmv(X, C, v, 15.0)) < 5e-5
+
+
+def test_mmv_out_argument_and_vector_rhs(odf):
+    X, _, _ = orc.make_synthetic(500, 64, 2, seed=1)
+    C = X[:100]
+    v = torch.randn(100, 15)
+    k = odf.GaussianKernel(20.0)
+    out = torch.full((500, 15), 9.0, device="cuda")
+    ret = k.mmv(X.cuda(), C.cuda(), v.cuda(), out=out)            # rpn.py:225 passes out=
+    assert ret.data_ptr() == out.data_ptr()
+    assert rel(out, orc.mmv(X, C, v, 20.0)) < 5e-5
+    more = torch.randn(100, 45)                                     # > 32 columns: chunked
+    assert rel(k.mmv(X.cuda(), C.cuda(), more.cuda()), orc.mmv(X, C, more, 20.0)) < 5e-5
+
+
+@pytest.mark.parametrize("n,M,d,T", [(3000, 500, 256, 21), (1000, 64, 48, 1), (5000, 1000, 1024, 30)])
+def test_dmmv_matches_oracle(odf, n, M, d, T):
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
+    C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
+    g = torch.Generator().manual_seed(8)
+    v, w = torch.randn(M, T, generator=g), torch.randn(n, T, generator=g)
+    k = odf.GaussianKernel(15.0)
+    Xg, Cg = X.cuda(), C.cuda()
+    assert rel(k.dmmv(Xg, Cg, v.cuda(), None), orc.dmmv(X, C, v, None, 15.0)) < 1e-4
+    assert rel(k.dmmv(Xg, Cg, None, w.cuda()), orc.dmmv(X, C, None, w, 15.0)) < 1e-4
+    assert rel(k.dmmv(Xg, Cg, v.cuda(), w.cuda()), orc.dmmv(X, C, v, w, 15.0)) < 1e-4
+
+
+@pytest.mark.parametrize("M,d,sigma", [(1000, 1024, 15.0), (333, 100, 5.0), (1500, 256, 50.0)])
+def test_kmm_matches_oracle(odf, M, d, sigma):
+    C, _, _ = orc.make_synthetic(M, d, 2, seed=9)
+    K = odf.GaussianKernel(sigma)(C.cuda())
+    Kr = orc.gaussian_kernel(C, C, sigma)
+    assert float((K.double().cpu() - Kr).abs().max()) < 5e-4
+    assert float(K.max()) <= 1.0 and float(K.diag().min()) > 0.999
+
+
+def test_duplicate_points_give_unit_kernel(odf):
+    """Centres are sampled from X with replacement: exact duplicates must score K ~ 1 (clamped)."""
+    X, _, _ = orc.make_synthetic(256, 1024, 2, seed=10)
+    C = X[[5, 5, 17, 200]]
+    v = torch.eye(4)
+    out = odf.GaussianKernel(5.0).mmv(X.cuda(), C.cuda(), v.cuda()).cpu()
+    assert abs(float(out[5, 0]) - 1) < 3e-4 and abs(float(out[5, 1]) - 1) < 3e-4 and abs(float(out[200, 3]) - 1) < 3e-4
+    assert float(out.max()) <= 1.0
+
+
+# ----------------------------------------------------------------------------- fit level
+def _gpu_fit(odf, X, Y, C, sigma, lam, **kw):
+    m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=C.shape[0], **kw)
+    m.fit(X.cuda(), Y.cuda(), centres=C.cuda())
+    return m
+
+
+def test_golden_fixture_fit_and_scores(odf):
+    g = np.load(os.path.join(GOLD, "falkon_small.npz"))
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    C = X[torch.from_numpy(g["centre_idx"])]
+    m = _gpu_fit(odf, X, Y, C, float(g["sigma"]), float(g["lam"]))
+    scores = m.predict(X[:64].cuda())
+    assert rel(scores, torch.from_numpy(g["scores"])) < SCORE_RTOL
+    assert rel(m.alpha_, torch.from_numpy(g["alpha"])) < 5e-2      # alpha itself is ill-conditioned
+
+
+@pytest.mark.parametrize("N,M,sigma,lam", [(20000, 1000, 15.0, 1e-3), (20000, 1000, 10.0, 1e-6),
+                                           (6000, 500, 20.0, 1e-3), (6000, 500, 5.0, 1e-4)])
+def test_config1_fit_matches_oracle(odf, N, M, sigma, lam):
+    """BASELINE config 1 (N=20k, d=1024, M=1k, 21 classes; and a reduced copy) with the
+    reference's sigma/lambda pairs: scores within 1e-3 relative, identical argmax class."""
+    d, T = 1024, 21
+    X, c, Y = orc.make_synthetic(N, d, T, seed=0)
+    C = X[orc.shared_centres(c, M, seed=1)]
+    m = _gpu_fit(odf, X, Y, C, sigma, lam)
+    assert m.fit_times_["sweeps"] == 23
+    alpha = orc.falkon_fit(X, Y, C, sigma, lam, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+    Xt, ct, _ = orc.make_synthetic(4000, d, T, seed=11)
+    s_gpu = m.predict(Xt.cuda()).cpu()
+    s_ref = orc.falkon_predict(Xt, C, alpha, sigma)
+    assert rel(s_gpu, s_ref) < SCORE_RTOL
+    assert torch.equal(s_gpu.argmax(1), s_ref.argmax(1))
+
+
+def test_per_class_mode_with_duplicate_centres(odf):
+    """Reference mode: one binary model, centres drawn WITH replacement (rank-deficient K_MM)."""
+    X, c, Y = orc.make_synthetic(6000, 256, 4, seed=2)
+    y = Y[:, 0].contiguous()
+    idx = orc.compute_indices_selection(y, 500, generator=torch.Generator().manual_seed(0))
+    assert len(set(idx)) < len(idx)
+    C = X[idx]
+    m = _gpu_fit(odf, X, y, C, 10.0, 1e-5)
+    alpha = orc.falkon_fit(X, y, C, 10.0, 1e-5, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+    assert m.alpha_.shape == (500, 1)
+    assert rel(m.predict(X[:2000].cuda()), orc.falkon_predict(X[:2000], C, alpha, 10.0)) < SCORE_RTOL
+
+
+def test_fused_zscore_equals_prenormalised(odf):
+    g = torch.Generator().manual_seed(12)
+    raw = torch.randn(3000, 128, generator=g) * 3 + 1.5
+    mean, scale = raw[:500].mean(0), 20.0 / float(raw[:500].norm(dim=1).mean())
+    Xn = orc.zscores(raw, mean, 20.0 / scale)
+    Y = torch.sign(torch.randn(3000, 2, generator=g))
+    idx = torch.arange(0, 3000, 10)
+    m1 = odf.InCoreFalkon(kernel=odf.GaussianKernel(15.0), penalty=1e-3, M=300)
+    m1.fit(raw.cuda(), Y.cuda(), centres=raw[idx].cuda(), zscore=(mean.cuda(), scale))
+    m2 = _gpu_fit(odf, Xn, Y, Xn[idx], 15.0, 1e-3)
+    assert rel(m1.ny_points_, m2.ny_points_) < 1e-6
+    assert rel(m1.predict(Xn[:512].cuda()), m2.predict(Xn[:512].cuda())) < 1e-4
+
+
+def test_model_roundtrip_on_device(odf):
+    X, c, Y = orc.make_synthetic(2000, 64, 2, seed=3)
+    m = _gpu_fit(odf, X, Y, X[:100], 15.0, 1e-3)
+    ref = m.predict(X[:300].cuda())
+    m2 = copy.deepcopy(m)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    m3.ny_points_ = m3.ny_points_.to("cpu").to("cuda")      # falkon_models_to_cuda contract
+    m3.alpha_ = m3.alpha_.to("cuda")
+    for k in (m2, m3):
+        assert torch.equal(k.predict(X[:300].cuda()), ref)
+    assert m.predict(X[:0].cuda()).shape == (0, 2)
+
+
+# ----------------------------------------------------------------------------- drop-in modules
+def _cfg(tmp_path, M, sigma, lam, classes=3):
+    import yaml
+    cfg = {"CHOSEN_CLASSES": ["__background__"] + ["c%d" % i for i in range(classes - 1)],
+           "ONLINE_REGION_CLASSIFIER": {"CLASSIFIER": {"sigma": sigma, "lambda": lam, "M": M},
+                                        "MINIBOOTSTRAP": {"EASY_THRESH": -0.9, "HARD_THRESH": -0.7}}}
+    p = tmp_path / "cfg.yaml"
+    p.write_text(yaml.dump(cfg))
+    return str(p)
+
+
+def test_falkon_wrapper_train_predict(odf, tmp_path):
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    X, c, Y = orc.make_synthetic(5000, 256, 3, seed=4)
+    y = Y[:, 1].contiguous()
+    w = falkon.FALKONWrapper(_cfg(tmp_path, 400, 15, 1e-3))
+    torch.manual_seed(7)
+    model = w.train(X.cuda(), y.cuda())
+    torch.manual_seed(7)
+    idx = orc.compute_indices_selection(y, 400)
+    assert model is not w.model and model.M == len(idx) == 400
+    assert torch.equal(model.ny_points_.cpu(), X[idx])
+    alpha = orc.falkon_fit(X, y, X[idx], 15.0, 1e-3, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+    pred = w.predict(model, X[:1000].cuda())
+    assert pred.shape == (1000, 1) and pred.is_cuda
+    assert rel(pred, orc.falkon_predict(X[:1000], X[idx], alpha, 15.0)) < SCORE_RTOL
+
+
+def test_host_flavour_keeps_results_on_host(odf, tmp_path):
+    import FALKONWrapper_with_centers_selection as falkon
+    X, c, Y = orc.make_synthetic(2000, 64, 2, seed=5)
+    w = falkon.FALKONWrapper(_cfg(tmp_path, 100, 15, 1e-3))
+    model = w.train(X, Y[:, 0].contiguous())
+    assert not model.ny_points_.is_cuda
+    pred = w.predict(model, X[:100])
+    assert not pred.is_cuda and pred.shape == (100, 1)
+
+
+def test_minibootstrap_matches_oracle_loop(odf, tmp_path):
+    """OnlineRegionClassifier.trainRegionClassifier vs the oracle's minibootstrap with oracle fits:
+    same hard/easy selections (index sets) and final scores within tolerance."""
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    import OnlineRegionClassifier_incore as ocr
+    d, M, sigma, lam = 128, 200, 15.0, 1e-3
+    X, c, _ = orc.make_synthetic(9000, d, 2, seed=6)
+    stats = {"mean": torch.zeros(d, device="cuda"), "std": torch.ones(d, device="cuda"),
+             "mean_norm": torch.tensor(20.0, device="cuda")}
+    positives = [X[c == 1][:300].cuda(), X[c == 2][:300].cuda()]
+    bg = X[c == 0]
+    negatives = [[bg[i * 700:(i + 1) * 700].cuda() for i in range(4)], [bg[3000 + i * 700:3000 + (i + 1) * 700].cuda() for i in range(3)]]
+    clf = falkon.FALKONWrapper(_cfg(tmp_path, M, sigma, lam))
+    rc = ocr.OnlineRegionClassifier(clf, [p.clone() for p in positives], [[n.clone() for n in ns] for ns in negatives],
+                                    stats, cfg_path=_cfg(tmp_path, M, sigma, lam))
+    torch.manual_seed(3)
+    models, caches = rc.trainRegionClassifier(opts={"return_caches": True})
+    assert len(models) == 2 and all(m is not None for m in models)
+
+    torch.manual_seed(3)
+
+    def train(Xc, y):
+        idx = orc.compute_indices_selection(y, M)
+        return (Xc[idx], orc.falkon_fit(Xc, y, Xc[idx], sigma, lam, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7))
+
+    def predict(model, Xq):
+        return orc.falkon_predict(Xq, model[0], model[1], sigma)
+
+    for i in range(2):
+        ref_model, ref_cache = orc.minibootstrap(positives[i].cpu(), [n.cpu() for n in negatives[i]], train, predict)
+        assert caches[i]["neg"].shape == ref_cache.shape
+        assert torch.equal(caches[i]["neg"].cpu(), ref_cache)          # same hard/easy index decisions
+        s = clf.predict(models[i], X[:1500].cuda())
+        assert rel(s, predict(ref_model, X[:1500])) < SCORE_RTOL
+
+
+# ----------------------------------------------------------------------------- integer post-processing
+def test_argmax_nms_and_map_parity(odf):
+    """Scores from the GPU model and from the oracle drive the (oracle) +1-convention post
+    processing: identical argmax, identical NMS keep indices per class, mAP within 0.1."""
+    N, d, T, M = 12000, 256, 5, 600
+    X, c, Y = orc.make_synthetic(N, d, T, seed=0)
+    C = X[orc.shared_centres(c, M, seed=1)]
+    m = _gpu_fit(odf, X, Y, C, 15.0, 1e-3)
+    alpha = orc.falkon_fit(X, Y, C, 15.0, 1e-3, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+    Xt, ct, _ = orc.make_synthetic(3000, d, T, seed=21)
+    s_gpu = m.predict(Xt.cuda()).cpu().numpy()
+    s_ref = orc.falkon_predict(Xt, C, alpha, 15.0).float().numpy()
+    assert (s_gpu.argmax(1) == s_ref.argmax(1)).all()
+    rng = np.random.RandomState(2)
+    dets_gpu, dets_ref, gts = [], [], []
+    for img in range(10):                                           # 300 boxes per "image"
+        sl = slice(img * 300, (img + 1) * 300)
+        xy = np.stack([rng.randint(0, 590, 300), rng.randint(0, 430, 300)], 1).astype(np.float32)
+        wh = rng.randint(10, 200, size=(300, 2)).astype(np.float32)
+        box = orc.clip_to_image(np.concatenate([xy, xy + wh], 1), 640, 480)
+        boxes = np.tile(box, (1, T + 1))
+        out = []
+        for s in (s_gpu, s_ref):
+            sc = np.concatenate([-np.ones((300, 1), np.float32), s[sl]], 1)
+            out.append(orc.filter_results(boxes, sc, -2.0, 0.3, 100))
+        for kg, kr in zip(out[0][3], out[1][3]):
+            assert np.array_equal(kg, kr)                           # bit-identical NMS keep indices
+        dets_gpu.append(out[0][:3])
+        dets_ref.append(out[1][:3])
+        lab = ct[sl].numpy()
+        gts.append((box[lab > 0], lab[lab > 0]))
+    map_gpu = orc.detection_map(dets_gpu, gts, T + 1)
+    map_ref = orc.detection_map(dets_ref, gts, T + 1)
+    assert abs(map_gpu - map_ref) * 100 <= 0.1
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_config2_shape(odf):
+    """BASELINE config 2/5 shape (N=1M x 1024, M=10k, T=30) is too big for the oracle, so check
+    size-independent properties: linearity in V, symmetry of K^T K, agreement of a random row
+    slice with the oracle, and row-block independence."""
+    N, d, M, T = 1_000_000, 1024, 10_000, 30
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X = torch.randn(N, d, device="cuda", generator=g)
+    X *= 20.0 / X[:4096].norm(dim=1).mean()
+    C = X[torch.randperm(N, device="cuda", generator=g)[:M]].contiguous()
+    from odf import ops
+    k = odf.GaussianKernel(20.0)
+    px, pc = ops.Prepared(X), ops.Prepared(C)
+    v1 = torch.randn(M, T, device="cuda", generator=g)
+    v2 = torch.randn(M, T, device="cuda", generator=g)
+    o1, o2 = k.mmv(px, pc, v1), k.mmv(px, pc, v2)
+    o12 = k.mmv(px, pc, 2.0 * v1 - 0.5 * v2)
+    assert rel(o12, 2.0 * o1 - 0.5 * o2) < 1e-4                      # linearity
+    rows = torch.randperm(N, device="cuda", generator=g)[:2048]
+    ref = orc.mmv(X[rows].cpu(), C.cpu(), v1.cpu(), 20.0)
+    assert rel(o1[rows], ref) < 5e-5                                # slice vs oracle
+    assert rel(k.mmv(X[rows].contiguous(), pc, v1), o1[rows]) < 1e-5   # row-block independence
+    h1 = k.dmmv(px, pc, v1, None)
+    h2 = k.dmmv(px, pc, v2, None)
+    a, b = (v2.double() * h1.double()).sum(), (v1.double() * h2.double()).sum()
+    assert abs(float(a - b)) / abs(float(a)) < 1e-4                  # u^T (K^T K v) == v^T (K^T K u)
