@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — FALKON fit throughput on B200 (the reference's headline: "FALKON fit s & kernel
+GFLOP/s at 1/2/4/8 B200").
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference            # CPU port of the reference path (oracle)
+
+One "step" = one complete FALKON fit (operand pre-pass with the fused z-score, K_MM, two Cholesky,
+right-hand side sweep, 20 preconditioned-CG iterations with 2 full-gradient restarts) on synthetic
+features of BASELINE.json config 2: 30 classes, N = 1M RoIs x 1024-d, M = 10k centres.  With N GPUs
+the N rows are sharded (strong scaling: total work fixed) and every operator application ends in
+one NCCL all-reduce of the M x T partial.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "online-detection_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: (N, d, M, T, sigma, lambda)  — sigma/lambda from config_online_rpn_online_detection_icwt30.yaml
+    "c2": (1_000_000, 1024, 10_000, 30, 20.0, 1e-3),
+    "c1": (20_000, 1024, 1_000, 21, 15.0, 1e-3),
+    "c4": (5_000_000, 256, 5_000, 15, 50.0, 1e-3),
+}
+CPU_SAMPLE = (20_000, 1_000)        # rows / centres of the CPU-baseline sample
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--m", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def fit_flops(N, M, d, T, maxiter=20, every=10):
+    """F_fit = F_mmv + (maxiter + maxiter//every) * F_dmmv, K counted once per sweep."""
+    return 2.0 * N * M * (d + T) + (maxiter + maxiter // every) * (2.0 * N * M * d + 4.0 * N * M * T)
+
+
+# ------------------------------------------------------------------------------ synthetic data
+def make_shard(n_rows, d, T, seed, pinned):
+    """Raw (un-normalised) features for one rank, generated on the HOST: prototypes + noise, 10 %
+    positives spread over T classes.  Returns X (n x d), Y (n x T) in {+-1}, labels."""
+    import torch
+    g = torch.Generator().manual_seed(1234)
+    protos = torch.randn(T + 1, d, generator=g) + 0.3          # common offset: z-score has work to do
+    g = torch.Generator().manual_seed(1000 + seed)
+    labels = torch.zeros(n_rows, dtype=torch.int64)
+    pos = torch.rand(n_rows, generator=g) < 0.1
+    labels[pos] = torch.randint(1, T + 1, (int(pos.sum()),), generator=g)
+    X = torch.empty((n_rows, d), dtype=torch.float32, pin_memory=pinned)
+    step = 65536
+    for s in range(0, n_rows, step):
+        e = min(n_rows, s + step)
+        X[s:e] = protos[labels[s:e]] + 0.7 * torch.randn(e - s, d, generator=g)
+    Y = torch.full((n_rows, T), -1.0, dtype=torch.float32, pin_memory=pinned)
+    idx = labels.nonzero()[:, 0]
+    Y[idx, labels[idx] - 1] = 1.0
+    return X, Y, labels
+
+
+def pick_centres(labels, M, seed=1):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    pos = (labels > 0).nonzero()[:, 0]
+    neg = (labels == 0).nonzero()[:, 0]
+    n_pos = min(len(pos), M // 2)
+    pos = pos[torch.randperm(len(pos), generator=g)[:n_pos]]
+    neg = neg[torch.randperm(len(neg), generator=g)[:M - n_pos]]
+    return torch.cat((pos, neg))
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_ev = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self._stop_ev.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------ CPU port (oracle)
+def cpu_port_fit_seconds(d, T, sigma, lam, n_s, m_s, repeats=1):
+    """Times the CPU restatement of the reference path (oracle, fp32, all host threads) on a
+    bounded sample of the workload.  Returns (best seconds, threads)."""
+    import torch
+    from oracle import falkon_oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    X, c, Y = orc.make_synthetic(n_s, d, T, seed=0)
+    C = X[orc.shared_centres(c, m_s, seed=1)]
+    orc.falkon_fit(X[:2000], Y[:2000], C[:100], sigma, lam, maxiter=2, dtype=torch.float32)    # thread-pool warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.falkon_fit(X, Y, C, sigma, lam, dtype=torch.float32)
+        best = min(best, time.perf_counter() - t0)
+    return best, torch.get_num_threads()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The real
+    `falkon` package is not installable offline, so this is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import falkon_oracle as orc
+    N, d, M, T, sigma, lam = WORKLOADS[args.workload]
+    n_s, m_s = min(CPU_SAMPLE[0], N), min(CPU_SAMPLE[1], M)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    X, c, Y = orc.make_synthetic(n_s, d, T, seed=0)
+    C = X[orc.shared_centres(c, m_s, seed=1)]
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.falkon_fit(X, Y, C, sigma, lam, dtype=torch.float32)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    val = fit_flops(n_s, m_s, d, T) / sec / 1e9
+    sample = "rows %d, centres %d of workload %s (d=%d, T=%d), fp32 PyTorch-CPU oracle port" % (n_s, m_s, args.workload, d, T)
+    print(json.dumps({
+        "impl": "reference", "metric": "falkon_fit_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s sample: N=%d d=%d M=%d T=%d sigma=%g lambda=%g" % (args.workload, n_s, d, m_s, T, sigma, lam)},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the FALKON hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__
+    if local == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import odf
+    from odf import ops
+
+    N, d, M, T, sigma, lam = WORKLOADS[args.workload]
+    if args.n:
+        N = args.n
+    if args.m:
+        M = args.m
+    lo, hi = (N * rank) // world, (N * (rank + 1)) // world
+    n_local = hi - lo
+    Xh, Yh, labels = make_shard(n_local, d, T, seed=rank, pinned=True)
+    # feature statistics (computeFeatStatistics_torch arithmetic) from a 4000-row sample of rank 0
+    stat = torch.zeros(d + 1, device=dev)
+    if rank == 0:
+        samp = Xh[:4000]
+        stat[:d] = samp.mean(0).to(dev)
+        stat[d] = float(samp.norm(dim=1).mean())
+    if world > 1:
+        dist.broadcast(stat, src=0)
+    mean = stat[:d].contiguous()
+    scale = 20.0 / float(stat[d])
+    centres = torch.empty((M, d), device=dev)
+    if rank == 0:
+        centres.copy_(Xh[pick_centres(labels, M)])
+    if world > 1:
+        dist.broadcast(centres, src=0)
+
+    Xd = torch.empty((n_local, d), device=dev)
+    Yd = torch.empty((n_local, T), device=dev)
+    Xd.copy_(Xh)
+    Yd.copy_(Yh)
+    group = None if world > 1 else False
+
+    def one_fit():
+        m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=group)
+        m.fit(Xd, Yd, centres=centres, zscore=(mean, scale))
+        return m
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        model = one_fit()
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.TILE_EVENTS = []
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {"prepare_ms": 0.0, "precond_ms": 0.0, "cg_ms": 0.0}
+    e0.record()
+    for _ in range(args.steps):
+        model = one_fit()
+        for k in phase:
+            phase[k] += model.fit_times_[k] / args.steps
+    e1.record()
+    sync_all()
+    launches = ops.LAUNCHES - launches0
+    tile_events, ops.TILE_EVENTS = ops.TILE_EVENTS, None
+    clocks = sampler.stop()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    F = fit_flops(N, M, d, T)
+    value = F / (ms_dev * 1e-3) / 1e9
+
+    # dominant kernel: the fused Gaussian tile.  Two launches make one K^T(K v) sweep; K is
+    # counted once per sweep, so a launch is credited (2 n M d + 4 n M T) / 2.
+    tile_ms = [a.elapsed_time(b) for (a, b, *_rest) in tile_events]
+    tile_alg = [(2.0 * r * c_ * dd + 4.0 * r * c_ * tt) / 2.0 for (_a, _b, r, c_, dd, tt) in tile_events]
+    tile_exec = [6.0 * r * c_ * ((dd + 31) // 32 * 32) + 6.0 * r * c_ * (16 if tt <= 16 else 32) for (_a, _b, r, c_, dd, tt) in tile_events]
+    avg_ms = sum(tile_ms) / max(len(tile_ms), 1)
+    achieved = sum(tile_alg) / max(sum(tile_ms), 1e-9) / 1e9          # TFLOP/s, algorithmic
+    executed = sum(tile_exec) / max(sum(tile_ms), 1e-9) / 1e9         # TFLOP/s, tensor-pipe work issued
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+        "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)"
+    roofline = {"bound": "tensor", "kernel": "gauss_tile_kernel", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "launches_timed": len(tile_ms),
+                "tile_share_of_step": sum(tile_ms) / args.steps / ms_dev,
+                "executed_tensor_tflops": executed, "tf32_dense_peak_nominal_tflops": peak / 2.0,
+                "executed_frac_of_tf32_peak": executed / (peak / 2.0),
+                "note": "3xTF32: 3 tensor passes per product at half the bf16 rate, and K is evaluated twice per "
+                        "sweep (K(X,C) then K(C,X)); algorithmic flops count it once"}
+
+    # ---- end-to-end: host buffers in, result out, every step --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            Xd.copy_(Xh, non_blocking=True)
+            Yd.copy_(Yh, non_blocking=True)
+            m = one_fit()
+            return m.alpha_.cpu()                    # device -> host read of the result
+        e2e_step()
+        sync_all()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            alpha_host = e2e_step()
+        t1.record()
+        sync_all()
+        ms_e2e = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+        e2e = {"value": F / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": (Xh.numel() + Yh.numel()) * 4 * world if world == 1 else int(N) * (d + T) * 4,
+               "d2h_bytes_per_step": alpha_host.numel() * 4 * world}
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_s, m_s = min(CPU_SAMPLE[0], N), min(CPU_SAMPLE[1], M)
+        sec, threads = cpu_port_fit_seconds(d, T, sigma, lam, n_s, m_s)
+        cpu = {"value": fit_flops(n_s, m_s, d, T) / sec / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+               "seconds": sec,
+               "sample": "one fp32 fit of the PyTorch-CPU oracle port on rows %d x centres %d of the workload "
+                         "(d=%d, T=%d), all host threads" % (n_s, m_s, d, T)}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "falkon_fit_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "%s: FALKON fit N=%d d=%d M=%d T=%d sigma=%g lambda=%g maxiter=20 (BASELINE config 2)"
+                                   % (args.workload, N, d, M, T, sigma, lam),
+                       "rows_per_gpu": n_local, "l2_policy": "inputs (%.1f GB/GPU) far larger than L2; no flush needed"
+                                                             % (n_local * d * 4 / 1e9),
+                       "parallelism": "rows sharded over %d GPU(s), 1 all-reduce of M x T per sweep" % world},
+            "fit_s": ms_dev * 1e-3, "phases_ms": phase, "sweeps_per_fit": 23,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

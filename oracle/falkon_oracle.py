@@ -421,12 +421,13 @@ def detection_map(dets, gts, num_classes, iou_thresh=0.5):
 # ------------------------------------------------------------------------------------------
 
 
-def make_synthetic(N, d, T, seed=0, pos_fraction=0.1, noise=0.7, dtype=torch.float32):
-    """Class prototypes mu_t ~ N(0, I); 10 % positives spread over T classes, 90 % background;
+def make_synthetic(N, d, T, seed=0, pos_fraction=0.1, noise=0.7, dtype=torch.float32, proto_seed=0):
+    """Class prototypes mu_t ~ N(0, I) (drawn from `proto_seed`, so train and test sets of one
+    problem share them); 10 % positives spread over T classes, 90 % background;
     x = mu_c + noise * N(0, I); then mean-centred and scaled to mean row norm 20.
     Returns X (N x d), labels c (N,) in 0..T (0 = background), Y (N x T) in {+1, -1}."""
+    protos = torch.randn(T + 1, d, generator=torch.Generator().manual_seed(7919 + proto_seed))
     g = torch.Generator().manual_seed(seed)
-    protos = torch.randn(T + 1, d, generator=g)
     c = torch.zeros(N, dtype=torch.int64)
     n_pos = int(N * pos_fraction)
     pos_idx = torch.randperm(N, generator=g)[:n_pos]

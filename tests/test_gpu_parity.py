@@ -22,6 +22,21 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+def assert_same_argmax(s_gpu, s_ref, max_tie_fraction=0.005):
+    """Identical argmax class wherever the decision is not a numerical tie: a row may differ only
+    if the oracle's own top-2 margin is inside the score tolerance band (background rows, where
+    every class scores about -1, are such near-ties), and such rows must be rare."""
+    s_gpu, s_ref = torch.as_tensor(s_gpu).double(), torch.as_tensor(s_ref).double()
+    if s_ref.shape[1] == 1:
+        return
+    top2 = s_ref.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    band = 2 * SCORE_RTOL * float(s_ref.abs().max())
+    diff = s_gpu.argmax(1) != s_ref.argmax(1)
+    assert not bool((diff & (margin > band)).any()), "argmax differs on a row with a clear margin"
+    assert float(diff.double().mean()) <= max_tie_fraction, "too many near-tie flips: %g" % float(diff.double().mean())
+
+
 @pytest.fixture(scope="module")
 def odf(lib):
     import odf as _odf
@@ -116,11 +131,14 @@ def test_config1_fit_matches_oracle(odf, N, M, sigma, lam):
     m = _gpu_fit(odf, X, Y, C, sigma, lam)
     assert m.fit_times_["sweeps"] == 23
     alpha = orc.falkon_fit(X, Y, C, sigma, lam, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
-    Xt, ct, _ = orc.make_synthetic(4000, d, T, seed=11)
+    Xt, ct, _ = orc.make_synthetic(4000, d, T, seed=11)         # same prototypes, fresh samples
     s_gpu = m.predict(Xt.cuda()).cpu()
     s_ref = orc.falkon_predict(Xt, C, alpha, sigma)
     assert rel(s_gpu, s_ref) < SCORE_RTOL
-    assert torch.equal(s_gpu.argmax(1), s_ref.argmax(1))
+    assert_same_argmax(s_gpu, s_ref)
+    pos = ct > 0                                                  # true objects: the decision that matters
+    assert torch.equal(s_gpu[pos].argmax(1), s_ref[pos].argmax(1))
+    assert float((s_ref[pos].argmax(1) + 1 == ct[pos]).double().mean()) > 0.9
 
 
 def test_per_class_mode_with_duplicate_centres(odf):
@@ -252,7 +270,8 @@ def test_argmax_nms_and_map_parity(odf):
     Xt, ct, _ = orc.make_synthetic(3000, d, T, seed=21)
     s_gpu = m.predict(Xt.cuda()).cpu().numpy()
     s_ref = orc.falkon_predict(Xt, C, alpha, 15.0).float().numpy()
-    assert (s_gpu.argmax(1) == s_ref.argmax(1)).all()
+    assert_same_argmax(s_gpu, s_ref)
+    assert (s_gpu[ct.numpy() > 0].argmax(1) == s_ref[ct.numpy() > 0].argmax(1)).all()
     rng = np.random.RandomState(2)
     dets_gpu, dets_ref, gts = [], [], []
     for img in range(10):                                           # 300 boxes per "image"
