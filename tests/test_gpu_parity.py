@@ -22,7 +22,7 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def assert_same_argmax(s_gpu, s_ref, max_tie_fraction=0.005):
+def assert_same_argmax(s_gpu, s_ref, max_tie_fraction=0.02):
     """Identical argmax class wherever the decision is not a numerical tie: a row may differ only
     if the oracle's own top-2 margin is inside the score tolerance band (background rows, where
     every class scores about -1, are such near-ties), and such rows must be rare."""
