@@ -33,25 +33,38 @@ extern "C" {
 #define ODF_SOLVE_A 2   /* B <- A^-1  B */
 #define ODF_SOLVE_AT 3  /* B <- A^-T  B */
 
+/* operand kinds of the fused tile: how the pre-pass stores the hi/lo split of a point set */
+#define ODF_KIND_TF32 0 /* tf32 in fp32 words, kind::tf32 MMAs ("3xTF32")                         */
+#define ODF_KIND_F16 1  /* fp16 after a power-of-two scaling, kind::f16 MMAs (same 2x11 bits, 2x rate) */
+
 const char* odf_last_error(void);
 int odf_version(void);
+/* kind used by the convenience entry points (odf_gauss_mmv/dmmv/kmm); default ODF_KIND_F16 */
+int odf_set_default_kind(int kind);
+int odf_default_kind(void);
 
 /* ---- layout helpers ------------------------------------------------------------------------ */
-int64_t odf_pad_dim(int64_t d);   /* feature pitch of prepared operands: round_up(d, 32)        */
+/* row pitch, in ELEMENTS, of a prepared operand array: features padded to the k-block width
+ * (32 tf32 / 64 fp16 elements = 128 bytes) plus the seed block and the ones block             */
+int64_t odf_operand_pitch(int64_t d, int kind);
+int64_t odf_operand_bytes(int64_t n, int64_t d, int kind); /* bytes of ONE of the hi / lo arrays */
 int64_t odf_pad_rows(int64_t n);  /* length of norm vectors / pitch of V^T: round_up(n, 128)    */
 int odf_tpad(int64_t T);          /* padded RHS count: 16 if T<=16, 32 if T<=32, else -1        */
 /* Number of column splits the tile launcher wants for this shape (size of the partial slab). */
-int odf_tile_splits(int64_t n_rows, int64_t n_cols, int64_t d);
+int odf_tile_splits(int64_t n_rows, int64_t n_cols, int64_t d, int kind);
 
 /* ---- operand preparation ------------------------------------------------------------------- */
-/* Fused z-score + 3xTF32 split + squared norms.
+/* Fused z-score + hi/lo split + squared norms (two passes over X).
  * Replaces OnlineRegionClassifier.zScores (src/modules/region-classifier/
  * OnlineRegionClassifier.py:224-227) and the norm pre-pass of falkon GaussianKernel.
- *   x' = (X[r,:] - mean) * scale      (mean may be NULL -> 0)
- *   hi = tf32(x'), lo = tf32(x' - hi) -> [n x odf_pad_dim(d)], zero padded
- *   sqnorm[r] = |x'|^2                -> odf_pad_rows(n) floats, zero padded                    */
+ *   x' = (X[r,:] - mean) * scale                      (mean may be NULL -> 0)
+ *   sqnorm[r] = |x'|^2   -> odf_pad_rows(n) floats, zero padded
+ *   opscale[0] = s       -> power of two (1 for ODF_KIND_TF32); opscale is a 2-float device buffer
+ *   hi = rn11(s x'), lo = rn11(s x' - hi)  -> [n x odf_operand_pitch(d, kind)] elements each
+ *   hi additionally carries the seed block (-s^2 |x'|^2 / 2 as hi, lo) and the ones block.   */
 int odf_prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean,
-                       float scale, float* hi, float* lo, float* sqnorm, void* stream);
+                       float scale, int kind, void* hi, void* lo, float* sqnorm, float* opscale,
+                       void* stream);
 /* In-place z-score only (same reference lines). */
 int odf_zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
                void* stream);
@@ -65,12 +78,13 @@ int odf_split_rhs(const float* V, int64_t m, int64_t T, int64_t ldv, float scale
  * with K = exp(-|r-q|^2 / (2 sigma^2)).  Stands in for falkon GaussianKernel.mmv
  * (call sites: FALKONWrapper_with_centers_selection_incore.py:75-82, roi_box_predictors.py:158,
  * roi_mask_predictors.py:90, rpn.py:225) and for each half of GaussianKernel.dmmv.
- * n_splits must come from odf_tile_splits(n_rows, n_cols, d).                                   */
-int odf_gauss_mmv_prepared(const float* r_hi, const float* r_lo, const float* r_sqnorm,
-                           int64_t n_rows, const float* q_hi, const float* q_lo,
-                           const float* q_sqnorm, int64_t n_cols, int64_t d_pad,
-                           const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad,
-                           int n_splits, float sigma, float* partial, void* stream);
+ * n_splits must come from odf_tile_splits(n_rows, n_cols, d, kind).                                   */
+int odf_gauss_mmv_prepared(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
+                           const float* r_opscale, int64_t n_rows, const void* q_hi,
+                           const void* q_lo, const float* q_sqnorm, const float* q_opscale,
+                           int64_t n_cols, int64_t d, const float* vt_hi, const float* vt_lo,
+                           int64_t ldvt, int T_pad, int n_splits, float sigma, float* partial,
+                           void* stream);
 /* out[r, t] = scale * sum_s partial[s][r][t] + addend[r, t]   (addend may be NULL) */
 int odf_finish_rows(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T,
                     float scale, const float* addend, int64_t ld_add, float* out, int64_t ldo,
@@ -81,8 +95,9 @@ int odf_finish_split(const float* partial, int n_splits, int64_t n_rows, int T_p
                      int64_t ldwt, void* stream);
 /* K[i, j] = exp(-|c_i - c_j|^2 / (2 sigma^2)), M x M, pitch ldk.  falkon Kernel.__call__ (K_MM
  * for FalkonPreconditioner.init, reached through InCoreFalkon.fit, ...incore.py:68).            */
-int odf_gauss_kmm_prepared(const float* c_hi, const float* c_lo, const float* c_sqnorm, int64_t M,
-                           int64_t d_pad, float sigma, float* K, int64_t ldk, void* stream);
+int odf_gauss_kmm_prepared(int kind, const void* c_hi, const void* c_lo, const float* c_sqnorm,
+                           const float* c_opscale, int64_t M, int64_t d, float sigma, float* K,
+                           int64_t ldk, void* stream);
 
 /* ---- convenience entry points on plain fp32 operands (prepare internally in `ws`) ----------- */
 #define ODF_OP_MMV 0
@@ -110,6 +125,16 @@ int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void
 /* B [M x T] (pitch ldb) <- op(Tri)^-1 B with Tri upper triangular (pitch M), op by `which`.   */
 int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t ldb, int which,
                       void* stream);
+
+/* Explicit inverse of an upper-triangular factor (Inv = Tri^-1, upper, pitch M; one TRSM against
+ * the identity, done once per fit) and its application as a plain GEMM:
+ *   Bout = Inv B (transposed = 0)   or   Bout = Inv^T B (transposed = 1),   B, Bout: M x T, pitch ldb.
+ * This replaces the 4 latency-bound triangular solves per CG iteration by bandwidth-bound GEMMs;
+ * it is algebraically the same preconditioner (any invertible T~, A~ used consistently leaves the
+ * fixed point of the preconditioned system unchanged up to the regulariser lam T~^T T~).          */
+int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream);
+int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T,
+                      int64_t ldb, int transposed, void* stream);
 
 /* ---- conjugate-gradient vector kernels on M x T blocks (per-column scalars) ------------------ */
 /* FalkonConjugateGradient / ConjugateGradient.solve.  `state` is a device

@@ -11,7 +11,7 @@
 namespace odf {
 
 // ---- implemented in odf_vec.cu
-int prepare_points(const float*, int64_t, int64_t, int64_t, const float*, float, float*, float*, float*, cudaStream_t);
+int prepare_points(const float*, int64_t, int64_t, int64_t, const float*, float, int, void*, void*, float*, float*, cudaStream_t);
 int zscore(float*, int64_t, int64_t, int64_t, const float*, float, cudaStream_t);
 int split_rhs(const float*, int64_t, int64_t, int64_t, float, float*, float*, int64_t, int, cudaStream_t);
 int finish_rows(const float*, int, int64_t, int, int64_t, float, const float*, int64_t, float*, int64_t, cudaStream_t);
@@ -26,6 +26,7 @@ int cg_residual(float*, const float*, const float*, int64_t, int64_t, int64_t, c
 int axpby(float*, float, const float*, float, const float*, int64_t, int64_t, int64_t, cudaStream_t);
 int add_diag(float*, int64_t, float, cudaStream_t);
 int zero_lower(float*, int64_t, cudaStream_t);
+int set_identity(float*, int64_t, cudaStream_t);
 
 namespace {
 thread_local std::string g_err = "";
@@ -59,16 +60,23 @@ struct Arena {
 };
 inline size_t al(size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); }
 
+int g_default_kind = ODF_KIND_F16;
+
 struct Prepared {
-  float *hi, *lo, *sqn;
+  void *hi, *lo;
+  float *sqn, *opscale;
 };
-size_t prepared_bytes(int64_t n, int64_t d) {
-  return 2 * al(sizeof(float) * n * round_up(d, 32)) + al(sizeof(float) * round_up(n, 128));
+size_t operand_bytes(int64_t n, int64_t d, int kind) {
+  return static_cast<size_t>(n) * operand_pitch(d, kind) * (kind == KIND_F16 ? 2 : 4);
 }
-bool take_prepared(Arena& a, int64_t n, int64_t d, Prepared* p) {
-  p->hi = a.take<float>(n * round_up(d, 32));
-  p->lo = a.take<float>(n * round_up(d, 32));
+size_t prepared_bytes(int64_t n, int64_t d, int kind) {
+  return 2 * al(operand_bytes(n, d, kind)) + al(sizeof(float) * round_up(n, 128)) + 256;
+}
+bool take_prepared(Arena& a, int64_t n, int64_t d, int kind, Prepared* p) {
+  p->hi = a.take<uint8_t>(operand_bytes(n, d, kind));
+  p->lo = a.take<uint8_t>(operand_bytes(n, d, kind));
   p->sqn = a.take<float>(round_up(n, 128));
+  p->opscale = a.take<float>(2);
   return a.ok();
 }
 
@@ -100,16 +108,24 @@ extern "C" {
 const char* odf_last_error(void) { return g_err.c_str(); }
 int odf_version(void) { return 100; }
 
-int64_t odf_pad_dim(int64_t d) { return round_up(d, 32); }
+int odf_set_default_kind(int kind) {
+  if (kind != ODF_KIND_TF32 && kind != ODF_KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
+  g_default_kind = kind;
+  return ODF_OK;
+}
+int odf_default_kind(void) { return g_default_kind; }
+
+int64_t odf_operand_pitch(int64_t d, int kind) { return operand_pitch(d, kind); }
+int64_t odf_operand_bytes(int64_t n, int64_t d, int kind) { return static_cast<int64_t>(operand_bytes(n, d, kind)); }
 int64_t odf_pad_rows(int64_t n) { return round_up(n, 128); }
 int odf_tpad(int64_t T) { return tpad_of(T); }
-int odf_tile_splits(int64_t n_rows, int64_t n_cols, int64_t d) {
-  return tile_default_splits(n_rows, n_cols, round_up(d, 32));
+int odf_tile_splits(int64_t n_rows, int64_t n_cols, int64_t d, int kind) {
+  return tile_default_splits(n_rows, n_cols, operand_pitch(d, kind) * (kind == KIND_F16 ? 2 : 4));
 }
 
 int odf_prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
-                       float* hi, float* lo, float* sqnorm, void* stream) {
-  return prepare_points(X, n, d, ldx, mean, scale, hi, lo, sqnorm, static_cast<cudaStream_t>(stream));
+                       int kind, void* hi, void* lo, float* sqnorm, float* opscale, void* stream) {
+  return prepare_points(X, n, d, ldx, mean, scale, kind, hi, lo, sqnorm, opscale, static_cast<cudaStream_t>(stream));
 }
 int odf_zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale, void* stream) {
   return zscore(X, n, d, ldx, mean, scale, static_cast<cudaStream_t>(stream));
@@ -119,15 +135,18 @@ int odf_split_rhs(const float* V, int64_t m, int64_t T, int64_t ldv, float scale
   return split_rhs(V, m, T, ldv, scale, vt_hi, vt_lo, ldvt, T_pad, static_cast<cudaStream_t>(stream));
 }
 
-int odf_gauss_mmv_prepared(const float* r_hi, const float* r_lo, const float* r_sqnorm, int64_t n_rows,
-                           const float* q_hi, const float* q_lo, const float* q_sqnorm, int64_t n_cols,
-                           int64_t d_pad, const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad,
-                           int n_splits, float sigma, float* partial, void* stream) {
+int odf_gauss_mmv_prepared(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
+                           const float* r_opscale, int64_t n_rows, const void* q_hi, const void* q_lo,
+                           const float* q_sqnorm, const float* q_opscale, int64_t n_cols, int64_t d,
+                           const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad, int n_splits,
+                           float sigma, float* partial, void* stream) {
   if (!(sigma > 0.f)) return set_error(ODF_ERR_ARG, "sigma must be positive");
+  if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
   TileLaunch L{};
-  L.r_hi = r_hi; L.r_lo = r_lo; L.r_norm = r_sqnorm; L.n_rows = n_rows;
-  L.q_hi = q_hi; L.q_lo = q_lo; L.q_norm = q_sqnorm; L.n_cols = n_cols;
-  L.d_pad = d_pad; L.vt_hi = vt_hi; L.vt_lo = vt_lo; L.ldvt = ldvt; L.T_pad = T_pad;
+  L.kind = kind;
+  L.r_hi = r_hi; L.r_lo = r_lo; L.r_norm = r_sqnorm; L.r_scale = r_opscale; L.n_rows = n_rows;
+  L.q_hi = q_hi; L.q_lo = q_lo; L.q_norm = q_sqnorm; L.q_scale = q_opscale; L.n_cols = n_cols;
+  L.d_pad = round_up(d, kblock_elems(kind)); L.vt_hi = vt_hi; L.vt_lo = vt_lo; L.ldvt = ldvt; L.T_pad = T_pad;
   L.mode = MODE_MMV; L.n_splits = n_splits; L.sigma = sigma;
   L.out = partial; L.ldo = T_pad; L.split_stride = n_rows * T_pad;
   return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
@@ -142,14 +161,17 @@ int odf_finish_split(const float* partial, int n_splits, int64_t n_rows, int T_p
   return finish_split(partial, n_splits, n_rows, T_pad, T, scale, addend, ld_add, wt_hi, wt_lo, ldwt, static_cast<cudaStream_t>(stream));
 }
 
-int odf_gauss_kmm_prepared(const float* c_hi, const float* c_lo, const float* c_sqnorm, int64_t M, int64_t d_pad,
-                           float sigma, float* K, int64_t ldk, void* stream) {
+int odf_gauss_kmm_prepared(int kind, const void* c_hi, const void* c_lo, const float* c_sqnorm,
+                           const float* c_opscale, int64_t M, int64_t d, float sigma, float* K, int64_t ldk,
+                           void* stream) {
   if (!(sigma > 0.f)) return set_error(ODF_ERR_ARG, "sigma must be positive");
+  if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
   TileLaunch L{};
-  L.r_hi = c_hi; L.r_lo = c_lo; L.r_norm = c_sqnorm; L.n_rows = M;
-  L.q_hi = c_hi; L.q_lo = c_lo; L.q_norm = c_sqnorm; L.n_cols = M;
-  L.d_pad = d_pad; L.T_pad = 16; L.mode = MODE_STORE;
-  L.n_splits = tile_default_splits(M, M, d_pad); L.sigma = sigma;
+  L.kind = kind;
+  L.r_hi = c_hi; L.r_lo = c_lo; L.r_norm = c_sqnorm; L.r_scale = c_opscale; L.n_rows = M;
+  L.q_hi = c_hi; L.q_lo = c_lo; L.q_norm = c_sqnorm; L.q_scale = c_opscale; L.n_cols = M;
+  L.d_pad = round_up(d, kblock_elems(kind)); L.T_pad = 16; L.mode = MODE_STORE;
+  L.n_splits = odf_tile_splits(M, M, d, kind); L.sigma = sigma;
   L.out = K; L.ldo = ldk; L.split_stride = 0;
   return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
 }
@@ -157,22 +179,22 @@ int odf_gauss_kmm_prepared(const float* c_hi, const float* c_lo, const float* c_
 // ---------------------------------------------------------------- convenience (plain fp32 in)
 size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T) {
   const int T_pad = tpad_of(T > 0 ? T : 1);
-  const int64_t dp = round_up(d, 32);
+  const int kind = g_default_kind;
   switch (op) {
     case ODF_OP_MMV: {
-      const int S = tile_default_splits(n, M, dp);
-      return prepared_bytes(n, d) + prepared_bytes(M, d) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
+      const int S = odf_tile_splits(n, M, d, kind);
+      return prepared_bytes(n, d, kind) + prepared_bytes(M, d, kind) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
              al(sizeof(float) * S * n * T_pad);
     }
     case ODF_OP_DMMV: {
-      const int S1 = tile_default_splits(n, M, dp);
-      const int S2 = tile_default_splits(M, n, dp);
-      return prepared_bytes(n, d) + prepared_bytes(M, d) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
+      const int S1 = odf_tile_splits(n, M, d, kind);
+      const int S2 = odf_tile_splits(M, n, d, kind);
+      return prepared_bytes(n, d, kind) + prepared_bytes(M, d, kind) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
              2 * al(sizeof(float) * T_pad * round_up(n, 128)) + al(sizeof(float) * S1 * n * T_pad) +
              al(sizeof(float) * S2 * M * T_pad);
     }
     case ODF_OP_KMM:
-      return prepared_bytes(M, d);
+      return prepared_bytes(M, d, kind);
     case ODF_OP_PRECOND: {
       // potrf scratch: query needs a handle + device; use a generous closed form instead
       return al(sizeof(float) * (static_cast<size_t>(M) * 256 + (1u << 20))) + 256;
@@ -188,22 +210,23 @@ int odf_gauss_mmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int T_pad = tpad_of(T);
   if (T_pad < 0) return set_error(ODF_ERR_ARG, "T must be <= 32 per call");
-  const int64_t dp = round_up(d, 32), ldvt = round_up(M, 128);
+  const int64_t ldvt = round_up(M, 128);
+  const int kind = g_default_kind;
   Arena a(ws, ws_bytes);
   Prepared px, pc;
-  take_prepared(a, n, d, &px);
-  take_prepared(a, M, d, &pc);
+  take_prepared(a, n, d, kind, &px);
+  take_prepared(a, M, d, kind, &pc);
   float* vth = a.take<float>(T_pad * ldvt);
   float* vtl = a.take<float>(T_pad * ldvt);
-  const int S = tile_default_splits(n, M, dp);
+  const int S = odf_tile_splits(n, M, d, kind);
   float* partial = a.take<float>(static_cast<size_t>(S) * n * T_pad);
   if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_mmv: workspace too small");
   int rc;
-  if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, px.hi, px.lo, px.sqn, st))) return rc;
-  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, pc.hi, pc.lo, pc.sqn, st))) return rc;
+  if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, kind, px.hi, px.lo, px.sqn, px.opscale, st))) return rc;
+  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, kind, pc.hi, pc.lo, pc.sqn, pc.opscale, st))) return rc;
   if ((rc = split_rhs(V, M, T, ldv, 1.f, vth, vtl, ldvt, T_pad, st))) return rc;
-  if ((rc = odf_gauss_mmv_prepared(px.hi, px.lo, px.sqn, n, pc.hi, pc.lo, pc.sqn, M, dp, vth, vtl, ldvt, T_pad, S,
-                                   sigma, partial, stream)))
+  if ((rc = odf_gauss_mmv_prepared(kind, px.hi, px.lo, px.sqn, px.opscale, n, pc.hi, pc.lo, pc.sqn, pc.opscale, M, d,
+                                   vth, vtl, ldvt, T_pad, S, sigma, partial, stream)))
     return rc;
   return finish_rows(partial, S, n, T_pad, T, 1.f, nullptr, 0, out, ldo, st);
 }
@@ -215,34 +238,35 @@ int odf_gauss_dmmv(const float* X, int64_t n, int64_t ldx, const float* C, int64
   const int T_pad = tpad_of(T);
   if (T_pad < 0) return set_error(ODF_ERR_ARG, "T must be <= 32 per call");
   if (!V && !W) return set_error(ODF_ERR_ARG, "dmmv needs V or W");
-  const int64_t dp = round_up(d, 32), ldvt = round_up(M, 128), ldwt = round_up(n, 128);
+  const int64_t ldvt = round_up(M, 128), ldwt = round_up(n, 128);
+  const int kind = g_default_kind;
   Arena a(ws, ws_bytes);
   Prepared px, pc;
-  take_prepared(a, n, d, &px);
-  take_prepared(a, M, d, &pc);
+  take_prepared(a, n, d, kind, &px);
+  take_prepared(a, M, d, kind, &pc);
   float* vth = a.take<float>(T_pad * ldvt);
   float* vtl = a.take<float>(T_pad * ldvt);
   float* wth = a.take<float>(T_pad * ldwt);
   float* wtl = a.take<float>(T_pad * ldwt);
-  const int S1 = tile_default_splits(n, M, dp);
-  const int S2 = tile_default_splits(M, n, dp);
+  const int S1 = odf_tile_splits(n, M, d, kind);
+  const int S2 = odf_tile_splits(M, n, d, kind);
   float* part1 = a.take<float>(static_cast<size_t>(S1) * n * T_pad);
   float* part2 = a.take<float>(static_cast<size_t>(S2) * M * T_pad);
   if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_dmmv: workspace too small");
   int rc;
-  if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, px.hi, px.lo, px.sqn, st))) return rc;
-  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, pc.hi, pc.lo, pc.sqn, st))) return rc;
+  if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, kind, px.hi, px.lo, px.sqn, px.opscale, st))) return rc;
+  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, kind, pc.hi, pc.lo, pc.sqn, pc.opscale, st))) return rc;
   if (V) {
     if ((rc = split_rhs(V, M, T, ldv, 1.f, vth, vtl, ldvt, T_pad, st))) return rc;
-    if ((rc = odf_gauss_mmv_prepared(px.hi, px.lo, px.sqn, n, pc.hi, pc.lo, pc.sqn, M, dp, vth, vtl, ldvt, T_pad, S1,
-                                     sigma, part1, stream)))
+    if ((rc = odf_gauss_mmv_prepared(kind, px.hi, px.lo, px.sqn, px.opscale, n, pc.hi, pc.lo, pc.sqn, pc.opscale, M, d,
+                                     vth, vtl, ldvt, T_pad, S1, sigma, part1, stream)))
       return rc;
     if ((rc = finish_split(part1, S1, n, T_pad, T, 1.f, W, ldw, wth, wtl, ldwt, st))) return rc;
   } else {
     if ((rc = split_rhs(W, n, T, ldw, 1.f, wth, wtl, ldwt, T_pad, st))) return rc;
   }
-  if ((rc = odf_gauss_mmv_prepared(pc.hi, pc.lo, pc.sqn, M, px.hi, px.lo, px.sqn, n, dp, wth, wtl, ldwt, T_pad, S2,
-                                   sigma, part2, stream)))
+  if ((rc = odf_gauss_mmv_prepared(kind, pc.hi, pc.lo, pc.sqn, pc.opscale, M, px.hi, px.lo, px.sqn, px.opscale, n, d,
+                                   wth, wtl, ldwt, T_pad, S2, sigma, part2, stream)))
     return rc;
   return finish_rows(part2, S2, M, T_pad, T, 1.f, nullptr, 0, out, ldo, st);
 }
@@ -250,12 +274,13 @@ int odf_gauss_dmmv(const float* X, int64_t n, int64_t ldx, const float* C, int64
 int odf_gauss_kmm(const float* C, int64_t M, int64_t ldc, int64_t d, float sigma, float* K, int64_t ldk, void* ws,
                   size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int kind = g_default_kind;
   Arena a(ws, ws_bytes);
   Prepared pc;
-  if (!take_prepared(a, M, d, &pc)) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_kmm: workspace too small");
+  if (!take_prepared(a, M, d, kind, &pc)) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_kmm: workspace too small");
   int rc;
-  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, pc.hi, pc.lo, pc.sqn, st))) return rc;
-  return odf_gauss_kmm_prepared(pc.hi, pc.lo, pc.sqn, M, round_up(d, 32), sigma, K, ldk, stream);
+  if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, kind, pc.hi, pc.lo, pc.sqn, pc.opscale, st))) return rc;
+  return odf_gauss_kmm_prepared(kind, pc.hi, pc.lo, pc.sqn, pc.opscale, M, d, sigma, K, ldk, stream);
 }
 
 // ---------------------------------------------------------------- preconditioner
@@ -313,6 +338,29 @@ int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t 
                                  transposed ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, static_cast<int>(T),
                                  static_cast<int>(M), &one, Tri, static_cast<int>(M), B, static_cast<int>(ldb));
   if (s != CUBLAS_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "cublasStrsm failed");
+  return ODF_OK;
+}
+
+int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = set_identity(Inv, M, st))) return rc;
+  if ((rc = odf_precond_solve(Tri, M, Inv, M, M, ODF_SOLVE_T, stream))) return rc;
+  return zero_lower(Inv, M, st);      // exact zeros below the diagonal (TRSM leaves rounding dust there)
+}
+
+int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T, int64_t ldb,
+                      int transposed, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = ensure_handles(st))) return rc;
+  if (Bin == Bout) return set_error(ODF_ERR_ARG, "precond_apply is out of place");
+  // row-major Bout = op(Inv) Bin   <=>   column-major Bout' (T x M) = Bin' (T x M) * op'(Inv')
+  const float one = 1.f, zero = 0.f;
+  cublasStatus_t s = cublasSgemm(g_cublas, CUBLAS_OP_N, transposed ? CUBLAS_OP_T : CUBLAS_OP_N, static_cast<int>(T),
+                                 static_cast<int>(M), static_cast<int>(M), &one, Bin, static_cast<int>(ldb), Inv,
+                                 static_cast<int>(M), &zero, Bout, static_cast<int>(ldb));
+  if (s != CUBLAS_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "cublasSgemm (precond_apply) failed");
   return ODF_OK;
 }
 

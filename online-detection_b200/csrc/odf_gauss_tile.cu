@@ -15,12 +15,19 @@
 //     rows = centres, columns = data (the Gaussian kernel is symmetric, K(X,C)^T = K(C,X)).
 //   * K_MM for the preconditioner (store epilogue, MODE_STORE).
 //
-// x.c runs on the tensor cores as a 3xTF32 product: operands are pre-split (odf_vec.cu) into
-// hi = tf32(x), lo = tf32(x - hi) and the tile accumulates hi.hi + lo.hi + hi.lo in fp32 TMEM,
-// which restores fp32-grade distances.  The epilogue adds the norms, clamps at 0, applies exp2
-// and splits K the same way; K_hi overwrites the S accumulator in place and together with K_lo
-// feeds the second tensor-core contraction straight from TMEM (A operand in TMEM, V^T tiles
-// from shared memory), again as a 3xTF32 product.
+// x.c runs on the tensor cores as a 3-pass split product: operands are pre-split (odf_vec.cu) into
+// hi = rn11(x), lo = rn11(x - hi) (11-bit significands) and the tile accumulates
+// hi.hi + lo.hi + hi.lo in fp32 TMEM, which restores fp32-grade distances.  Two operand kinds share
+// the kernel (template): KIND_TF32 (hi/lo stored as tf32 in fp32 words, kind::tf32 MMAs, "3xTF32")
+// and KIND_F16 (hi/lo stored as fp16 after a power-of-two scaling of the point set, kind::f16
+// MMAs at twice the tf32 rate and half the operand bytes; same 2 x 11 significand bits).
+// The tensor core accumulates in fp32 with truncation, so a long chain of same-sign partial sums
+// drifts; every tile therefore starts from a rank-1 MMA that seeds the accumulator with
+// -|x_r|^2/2 (an extra k-block appended to the operand arrays by the pre-pass), which keeps the
+// running sums of near-neighbour pairs centred on zero: acc = x.c - |x|^2/2, D = |c|^2 - 2 acc.
+// The epilogue clamps D at 0, applies exp2 and splits K into tf32 hi/lo; K_hi overwrites the S
+// accumulator in place and together with K_lo feeds the second tensor-core contraction straight
+// from TMEM (A operand in TMEM, V^T tiles from shared memory), again as a 3xTF32 product.
 //
 // Warp roles (256 threads, 1 CTA / SM):
 //   warp 0  lane 0 : TMA producer for the operand pipeline (R_hi, R_lo, Q_hi, Q_lo k-blocks)
@@ -37,9 +44,9 @@ namespace {
 
 constexpr int BM = 128;                    // rows per tile (TMEM lanes)
 constexpr int BN = 128;                    // columns per tile
-constexpr int BK = 32;                     // fp32 elements per k-block (= one 128B swizzle atom)
+constexpr int BKB = 128;                   // bytes per k-block row (= one 128B swizzle atom)
 constexpr int NS = 3;                      // operand pipeline depth
-constexpr int TILE_BYTES = BM * BK * 4;    // 16 KB
+constexpr int TILE_BYTES = BM * BKB;        // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // R_hi, R_lo, Q_hi, Q_lo
 constexpr int MAX_TPAD = 32;
 constexpr int V_ATOM_BYTES_MAX = MAX_TPAD * 128;         // one [T_pad x 32] box
@@ -88,6 +95,7 @@ __device__ __forceinline__ WorkItem decode_item(const TileParams& p, int idx) {
 
 }  // namespace
 
+template <int KIND>
 __global__ void __launch_bounds__(256, 1)
 gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
                   const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
@@ -149,6 +157,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
   const int n_items = p.n_rowblocks * p.n_splits;
   const int KB = p.kblocks;
   const int T_pad = p.T_pad;
+  constexpr int BK = (KIND == KIND_F16) ? 64 : 32;      // elements per k-block
 
   if (warp == 0 && lane == 0) {
     // ======================= operand TMA producer =======================
@@ -158,15 +167,22 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
       const WorkItem w = decode_item(p, it);
       for (int j = w.jt0; j < w.jt1; ++j) {
         const int col0 = j * BN;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = -1; kb < KB; ++kb) {
           mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
           const uint32_t full = BAR(B_FULL + stage);
           const uint32_t dst = smem_u32(stage_base + stage * STAGE_BYTES);
-          mbar_arrive_expect_tx(full, STAGE_BYTES);
-          tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, kb * BK, w.row0);
-          tma_load_2d(dst + 1 * TILE_BYTES, &tmRl, full, kb * BK, w.row0);
-          tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, kb * BK, col0);
-          tma_load_2d(dst + 3 * TILE_BYTES, &tmQl, full, kb * BK, col0);
+          if (kb < 0) {
+            // seed block: rows bring [-|x|^2/2 hi, lo, 0...], columns bring [1, 1, 0...]
+            mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+            tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, KB * BK, w.row0);
+            tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, (KB + 1) * BK, col0);
+          } else {
+            mbar_arrive_expect_tx(full, STAGE_BYTES);
+            tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, kb * BK, w.row0);
+            tma_load_2d(dst + 1 * TILE_BYTES, &tmRl, full, kb * BK, w.row0);
+            tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, kb * BK, col0);
+            tma_load_2d(dst + 3 * TILE_BYTES, &tmQl, full, kb * BK, col0);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -191,7 +207,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
     }
   } else if (warp == 1 && lane == 0) {
     // ======================= MMA issuer =======================
-    const uint32_t idesc_s = make_idesc_tf32(BM, BN);
+    const uint32_t idesc_s = (KIND == KIND_F16) ? make_idesc_f16(BM, BN) : make_idesc_tf32(BM, BN);
     const uint32_t idesc_pv = make_idesc_tf32(BM, T_pad);
     const uint32_t atom_bytes = T_pad * 128;
     int stage = 0;
@@ -233,19 +249,25 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
       const WorkItem w = decode_item(p, it);
       for (int j = w.jt0; j < w.jt1; ++j) {
         const uint32_t t_s = tmem_base + ((n & 1) ? TM_S1 : TM_S0);
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = -1; kb < KB; ++kb) {
           mbar_wait(BAR(B_FULL + stage), phase);
           tc_fence_after();
           const uint32_t sb = smem_u32(stage_base + stage * STAGE_BYTES);
+          if (kb < 0) {
+            // rank-1 seed: acc = (-|x|^2/2) * 1   (first k-step of the seed block only)
+            mma_ss<KIND>(t_s, make_sdesc_sw128(sb + 0 * TILE_BYTES), make_sdesc_sw128(sb + 2 * TILE_BYTES),
+                         idesc_s, 0u);
+          } else {
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint64_t a_hi = make_sdesc_sw128(sb + 0 * TILE_BYTES + ks * 32);
-            const uint64_t a_lo = make_sdesc_sw128(sb + 1 * TILE_BYTES + ks * 32);
-            const uint64_t b_hi = make_sdesc_sw128(sb + 2 * TILE_BYTES + ks * 32);
-            const uint64_t b_lo = make_sdesc_sw128(sb + 3 * TILE_BYTES + ks * 32);
-            mma_tf32_ss(t_s, a_hi, b_hi, idesc_s, (kb | ks) ? 1u : 0u);
-            mma_tf32_ss(t_s, a_lo, b_hi, idesc_s, 1u);
-            mma_tf32_ss(t_s, a_hi, b_lo, idesc_s, 1u);
+            for (int ks = 0; ks < 4; ++ks) {       // 4 k-steps of 32 bytes per 128-byte k-block
+              const uint64_t a_hi = make_sdesc_sw128(sb + 0 * TILE_BYTES + ks * 32);
+              const uint64_t a_lo = make_sdesc_sw128(sb + 1 * TILE_BYTES + ks * 32);
+              const uint64_t b_hi = make_sdesc_sw128(sb + 2 * TILE_BYTES + ks * 32);
+              const uint64_t b_lo = make_sdesc_sw128(sb + 3 * TILE_BYTES + ks * 32);
+              mma_ss<KIND>(t_s, a_lo, b_hi, idesc_s, 1u);      // small terms first
+              mma_ss<KIND>(t_s, a_hi, b_lo, idesc_s, 1u);
+              mma_ss<KIND>(t_s, a_hi, b_hi, idesc_s, 1u);
+            }
           }
           tc_commit(BAR(B_EMPTY + stage));
           if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -265,12 +287,16 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
     const int row = q * 32 + lane;          // row inside the block
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float nsl2 = p.neg_scale_log2;
+    // operand scalings (powers of two written by the pre-pass; 1 for KIND_TF32)
+    const float s_r = __ldg(p.r_scale), s_q = __ldg(p.q_scale);
+    const float m2inv = -2.f / (s_r * s_q);        // acc -> -2 (x.c - rho |x|^2 / 2)
+    const float one_m_rho = 1.f - s_r / s_q;       // 0 when both point sets share a scale
     uint32_t n = 0;
     uint32_t item_cnt = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_cnt) {
       const WorkItem w = decode_item(p, it);
       const int grow = w.row0 + row;
-      const float rn = (grow < p.n_rows) ? __ldg(p.rnorm + grow) : 0.f;
+      const float rn = ((grow < p.n_rows) ? __ldg(p.rnorm + grow) : 0.f) * one_m_rho;
       for (int j = w.jt0; j < w.jt1; ++j, ++n) {
         const uint32_t b = n & 1;
         mbar_wait(BAR(B_SFULL + b), (n >> 1) & 1);
@@ -295,7 +321,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
             uint32_t lo[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              float d2 = fmaf(-2.f, __uint_as_float(s[c]), rn + qn[c]);
+              float d2 = fmaf(m2inv, __uint_as_float(s[c]), rn + qn[c]);
               d2 = fmaxf(d2, 0.f);
               const float kv = ex2_approx(d2 * nsl2);
               const float hi = tf32_rn(kv);
@@ -309,7 +335,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
             // MODE_STORE: write K straight to global (row-major, ld = ldo)
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              float d2 = fmaf(-2.f, __uint_as_float(s[c]), rn + qn[c]);
+              float d2 = fmaf(m2inv, __uint_as_float(s[c]), rn + qn[c]);
               d2 = fmaxf(d2, 0.f);
               s[c] = __float_as_uint(ex2_approx(d2 * nsl2));
             }
@@ -388,16 +414,18 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows x cols] with row pitch ld (elements); box = [box_rows x 32], 128B swizzle.
-int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld,
-             int box_rows) {
+// 2-D tensor [rows x cols] of fp32 (esize 4) or fp16 (esize 2) with row pitch ld (elements);
+// box = [box_rows x 128 bytes], 128B swizzle.
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld,
+             int box_rows, int esize = 4) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esize};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+  CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -422,7 +450,8 @@ int num_sms() {
 
 }  // namespace
 
-int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t d_pad) {
+// `row_bytes` = bytes of one point in ONE of the hi / lo arrays
+int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t row_bytes) {
   const int sms = num_sms();
   const int64_t n_rb = (n_rows + BM - 1) / BM;
   const int64_t n_ct = (n_cols + BN - 1) / BN;
@@ -430,7 +459,7 @@ int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t d_pad) {
   // (a) not enough row blocks to fill the machine a few times over: split the column range
   if (n_rb < 8 * sms) splits = (8 * sms + n_rb - 1) / n_rb;
   // (b) row blocks too fat for L2 when every SM streams its own: make ~12 CTAs share one
-  const int64_t rb_bytes = static_cast<int64_t>(BM) * d_pad * 8;
+  const int64_t rb_bytes = static_cast<int64_t>(BM) * row_bytes * 2;
   if (rb_bytes * sms > (48ll << 20) && splits < 12) splits = 12;
   // keep at least 4 column tiles per item so the pipeline fill/drain stays amortised
   const int64_t max_splits = n_ct >= 4 ? n_ct / 4 : 1;
@@ -443,22 +472,28 @@ int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t d_pad) {
 }
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
-  if (L.d_pad % BK != 0 || L.d_pad <= 0) return set_error(ODF_ERR_ARG, "d_pad must be a positive multiple of 32");
+  if (L.kind != KIND_TF32 && L.kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
+  const int64_t BK = kblock_elems(L.kind);
+  const int esize = L.kind == KIND_F16 ? 2 : 4;
+  const int64_t pitch = L.d_pad + 2 * BK;
+  if (L.d_pad % BK != 0 || L.d_pad <= 0) return set_error(ODF_ERR_ARG, "d_pad must be a positive multiple of the k-block width");
   if (L.n_rows <= 0 || L.n_cols <= 0) return set_error(ODF_ERR_ARG, "empty operand");
   if (L.mode == MODE_MMV && !(L.T_pad == 16 || L.T_pad == 32))
     return set_error(ODF_ERR_ARG, "T_pad must be 16 or 32");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gauss_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gauss_tile_kernel)");
     attr_set = true;
   }
   CUtensorMap mRh, mRl, mQh, mQl, mVh, mVl;
   int rc;
-  if ((rc = make_map(&mRh, L.r_hi, L.n_rows, L.d_pad, L.d_pad, BM))) return rc;
-  if ((rc = make_map(&mRl, L.r_lo, L.n_rows, L.d_pad, L.d_pad, BM))) return rc;
-  if ((rc = make_map(&mQh, L.q_hi, L.n_cols, L.d_pad, L.d_pad, BN))) return rc;
-  if ((rc = make_map(&mQl, L.q_lo, L.n_cols, L.d_pad, L.d_pad, BN))) return rc;
+  if ((rc = make_map(&mRh, L.r_hi, L.n_rows, pitch, pitch, BM, esize))) return rc;
+  if ((rc = make_map(&mRl, L.r_lo, L.n_rows, pitch, pitch, BM, esize))) return rc;
+  if ((rc = make_map(&mQh, L.q_hi, L.n_cols, pitch, pitch, BN, esize))) return rc;
+  if ((rc = make_map(&mQl, L.q_lo, L.n_cols, pitch, pitch, BN, esize))) return rc;
   if (L.mode == MODE_MMV) {
     if ((rc = make_map(&mVh, L.vt_hi, L.T_pad, L.ldvt, L.ldvt, L.T_pad))) return rc;
     if ((rc = make_map(&mVl, L.vt_lo, L.T_pad, L.ldvt, L.ldvt, L.T_pad))) return rc;
@@ -486,13 +521,18 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
   p.neg_scale_log2 = static_cast<float>(-1.4426950408889634 / (2.0 * double(L.sigma) * double(L.sigma)));
   p.rnorm = L.r_norm;
   p.qnorm = L.q_norm;
+  p.r_scale = L.r_scale;
+  p.q_scale = L.q_scale;
   p.out = L.out;
   p.ldo = L.ldo;
   p.split_stride = L.split_stride;
   p.store_vec4 = (L.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) ? 1 : 0;
   const int n_items = p.n_rowblocks * p.n_splits;
   const int grid = n_items < sms ? n_items : sms;
-  gauss_tile_kernel<<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  if (L.kind == KIND_F16)
+    gauss_tile_kernel<KIND_F16><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  else
+    gauss_tile_kernel<KIND_TF32><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "gauss_tile_kernel launch");
   return ODF_OK;

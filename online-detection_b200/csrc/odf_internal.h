@@ -9,17 +9,20 @@
 namespace odf {
 
 enum : int { MODE_MMV = 0, MODE_STORE = 1 };
+enum : int { KIND_TF32 = ODF_KIND_TF32, KIND_F16 = ODF_KIND_F16 };
 
 // Kernel-side parameters of the fused Gaussian tile (see odf_gauss_tile.cu).
 struct TileParams {
   int n_rows, n_cols;      // points on the row / column side
-  int kblocks;             // d_pad / 32
+  int kblocks;             // 128-byte k-blocks of real features (d_pad / 32 tf32 or d_pad / 64 fp16)
   int T_pad;               // padded number of right-hand sides (16 or 32)
   int mode;                // MODE_MMV or MODE_STORE
   int n_rowblocks, n_coltiles;
   int n_splits, tiles_per_split, group_rows;
   int store_vec4;
   float neg_scale_log2;    // -log2(e) / (2 sigma^2)
+  const float* r_scale;    // device scalars: power-of-two scaling of the row / column point set
+  const float* q_scale;
   const float* rnorm;      // |row point|^2, padded to a multiple of 128 entries
   const float* qnorm;      // |column point|^2, padded to a multiple of 128 entries
   float* out;              // MODE_MMV: partial slabs [n_splits][n_rows][T_pad]; MODE_STORE: K
@@ -29,11 +32,14 @@ struct TileParams {
 
 // Host-side launch description.
 struct TileLaunch {
-  const float *r_hi, *r_lo, *r_norm;
+  int kind;                    // KIND_TF32 or KIND_F16
+  const void *r_hi, *r_lo;
+  const float *r_norm, *r_scale;
   int64_t n_rows;
-  const float *q_hi, *q_lo, *q_norm;
+  const void *q_hi, *q_lo;
+  const float *q_norm, *q_scale;
   int64_t n_cols;
-  int64_t d_pad;
+  int64_t d_pad;               // padded feature count (multiple of the k-block width)
   const float *vt_hi, *vt_lo;  // [T_pad x ldvt], zero beyond n_cols
   int64_t ldvt;
   int T_pad;
@@ -46,12 +52,18 @@ struct TileLaunch {
 };
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream);
-int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t d_pad);
+int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t row_bytes);
 
 // error plumbing (thread-local last-error string behind odf_last_error())
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
 
+inline int64_t kblock_elems(int kind) { return kind == KIND_F16 ? 64 : 32; }
+// operand row pitch in elements: padded features + seed block + ones block
+inline int64_t operand_pitch(int64_t d, int kind) {
+  const int64_t bk = kblock_elems(kind);
+  return (d + bk - 1) / bk * bk + 2 * bk;
+}
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 }  // namespace odf

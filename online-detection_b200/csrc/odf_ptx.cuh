@@ -135,11 +135,35 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 operands, fp32 accumulate)
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND == 1) mma_f16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else mma_tf32_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+
 // Instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major (bit layout as in the
 // PTX ISA "Instruction descriptor" table: c_format[4,6) a_format[7,10) b_format[10,13)
 // a_major[15] b_major[16] n>>3 [17,23) m>>4 [24,29)).
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// kind::f16 with fp16 A/B (format 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor for a K-major operand stored as 128-byte rows with the

@@ -2,6 +2,8 @@
 // 3xTF32 split + norms), right-hand-side split/transposition, split-slab reduction and the
 // per-column conjugate-gradient vector updates.  All are coalesced, vectorised where the layout
 // allows it and reduction-order deterministic (no floating-point atomics).
+#include <cuda_fp16.h>
+
 #include "odf_ptx.cuh"
 #include "odf_internal.h"
 
@@ -16,12 +18,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------ prepare_points
-// One warp per row.  Reads X once (4 B/elem), writes hi and lo (8 B/elem) and one norm.
+// Pass A: one warp per row: |x'|^2 with x' = (x - mean) * scale, and the maximum over rows
+// (non-negative floats order like their bit patterns, so an integer atomicMax does it).
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-prepare_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx,
-               const float* __restrict__ mean, float scale, float* __restrict__ hi,
-               float* __restrict__ lo, int d_pad, float* __restrict__ sqn, int64_t n_pad) {
+rownorm_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx,
+               const float* __restrict__ mean, float scale, float* __restrict__ sqn, int64_t n_pad,
+               unsigned int* __restrict__ maxbits) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= n_pad) return;
@@ -30,10 +33,8 @@ prepare_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx,
     return;
   }
   const float* xr = X + row * ldx;
-  float* hr = hi + row * d_pad;
-  float* lr = lo + row * d_pad;
   double acc = 0.0;
-  for (int c = lane * 4; c < d_pad; c += 128) {
+  for (int c = lane * 4; c < d; c += 128) {
     float v[4];
     if (VEC && c + 3 < d) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
@@ -42,25 +43,107 @@ prepare_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx,
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = (c + k < d) ? __ldg(xr + c + k) : 0.f;
     }
-    float h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float x = v[k];
       if (c + k < d) {
+        float x = v[k];
         if (mean) x -= __ldg(mean + c + k);
         x *= scale;
-      } else {
-        x = 0.f;
+        acc += static_cast<double>(x) * static_cast<double>(x);
       }
-      h[k] = tf32_rn(x);
-      l[k] = tf32_rn(x - h[k]);
-      acc += static_cast<double>(x) * static_cast<double>(x);
     }
-    *reinterpret_cast<float4*>(hr + c) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(lr + c) = make_float4(l[0], l[1], l[2], l[3]);
   }
   acc = warp_sum(acc);
-  if (lane == 0) sqn[row] = static_cast<float>(acc);
+  if (lane == 0) {
+    const float f = static_cast<float>(acc);
+    sqn[row] = f;
+    atomicMax(maxbits, __float_as_uint(f));
+  }
+}
+
+// Power-of-two operand scaling for fp16 storage: s * max|x| lands in (128, 256], so that the seed
+// value s^2 |x|^2 / 2 stays below 2^15 and typical elements sit well inside fp16's normal range.
+__device__ __forceinline__ float f16_operand_scale(unsigned int maxbits) {
+  const float maxsq = __uint_as_float(maxbits);
+  if (!(maxsq > 0.f) || !isfinite(maxsq)) return 1.f;
+  float e = floorf(log2f(256.f * rsqrtf(maxsq)));
+  e = fminf(fmaxf(e, -60.f), 60.f);
+  return exp2f(e);
+}
+
+template <int KIND> struct OpElem;
+template <> struct OpElem<KIND_TF32> {
+  using type = float;
+  static __device__ __forceinline__ void split(float v, float& hi, float& lo) { hi = tf32_rn(v); lo = tf32_rn(v - hi); }
+};
+template <> struct OpElem<KIND_F16> {
+  using type = __half;
+  static __device__ __forceinline__ void split(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+  }
+};
+
+// Pass B: one warp per row writes the split operand row:
+//   [ features (d, zero padded to d_pad) | seed block: g_hi, g_lo, 0.. | ones block: 1, 1, 0.. ]
+// with g = -s^2 |x'|^2 / 2 (the rank-1 accumulator seed of the tile kernel).  Only `hi` carries the
+// two extra blocks.
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx, const float* __restrict__ mean,
+             float scale, typename OpElem<KIND>::type* __restrict__ hi,
+             typename OpElem<KIND>::type* __restrict__ lo, int d_pad, int pitch,
+             const float* __restrict__ sqn, float* __restrict__ opscale) {
+  using E = typename OpElem<KIND>::type;
+  constexpr int BK = (KIND == KIND_F16) ? 64 : 32;
+  const float s = (KIND == KIND_F16) ? f16_operand_scale(reinterpret_cast<const unsigned int*>(opscale)[1]) : 1.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) opscale[0] = s;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* xr = X + row * ldx;
+  E* hr = hi + row * pitch;
+  E* lr = lo + row * pitch;
+  const float g = -0.5f * __ldg(sqn + row) * s * s;
+  for (int c = lane * 4; c < pitch; c += 128) {
+    float v[4];
+    if (c < d_pad) {
+      if (VEC && c + 3 < d) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (c + k < d) ? __ldg(xr + c + k) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c + k < d) {
+          if (mean) v[k] -= __ldg(mean + c + k);
+          v[k] *= scale * s;
+        } else {
+          v[k] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = 0.f;
+      if (c == d_pad + BK) { v[0] = 1.f; v[1] = 1.f; }           // ones block
+    }
+    E h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) OpElem<KIND>::split(v[k], h[k], l[k]);
+    if (c == d_pad) {                                            // seed block: g_hi, g_lo
+      E gh, gl;
+      OpElem<KIND>::split(g, gh, gl);
+      h[0] = gh; h[1] = gl;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hr[c + k] = h[k];
+    if (c < d_pad) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lr[c + k] = l[k];
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -327,6 +410,16 @@ zero_lower_kernel(float* __restrict__ A, int64_t M) {
     A[r * M + c] = 0.f;
 }
 
+__global__ void __launch_bounds__(256)
+set_identity_kernel(float* __restrict__ A, int64_t M) {
+  const int64_t total = M * M;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / M;
+    A[i] = (i - r * M == r) ? 1.f : 0.f;
+  }
+}
+
 int grid_for(int64_t total, int block, int cap = 148 * 8) {
   int64_t g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -344,17 +437,29 @@ int check_launch(const char* what) {
 
 // ---- internal C++ entry points used by odf_api.cu ------------------------------------------
 int prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
-                   float* hi, float* lo, float* sqn, cudaStream_t st) {
+                   int kind, void* hi, void* lo, float* sqn, float* opscale, cudaStream_t st) {
   if (n <= 0 || d <= 0 || ldx < d) return set_error(ODF_ERR_ARG, "prepare_points: bad shape");
+  if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "prepare_points: unknown operand kind");
   const int64_t n_pad = round_up(n, 128);
-  const int d_pad = static_cast<int>(round_up(d, 32));
+  const int bk = static_cast<int>(kblock_elems(kind));
+  const int d_pad = static_cast<int>(round_up(d, bk));
+  const int pitch = d_pad + 2 * bk;
   const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  const unsigned grid = static_cast<unsigned>((n_pad + 7) / 8);
-  if (vec)
-    prepare_kernel<true><<<grid, 256, 0, st>>>(X, n, static_cast<int>(d), ldx, mean, scale, hi, lo, d_pad, sqn, n_pad);
-  else
-    prepare_kernel<false><<<grid, 256, 0, st>>>(X, n, static_cast<int>(d), ldx, mean, scale, hi, lo, d_pad, sqn, n_pad);
-  return check_launch("prepare_kernel");
+  cudaError_t e = cudaMemsetAsync(opscale, 0, 2 * sizeof(float), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "prepare_points: memset");
+  unsigned int* maxbits = reinterpret_cast<unsigned int*>(opscale) + 1;
+  const unsigned gridA = static_cast<unsigned>((n_pad + 7) / 8), gridB = static_cast<unsigned>((n + 7) / 8);
+  const int di = static_cast<int>(d);
+  if (vec) rownorm_kernel<true><<<gridA, 256, 0, st>>>(X, n, di, ldx, mean, scale, sqn, n_pad, maxbits);
+  else rownorm_kernel<false><<<gridA, 256, 0, st>>>(X, n, di, ldx, mean, scale, sqn, n_pad, maxbits);
+  if (kind == KIND_F16) {
+    if (vec) split_kernel<KIND_F16, true><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<__half*>(hi), static_cast<__half*>(lo), d_pad, pitch, sqn, opscale);
+    else split_kernel<KIND_F16, false><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<__half*>(hi), static_cast<__half*>(lo), d_pad, pitch, sqn, opscale);
+  } else {
+    if (vec) split_kernel<KIND_TF32, true><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<float*>(hi), static_cast<float*>(lo), d_pad, pitch, sqn, opscale);
+    else split_kernel<KIND_TF32, false><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<float*>(hi), static_cast<float*>(lo), d_pad, pitch, sqn, opscale);
+  }
+  return check_launch("prepare kernels");
 }
 
 int zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale, cudaStream_t st) {
@@ -441,6 +546,10 @@ int axpby(float* out, float alpha, const float* A, float beta, const float* Bm, 
 int add_diag(float* A, int64_t M, float v, cudaStream_t st) {
   add_diag_kernel<<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(A, M, v);
   return check_launch("add_diag");
+}
+int set_identity(float* A, int64_t M, cudaStream_t st) {
+  set_identity_kernel<<<grid_for(M * M, 256, 148 * 16), 256, 0, st>>>(A, M);
+  return check_launch("set_identity");
 }
 int zero_lower(float* A, int64_t M, cudaStream_t st) {
   dim3 grid(8, static_cast<unsigned>(M));

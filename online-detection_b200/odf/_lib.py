@@ -16,19 +16,22 @@ c_sz = ctypes.c_size_t
 SIGNATURES = {
     "odf_last_error": (ctypes.c_char_p, []),
     "odf_version": (c_int, []),
-    "odf_pad_dim": (c_i64, [c_i64]),
+    "odf_set_default_kind": (c_int, [c_int]),
+    "odf_default_kind": (c_int, []),
+    "odf_operand_pitch": (c_i64, [c_i64, c_int]),
+    "odf_operand_bytes": (c_i64, [c_i64, c_i64, c_int]),
     "odf_pad_rows": (c_i64, [c_i64]),
     "odf_tpad": (c_int, [c_i64]),
-    "odf_tile_splits": (c_int, [c_i64, c_i64, c_i64]),
-    "odf_prepare_points": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_f, c_fp, c_fp, c_fp, c_fp]),
+    "odf_tile_splits": (c_int, [c_i64, c_i64, c_i64, c_int]),
+    "odf_prepare_points": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "odf_zscore": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_f, c_fp]),
     "odf_split_rhs": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_i64, c_int, c_fp]),
-    "odf_gauss_mmv_prepared": (c_int, [c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_i64, c_i64,
+    "odf_gauss_mmv_prepared": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64,
                                        c_fp, c_fp, c_i64, c_int, c_int, c_f, c_fp, c_fp]),
     "odf_finish_rows": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_i64, c_fp]),
     "odf_finish_split": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_fp,
                                  c_i64, c_fp]),
-    "odf_gauss_kmm_prepared": (c_int, [c_fp, c_fp, c_fp, c_i64, c_i64, c_f, c_fp, c_i64, c_fp]),
+    "odf_gauss_kmm_prepared": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64, c_f, c_fp, c_i64, c_fp]),
     "odf_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_i64, c_i64]),
     "odf_gauss_mmv": (c_int, [c_fp, c_i64, c_i64, c_fp, c_i64, c_i64, c_i64, c_fp, c_i64, c_i64, c_f,
                               c_fp, c_i64, c_fp, c_sz, c_fp]),
@@ -37,6 +40,8 @@ SIGNATURES = {
     "odf_gauss_kmm": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_i64, c_fp, c_sz, c_fp]),
     "odf_precond_init": (c_int, [c_fp, c_fp, c_i64, c_f, c_f, c_fp, c_sz, c_fp]),
     "odf_precond_solve": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_fp]),
+    "odf_precond_invert": (c_int, [c_fp, c_fp, c_i64, c_fp]),
+    "odf_precond_apply": (c_int, [c_fp, c_i64, c_fp, c_fp, c_i64, c_i64, c_int, c_fp]),
     "odf_cg_init": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_sz, c_fp]),
     "odf_cg_alpha": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_sz, c_fp]),
     "odf_cg_axpy_a": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp]),
@@ -48,6 +53,8 @@ SIGNATURES = {
 }
 
 ODF_OP_MMV, ODF_OP_DMMV, ODF_OP_KMM, ODF_OP_PRECOND = 0, 1, 2, 3
+ODF_KIND_TF32, ODF_KIND_F16 = 0, 1
+KIND_NAMES = {"tf32": ODF_KIND_TF32, "f16": ODF_KIND_F16}
 ODF_SOLVE_T, ODF_SOLVE_TT, ODF_SOLVE_A, ODF_SOLVE_AT = 0, 1, 2, 3
 
 

@@ -28,7 +28,7 @@ class FalkonOptions:
     """Subset of falkon.options.FalkonOptions the reference sets (…incore.py:56)."""
 
     def __init__(self, cg_tolerance=1e-7, cg_full_gradient_every=10, cg_epsilon_32=1e-7, pc_epsilon_32=1e-5,
-                 debug=False, **ignored):
+                 debug=False, operand_kind=None, **ignored):
         # ignored upstream knobs: keops_active, min_cuda_iter_size_32/64, min_cuda_pc_size_32/64,
         # store_kernel_d_threshold, use_cpu, no_single_kernel … (placement / caching choices that
         # have no meaning here: everything runs on the GPU and K_nm is never materialised)
@@ -37,6 +37,12 @@ class FalkonOptions:
         self.cg_epsilon_32 = cg_epsilon_32
         self.pc_epsilon_32 = pc_epsilon_32
         self.debug = debug
+        # how the fused tile stores its split operands: "f16" (default: scaled fp16 hi/lo, kind::f16
+        # MMAs) or "tf32" (tf32 hi/lo in fp32 words, kind::tf32 MMAs); both carry 2 x 11 bits
+        self.operand_kind = operand_kind
+        # "inverse": apply T^-1 / A^-1 as GEMMs with explicit inverses built once per fit (default);
+        # "trsm": four triangular solves per CG iteration, as upstream does
+        self.precond_apply = ignored.pop("precond_apply", "inverse")
         self.ignored = dict(ignored)
 
 
@@ -48,6 +54,15 @@ class GaussianKernel:
     def __init__(self, sigma, opt=None):
         self.sigma = float(sigma)
         self.opt = opt
+
+    def _kind(self):
+        return getattr(self.opt, "operand_kind", None) if self.opt is not None else None
+
+    def _prep(self, X, like=None):
+        if isinstance(X, ops.Prepared):
+            return X
+        kind = like.kind if isinstance(like, ops.Prepared) else self._kind()
+        return ops.Prepared(X, kind=kind)
 
     def __repr__(self):
         return "GaussianKernel(sigma=%g)" % self.sigma
@@ -63,8 +78,8 @@ class GaussianKernel:
             out = torch.empty((n, T), dtype=torch.float32, device=v.device)
         if n == 0:
             return out[:, 0] if squeeze else out
-        rows = X1 if isinstance(X1, ops.Prepared) else ops.Prepared(X1)
-        cols = X2 if isinstance(X2, ops.Prepared) else ops.Prepared(X2)
+        cols = self._prep(X2, like=X1)
+        rows = self._prep(X1, like=cols)
         ops.mmv_into(rows, cols, v, self.sigma, out)
         return out[:, 0] if squeeze else out
 
@@ -77,8 +92,8 @@ class GaussianKernel:
         dev = (v if v is not None else w).device
         if out is None:
             out = torch.empty((M, T), dtype=torch.float32, device=dev)
-        rows = X1 if isinstance(X1, ops.Prepared) else ops.Prepared(X1)
-        cols = X2 if isinstance(X2, ops.Prepared) else ops.Prepared(X2)
+        cols = self._prep(X2, like=X1)
+        rows = self._prep(X1, like=cols)
         sw = ops.Sweeper(rows, cols, self.sigma, min(T, 32))
         for t0 in range(0, T, 32):
             t1 = min(T, t0 + 32)
@@ -90,8 +105,7 @@ class GaussianKernel:
     def __call__(self, X1, X2=None, out=None, opt=None):
         if X2 is not None and X2 is not X1:
             raise NotImplementedError("only the symmetric K(X, X) block is on the hot path")
-        prep = X1 if isinstance(X1, ops.Prepared) else ops.Prepared(X1)
-        return ops.kmm(prep, self.sigma, out)
+        return ops.kmm(self._prep(X1), self.sigma, out)
 
 
 def _dist_info(group):
@@ -124,6 +138,30 @@ class _Timer:
         if self.cuda:
             return self.marks[i].elapsed_time(self.marks[j])
         return (self.marks[j] - self.marks[i]) * 1e3
+
+
+class _TriFactor:
+    """Upper-triangular factor applied by triangular solves (cuBLAS TRSM)."""
+
+    def __init__(self, be, Tri):
+        self.be, self.Tri = be, Tri
+
+    def solve(self, b, out, transposed):
+        out.copy_(b)
+        first = self.be.precond_solve_      # `which` only selects plain / transposed
+        first(self.Tri, out, SOLVE_TT if transposed else SOLVE_T)
+        return out
+
+
+class _InvFactor:
+    """Upper-triangular factor applied through its explicit inverse (one GEMM per application)."""
+
+    def __init__(self, be, Tri):
+        self.be = be
+        self.Inv = be.precond_invert(Tri)
+
+    def solve(self, b, out, transposed):
+        return self.be.precond_apply(self.Inv, b, out, transposed)
 
 
 class Falkon:
@@ -214,15 +252,21 @@ class Falkon:
             raise ValueError("fit needs at least one row")
 
         zs = () if zscore is None else (zscore[0], float(zscore[1]))
-        pc = be.Prepared(centres, *zs)
-        px = be.Prepared(X, *zs) if n_local > 0 else None
-        if zs:
+        kind = opt.operand_kind
+        zs = zs if zs else (None, 1.0)
+        pc = be.Prepared(centres, zs[0], zs[1], kind=kind)
+        px = be.Prepared(X, zs[0], zs[1], kind=kind) if n_local > 0 else None
+        if zscore is not None:
             centres = be.zscore_(centres.clone(), zs[0], zs[1])     # ny_points_ live in normalised space
         tm.mark()
 
         # ---- preconditioner (built once per fit, replicated on every rank) --------------------
         Kmm = be.kmm(pc, sigma)
         Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
+        if opt.precond_apply == "inverse":
+            Tm, Am = _InvFactor(be, Tm), _InvFactor(be, Am)
+        else:
+            Tm, Am = _TriFactor(be, Tm), _TriFactor(be, Am)
         tm.mark()
 
         alpha = torch.empty((M, T), dtype=torch.float32, device=dev)
@@ -250,7 +294,7 @@ class Falkon:
         eps, tol = opt.cg_epsilon_32, opt.cg_tolerance
         sw = be.Sweeper(px, pc, sigma, T) if px is not None else None
         new = lambda: torch.empty((M, T), dtype=torch.float32, device=dev)  # noqa: E731
-        B, R, P, AP, beta, v, u, c, H = new(), new(), new(), new(), new(), new(), new(), new(), new()
+        B, R, P, AP, beta, v, u, c, H, H2 = (new() for _ in range(10))
         self._sweeps = 0
 
         def sweep(vv, ww, out, w_scale=1.0):
@@ -264,20 +308,17 @@ class Falkon:
             self._sweeps += 1
             return out
 
-        # B = apply_t(K_nm^T (Y / N))
-        sweep(None, Yb, B, 1.0 / N)
-        be.precond_solve_(Tm, B, SOLVE_TT)
-        be.precond_solve_(Am, B, SOLVE_AT)
+        # B = apply_t(K_nm^T (Y / N)) = A^-T T^-T K_nm^T (Y / N)
+        sweep(None, Yb, c, 1.0 / N)
+        Am.solve(Tm.solve(c, u, True), B, True)
 
         def op(s, out):
-            v.copy_(s)
-            be.precond_solve_(Am, v, SOLVE_A)        # v = A^-1 s
-            u.copy_(v)
-            be.precond_solve_(Tm, u, SOLVE_T)        # u = T^-1 v
+            Am.solve(s, v, False)                    # v = A^-1 s
+            Tm.solve(v, u, False)                    # u = T^-1 v
             sweep(u, None, c)                        # c = K_nm^T K_nm u  (all ranks)
-            be.precond_solve_(Tm, c, SOLVE_TT)       # T^-T c
-            be.axpby(out, 1.0 / N, c, lam, v)        # c / N + lam v
-            be.precond_solve_(Am, out, SOLVE_AT)
+            Tm.solve(c, u, True)                     # T^-T c
+            be.axpby(H2, 1.0 / N, u, lam, v)         # c / N + lam v
+            Am.solve(H2, out, True)
             return out
 
         beta.zero_()
@@ -315,16 +356,16 @@ class Falkon:
                 flag_ev.record()
             done = i + 1
         # alpha = T^-1 A^-1 beta
-        be.precond_solve_(Am, beta, SOLVE_A)
-        be.precond_solve_(Tm, beta, SOLVE_T)
-        alpha_out.copy_(beta)
+        Tm.solve(Am.solve(beta, v, False), u, False)
+        alpha_out.copy_(u)
         return done
 
     # ------------------------------------------------------------------ predict
     def _centres_prepared(self):
         be = self._be
         if self._prep_cache is None or self._prep_cache.hi.device != self.ny_points_.device:
-            object.__setattr__(self, "_prep_cache", be.Prepared(self.ny_points_.to(torch.float32)))
+            object.__setattr__(self, "_prep_cache", be.Prepared(self.ny_points_.to(torch.float32),
+                                                                 kind=self.options.operand_kind))
         return self._prep_cache
 
     def predict(self, X, y=None):
@@ -335,7 +376,8 @@ class Falkon:
         out = torch.empty((X.shape[0], alpha.shape[1]), dtype=torch.float32, device=X.device)
         if X.shape[0] == 0:
             return out
-        be.mmv_into(be.Prepared(X.to(torch.float32)), self._centres_prepared(), alpha.to(torch.float32),
+        pc = self._centres_prepared()
+        be.mmv_into(be.Prepared(X.to(torch.float32), kind=getattr(pc, "kind", None)), pc, alpha.to(torch.float32),
                     self.kernel.sigma, out)
         return out
 

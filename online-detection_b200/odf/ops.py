@@ -45,28 +45,46 @@ def _rowmajor(t):
     return t, (t.stride(0) if t.dim() == 2 else t.shape[-1])
 
 
+DEFAULT_KIND = None     # None -> the library default (odf_default_kind(): fp16-scaled split)
+
+
+def resolve_kind(kind=None):
+    if kind is None:
+        kind = DEFAULT_KIND
+    if kind is None:
+        return int(_lib.load().odf_default_kind())
+    if isinstance(kind, str):
+        return _lib.KIND_NAMES[kind.lower()]
+    return int(kind)
+
+
 class Prepared:
-    """3xTF32 operand form of a point set: hi/lo [n x d_pad] and squared norms (odf_prepare_points)."""
+    """Split operand form of a point set (odf_prepare_points): hi/lo arrays of
+    [n x odf_operand_pitch(d, kind)] tf32-in-fp32 or scaled-fp16 elements, squared norms, and the
+    power-of-two operand scale on the device."""
 
-    __slots__ = ("hi", "lo", "sqn", "n", "d", "d_pad")
+    __slots__ = ("hi", "lo", "sqn", "opscale", "n", "d", "kind", "pitch")
 
-    def __init__(self, X, mean=None, scale=1.0):
+    def __init__(self, X, mean=None, scale=1.0, kind=None):
         L = _lib.load()
         X = _req(X, "X", 2)
         X, ldx = _rowmajor(X)
         self.n, self.d = int(X.shape[0]), int(X.shape[1])
         if self.n == 0:
             raise ValueError("empty point set")
-        self.d_pad = int(L.odf_pad_dim(self.d))
+        self.kind = resolve_kind(kind)
+        self.pitch = int(L.odf_operand_pitch(self.d, self.kind))
         dev = X.device
-        self.hi = torch.empty((self.n, self.d_pad), dtype=torch.float32, device=dev)
-        self.lo = torch.empty((self.n, self.d_pad), dtype=torch.float32, device=dev)
+        edt = torch.float16 if self.kind == _lib.ODF_KIND_F16 else torch.float32
+        self.hi = torch.empty((self.n, self.pitch), dtype=edt, device=dev)
+        self.lo = torch.empty((self.n, self.pitch), dtype=edt, device=dev)
         self.sqn = torch.empty((int(L.odf_pad_rows(self.n)),), dtype=torch.float32, device=dev)
+        self.opscale = torch.empty((2,), dtype=torch.float32, device=dev)
         if mean is not None:
             mean = _req(mean, "mean").contiguous()
-        check(L.odf_prepare_points(ptr(X), self.n, self.d, ldx, ptr(mean), float(scale), ptr(self.hi),
-                                   ptr(self.lo), ptr(self.sqn), _stream()), "odf_prepare_points")
-        _count(1)
+        check(L.odf_prepare_points(ptr(X), self.n, self.d, ldx, ptr(mean), float(scale), self.kind, ptr(self.hi),
+                                   ptr(self.lo), ptr(self.sqn), ptr(self.opscale), _stream()), "odf_prepare_points")
+        _count(2)
 
 
 class SplitRhs:
@@ -94,28 +112,29 @@ class SplitRhs:
         return self
 
 
-def tile_splits(n_rows, n_cols, d):
-    return int(_lib.load().odf_tile_splits(n_rows, n_cols, d))
+def tile_splits(n_rows, n_cols, d, kind):
+    return int(_lib.load().odf_tile_splits(n_rows, n_cols, d, kind))
 
 
 def alloc_partial(rows, cols, T_pad, device):
     """Partial-slab buffer for mmv_partial(rows, cols, ...)."""
-    S = tile_splits(rows.n, cols.n, rows.d)
+    S = tile_splits(rows.n, cols.n, rows.d, rows.kind)
     return torch.empty((S, rows.n, T_pad), dtype=torch.float32, device=device)
 
 
 def mmv_partial(rows, cols, rhs, sigma, partial):
     """partial[s] = K(rows, cols restricted to split s) @ rhs  — the fused tcgen05 tile."""
     L = _lib.load()
-    assert rows.d_pad == cols.d_pad and rhs.m == cols.n
+    assert rows.d == cols.d and rows.kind == cols.kind and rhs.m == cols.n
     S = int(partial.shape[0])
     ev = None
     if TILE_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    check(L.odf_gauss_mmv_prepared(ptr(rows.hi), ptr(rows.lo), ptr(rows.sqn), rows.n, ptr(cols.hi), ptr(cols.lo),
-                                   ptr(cols.sqn), cols.n, rows.d_pad, ptr(rhs.hi), ptr(rhs.lo), rhs.ld, rhs.T_pad,
-                                   S, float(sigma), ptr(partial), _stream()), "odf_gauss_mmv_prepared")
+    check(L.odf_gauss_mmv_prepared(rows.kind, ptr(rows.hi), ptr(rows.lo), ptr(rows.sqn), ptr(rows.opscale), rows.n,
+                                   ptr(cols.hi), ptr(cols.lo), ptr(cols.sqn), ptr(cols.opscale), cols.n, rows.d,
+                                   ptr(rhs.hi), ptr(rhs.lo), rhs.ld, rhs.T_pad, S, float(sigma), ptr(partial),
+                                   _stream()), "odf_gauss_mmv_prepared")
     if ev is not None:
         ev[1].record()
         TILE_EVENTS.append((ev[0], ev[1], rows.n, cols.n, rows.d, rhs.T))
@@ -153,8 +172,8 @@ def kmm(prep, sigma, out=None):
     M = prep.n
     if out is None:
         out = torch.empty((M, M), dtype=torch.float32, device=prep.hi.device)
-    check(L.odf_gauss_kmm_prepared(ptr(prep.hi), ptr(prep.lo), ptr(prep.sqn), M, prep.d_pad, float(sigma), ptr(out),
-                                   out.stride(0), _stream()), "odf_gauss_kmm_prepared")
+    check(L.odf_gauss_kmm_prepared(prep.kind, ptr(prep.hi), ptr(prep.lo), ptr(prep.sqn), ptr(prep.opscale), M, prep.d,
+                                   float(sigma), ptr(out), out.stride(0), _stream()), "odf_gauss_kmm_prepared")
     _count(1)
     return out
 
@@ -189,6 +208,24 @@ def precond_solve_(Tri, B, which):
     check(L.odf_precond_solve(ptr(Tri), Tri.shape[0], ptr(B), B.shape[1], B.stride(0), int(which), _stream()),
           "odf_precond_solve")
     return B
+
+
+def precond_invert(Tri):
+    """Explicit inverse of an upper-triangular factor (one TRSM against the identity)."""
+    L = _lib.load()
+    Inv = torch.empty_like(Tri)
+    check(L.odf_precond_invert(ptr(Tri), ptr(Inv), Tri.shape[0], _stream()), "odf_precond_invert")
+    _count(2)
+    return Inv
+
+
+def precond_apply(Inv, Bin, Bout, transposed):
+    """Bout = Inv @ Bin (or Inv^T @ Bin): a bandwidth-bound GEMM instead of a triangular solve."""
+    L = _lib.load()
+    assert Bin.stride(1) == 1 and Bout.stride(1) == 1 and Bin.stride(0) == Bout.stride(0)
+    check(L.odf_precond_apply(ptr(Inv), Inv.shape[0], ptr(Bin), ptr(Bout), Bin.shape[1], Bin.stride(0),
+                              1 if transposed else 0, _stream()), "odf_precond_apply")
+    return Bout
 
 
 # ---- CG vector kernels ------------------------------------------------------------------------

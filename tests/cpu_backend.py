@@ -9,13 +9,13 @@ DT = torch.float64
 
 
 class Prepared:
-    def __init__(self, X, mean=None, scale=1.0):
+    def __init__(self, X, mean=None, scale=1.0, kind=None):
         Xp = X.to(DT)
         if mean is not None:
             Xp = Xp - mean.to(DT)
         self.X = Xp * scale
         self.n, self.d = X.shape
-        self.d_pad = self.d
+        self.kind = 0
         self.hi = X          # only .device is consulted
 
 
@@ -35,6 +35,15 @@ def precond_solve_(Tri, B, which):
     sol = torch.linalg.solve_triangular(Tri.T if tr else Tri, B.to(DT), upper=not tr)
     B.copy_(sol.to(B.dtype))
     return B
+
+
+def precond_invert(Tri):
+    return torch.linalg.solve_triangular(Tri, torch.eye(Tri.shape[0], dtype=Tri.dtype), upper=True)
+
+
+def precond_apply(Inv, Bin, Bout, transposed):
+    Bout.copy_(((Inv.T if transposed else Inv) @ Bin.to(Inv.dtype)).to(Bout.dtype))
+    return Bout
 
 
 class Sweeper:

@@ -39,12 +39,15 @@ def test_header_is_plain_c(tmp_path):
 
 
 def test_layout_helpers(lib):
-    assert lib.odf_pad_dim(1) == 32 and lib.odf_pad_dim(1024) == 1024 and lib.odf_pad_dim(1025) == 1056
+    assert lib.odf_operand_pitch(1, 0) == 96 and lib.odf_operand_pitch(1024, 0) == 1088
+    assert lib.odf_operand_pitch(1, 1) == 192 and lib.odf_operand_pitch(1024, 1) == 1152 and lib.odf_operand_pitch(1025, 1) == 1216
+    assert lib.odf_operand_bytes(10, 1024, 1) == 10 * 1152 * 2 and lib.odf_operand_bytes(10, 1024, 0) == 10 * 1088 * 4
+    assert lib.odf_default_kind() in (0, 1) and lib.odf_set_default_kind(7) != 0
     assert lib.odf_pad_rows(1) == 128 and lib.odf_pad_rows(128) == 128 and lib.odf_pad_rows(129) == 256
     assert lib.odf_tpad(1) == 16 and lib.odf_tpad(16) == 16 and lib.odf_tpad(17) == 32 and lib.odf_tpad(33) == -1
     assert lib.odf_version() >= 100
     for (n, m, d) in [(128, 128, 32), (1000000, 10000, 1024), (10000, 1000000, 1024), (300, 70000, 256)]:
-        s = lib.odf_tile_splits(n, m, d)
+        s = lib.odf_tile_splits(n, m, d, 1)
         tiles = (m + 127) // 128
         per = (tiles + s - 1) // s
         assert s >= 1 and (tiles + per - 1) // per == s        # no empty split
