@@ -85,6 +85,21 @@ int odf_gauss_mmv_prepared(int kind, const void* r_hi, const void* r_lo, const f
                            int64_t n_cols, int64_t d, const float* vt_hi, const float* vt_lo,
                            int64_t ldvt, int T_pad, int n_splits, float sigma, float* partial,
                            void* stream);
+/* Same as odf_gauss_mmv_prepared, and additionally spills the K tiles (fp32, exactly the K_hi + K_lo
+ * the contraction used) into the transient row panel P [n_rows x ldp], ldp >= odf_pad_rows(n_cols),
+ * for odf_panel_tmm.  The panel covers one launch (a chunk of rows), never the whole K_nm.      */
+int odf_gauss_mmv_prepared_spill(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
+                                 const float* r_opscale, int64_t n_rows, const void* q_hi,
+                                 const void* q_lo, const float* q_sqnorm, const float* q_opscale,
+                                 int64_t n_cols, int64_t d, const float* vt_hi, const float* vt_lo,
+                                 int64_t ldvt, int T_pad, int n_splits, float sigma, float* partial,
+                                 float* panel, int64_t ldp, void* stream);
+/* out_partial[s][c][0..T_pad) = sum over the rows of split s of P[r][c] * W[r][0..T_pad):
+ * the K_blk^T w half of GaussianKernel.dmmv on a spilled panel (fp32 FMA, HBM-streaming).
+ * W is [n_rows x T_pad] (zero padded columns); n_splits = odf_panel_splits(n_rows, M).           */
+int odf_panel_splits(int64_t n_rows, int64_t M);
+int odf_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, int64_t M, int T_pad,
+                  int n_splits, float* out_partial, void* stream);
 /* out[r, t] = scale * sum_s partial[s][r][t] + addend[r, t]   (addend may be NULL) */
 int odf_finish_rows(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T,
                     float scale, const float* addend, int64_t ld_add, float* out, int64_t ldo,

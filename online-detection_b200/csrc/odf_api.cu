@@ -140,6 +140,21 @@ int odf_gauss_mmv_prepared(int kind, const void* r_hi, const void* r_lo, const f
                            const float* q_sqnorm, const float* q_opscale, int64_t n_cols, int64_t d,
                            const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad, int n_splits,
                            float sigma, float* partial, void* stream) {
+  return odf_gauss_mmv_prepared_spill(kind, r_hi, r_lo, r_sqnorm, r_opscale, n_rows, q_hi, q_lo, q_sqnorm, q_opscale,
+                                      n_cols, d, vt_hi, vt_lo, ldvt, T_pad, n_splits, sigma, partial, nullptr, 0, stream);
+}
+
+int odf_panel_splits(int64_t n_rows, int64_t M) { return panel_splits(n_rows, M); }
+int odf_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, int64_t M, int T_pad, int n_splits,
+                  float* out_partial, void* stream) {
+  return launch_panel_tmm(P, ldp, W, n_rows, M, T_pad, n_splits, out_partial, static_cast<cudaStream_t>(stream));
+}
+
+int odf_gauss_mmv_prepared_spill(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
+                                 const float* r_opscale, int64_t n_rows, const void* q_hi, const void* q_lo,
+                                 const float* q_sqnorm, const float* q_opscale, int64_t n_cols, int64_t d,
+                                 const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad, int n_splits,
+                                 float sigma, float* partial, float* panel, int64_t ldp, void* stream) {
   if (!(sigma > 0.f)) return set_error(ODF_ERR_ARG, "sigma must be positive");
   if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
   TileLaunch L{};
@@ -149,6 +164,7 @@ int odf_gauss_mmv_prepared(int kind, const void* r_hi, const void* r_lo, const f
   L.d_pad = round_up(d, kblock_elems(kind)); L.vt_hi = vt_hi; L.vt_lo = vt_lo; L.ldvt = ldvt; L.T_pad = T_pad;
   L.mode = MODE_MMV; L.n_splits = n_splits; L.sigma = sigma;
   L.out = partial; L.ldo = T_pad; L.split_stride = n_rows * T_pad;
+  L.panel = panel; L.ldpanel = ldp;
   return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
 }
 

@@ -331,6 +331,19 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
             if (ch == 0 && n > 0) mbar_wait(BAR(B_PVDONE), (n - 1) & 1);  // K_lo buffer free
             tmem_st32(t_s + ch * 32, s);
             tmem_st32(t_lo + ch * 32, lo);
+            if (p.panel != nullptr && grow < p.n_rows) {
+              // spill K = K_hi + K_lo (exactly what the contraction above uses) to the row panel
+              float* prow = p.panel + static_cast<int64_t>(grow) * p.ldpanel + col0 + ch * 32;
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                float4 t;
+                t.x = __uint_as_float(s[4 * v + 0]) + __uint_as_float(lo[4 * v + 0]);
+                t.y = __uint_as_float(s[4 * v + 1]) + __uint_as_float(lo[4 * v + 1]);
+                t.z = __uint_as_float(s[4 * v + 2]) + __uint_as_float(lo[4 * v + 2]);
+                t.w = __uint_as_float(s[4 * v + 3]) + __uint_as_float(lo[4 * v + 3]);
+                *reinterpret_cast<float4*>(prow + 4 * v) = t;
+              }
+            }
           } else {
             // MODE_STORE: write K straight to global (row-major, ld = ldo)
 #pragma unroll
@@ -526,6 +539,11 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
   p.out = L.out;
   p.ldo = L.ldo;
   p.split_stride = L.split_stride;
+  p.panel = L.panel;
+  p.ldpanel = L.ldpanel;
+  if (L.panel != nullptr && (L.mode != MODE_MMV || L.ldpanel < static_cast<int64_t>(p.n_coltiles) * BN ||
+                             L.ldpanel % 4 != 0 || (reinterpret_cast<uintptr_t>(L.panel) & 15) != 0))
+    return set_error(ODF_ERR_ARG, "panel must be 16-byte aligned with pitch >= round_up(n_cols, 128)");
   p.store_vec4 = (L.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) ? 1 : 0;
   const int n_items = p.n_rowblocks * p.n_splits;
   const int grid = n_items < sms ? n_items : sms;

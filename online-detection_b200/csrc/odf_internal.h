@@ -28,6 +28,8 @@ struct TileParams {
   float* out;              // MODE_MMV: partial slabs [n_splits][n_rows][T_pad]; MODE_STORE: K
   int64_t ldo;             // MODE_STORE: row pitch of K
   int64_t split_stride;    // MODE_MMV: elements between split slabs
+  float* panel;            // optional (MODE_MMV): spill K tiles here, [n_rows x ldpanel] fp32
+  int64_t ldpanel;
 };
 
 // Host-side launch description.
@@ -49,9 +51,14 @@ struct TileLaunch {
   float* out;
   int64_t ldo;
   int64_t split_stride;
+  float* panel;                // optional K spill (MODE_MMV)
+  int64_t ldpanel;
 };
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream);
+int panel_splits(int64_t n_rows, int64_t M);
+int launch_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, int64_t M, int T_pad,
+                     int n_splits, float* out_partial, cudaStream_t st);
 int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t row_bytes);
 
 // error plumbing (thread-local last-error string behind odf_last_error())

@@ -28,6 +28,10 @@ SIGNATURES = {
     "odf_split_rhs": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_i64, c_int, c_fp]),
     "odf_gauss_mmv_prepared": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64,
                                        c_fp, c_fp, c_i64, c_int, c_int, c_f, c_fp, c_fp]),
+    "odf_gauss_mmv_prepared_spill": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64,
+                                             c_fp, c_fp, c_i64, c_int, c_int, c_f, c_fp, c_fp, c_i64, c_fp]),
+    "odf_panel_splits": (c_int, [c_i64, c_i64]),
+    "odf_panel_tmm": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_int, c_fp, c_fp]),
     "odf_finish_rows": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_i64, c_fp]),
     "odf_finish_split": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_fp,
                                  c_i64, c_fp]),

@@ -43,6 +43,9 @@ class FalkonOptions:
         # "inverse": apply T^-1 / A^-1 as GEMMs with explicit inverses built once per fit (default);
         # "trsm": four triangular solves per CG iteration, as upstream does
         self.precond_apply = ignored.pop("precond_apply", "inverse")
+        # "panel": K is evaluated once per sweep, its tiles are spilled to a transient row panel and
+        # contracted by the panel kernel; "recompute": evaluate K twice (no panel workspace)
+        self.sweep_mode = ignored.pop("sweep_mode", "panel")
         self.ignored = dict(ignored)
 
 
@@ -94,11 +97,12 @@ class GaussianKernel:
             out = torch.empty((M, T), dtype=torch.float32, device=dev)
         cols = self._prep(X2, like=X1)
         rows = self._prep(X1, like=cols)
-        sw = ops.Sweeper(rows, cols, self.sigma, min(T, 32))
+        mode = getattr(self.opt, "sweep_mode", "panel") if self.opt is not None else "panel"
+        sw = ops.Sweeper(rows, cols, self.sigma, min(T, 32), mode=mode)
         for t0 in range(0, T, 32):
             t1 = min(T, t0 + 32)
             if t1 - t0 != sw.T:
-                sw = ops.Sweeper(rows, cols, self.sigma, t1 - t0)
+                sw = ops.Sweeper(rows, cols, self.sigma, t1 - t0, mode=mode)
             sw.dmmv(None if v is None else v[:, t0:t1], None if w is None else w[:, t0:t1], out[:, t0:t1])
         return out
 
@@ -292,7 +296,7 @@ class Falkon:
         dev = pc.hi.device
         M, T = pc.n, Yb.shape[1]
         eps, tol = opt.cg_epsilon_32, opt.cg_tolerance
-        sw = be.Sweeper(px, pc, sigma, T) if px is not None else None
+        sw = be.Sweeper(px, pc, sigma, T, mode=opt.sweep_mode) if px is not None else None
         new = lambda: torch.empty((M, T), dtype=torch.float32, device=dev)  # noqa: E731
         B, R, P, AP, beta, v, u, c, H, H2 = (new() for _ in range(10))
         self._sweeps = 0

@@ -13,6 +13,8 @@ from ._lib import check, ptr
 # around every launch of the fused tile.
 LAUNCHES = 0
 TILE_EVENTS = None      # set to a list to record (start, stop, flops) per tile launch
+PANEL_EVENTS = None     # same for the panel contraction kernel
+PANEL_ROWS = 131072     # rows per spilled K panel (x pad_rows(M) x 4 B of transient workspace)
 
 
 def _count(n):
@@ -122,11 +124,39 @@ def alloc_partial(rows, cols, T_pad, device):
     return torch.empty((S, rows.n, T_pad), dtype=torch.float32, device=device)
 
 
-def mmv_partial(rows, cols, rhs, sigma, partial):
-    """partial[s] = K(rows, cols restricted to split s) @ rhs  — the fused tcgen05 tile."""
+class RowView:
+    """A contiguous row range [r0, r1) of a Prepared point set (no copy)."""
+
+    __slots__ = ("hi", "lo", "sqn", "opscale", "n", "d", "kind", "pitch")
+
+    def __init__(self, prep, r0, r1):
+        assert r0 % 128 == 0 and 0 <= r0 < r1 <= prep.n
+        self.hi, self.lo, self.sqn = prep.hi[r0:r1], prep.lo[r0:r1], prep.sqn[r0:]
+        self.opscale, self.n, self.d, self.kind, self.pitch = prep.opscale, r1 - r0, prep.d, prep.kind, prep.pitch
+
+
+def mmv_partial(rows, cols, rhs, sigma, partial, panel=None):
+    """partial[s] = K(rows, cols restricted to split s) @ rhs  — the fused tcgen05 tile.
+    With `panel` ([rows.n x pad_rows(cols.n)] fp32) the K tiles are also spilled for panel_tmm."""
     L = _lib.load()
     assert rows.d == cols.d and rows.kind == cols.kind and rhs.m == cols.n
     S = int(partial.shape[0])
+    if panel is not None:
+        assert panel.shape[0] >= rows.n and panel.stride(1) == 1
+        ev = None
+        if TILE_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        check(L.odf_gauss_mmv_prepared_spill(rows.kind, ptr(rows.hi), ptr(rows.lo), ptr(rows.sqn), ptr(rows.opscale),
+                                             rows.n, ptr(cols.hi), ptr(cols.lo), ptr(cols.sqn), ptr(cols.opscale),
+                                             cols.n, rows.d, ptr(rhs.hi), ptr(rhs.lo), rhs.ld, rhs.T_pad, S,
+                                             float(sigma), ptr(partial), ptr(panel), panel.stride(0), _stream()),
+              "odf_gauss_mmv_prepared_spill")
+        if ev is not None:
+            ev[1].record()
+            TILE_EVENTS.append((ev[0], ev[1], rows.n, cols.n, rows.d, rhs.T))
+        _count(1)
+        return
     ev = None
     if TILE_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -138,6 +168,23 @@ def mmv_partial(rows, cols, rhs, sigma, partial):
     if ev is not None:
         ev[1].record()
         TILE_EVENTS.append((ev[0], ev[1], rows.n, cols.n, rows.d, rhs.T))
+    _count(1)
+
+
+def panel_tmm(panel, W, n_rows, M, out_partial):
+    """out_partial[s] = panel[rows of split s]^T @ W   (fp32 FMA kernel streaming the panel)."""
+    L = _lib.load()
+    S, M_, T_pad = out_partial.shape
+    assert M_ == M and W.shape[1] == T_pad and W.is_contiguous() and S == int(L.odf_panel_splits(n_rows, M))
+    ev = None
+    if PANEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(L.odf_panel_tmm(ptr(panel), panel.stride(0), ptr(W), n_rows, M, T_pad, S, ptr(out_partial), _stream()),
+          "odf_panel_tmm")
+    if ev is not None:
+        ev[1].record()
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad))
     _count(1)
 
 
@@ -297,28 +344,55 @@ def mmv_into(rows, cols, v, sigma, out):
 
 
 class Sweeper:
-    """Pre-allocated buffers for repeated K_nm^T (K_nm V + W) sweeps with T <= 32 columns."""
+    """Pre-allocated buffers for repeated K_nm^T (K_nm V + W) sweeps with T <= 32 columns.
 
-    def __init__(self, rows, cols, sigma, T):
+    mode "panel" (default): rows go through in chunks; the fused tile computes K_chunk V and spills
+    its K tiles to a transient panel, then the panel kernel forms K_chunk^T (K_chunk V + W).  K is
+    evaluated once per sweep.  mode "recompute": the second half re-evaluates K in the transposed
+    orientation with the same fused tile (no panel workspace, 2x tensor work)."""
+
+    def __init__(self, rows, cols, sigma, T, mode="panel"):
+        L = _lib.load()
         dev = rows.hi.device
-        self.rows, self.cols, self.sigma, self.T = rows, cols, sigma, int(T)
+        self.rows, self.cols, self.sigma, self.T, self.mode = rows, cols, sigma, int(T), mode
         self.v_rhs = SplitRhs(cols.n, T, dev)       # V^T  (T_pad x M)
-        self.w_rhs = SplitRhs(rows.n, T, dev)       # W^T  (T_pad x n)
-        self.part1 = alloc_partial(rows, cols, self.v_rhs.T_pad, dev)   # rows = data
-        self.part2 = alloc_partial(cols, rows, self.v_rhs.T_pad, dev)   # rows = centres
+        self.w_rhs = SplitRhs(rows.n, T, dev)       # W^T  (T_pad x n), used by "recompute" and by the v=None sweep
+        Tp = self.v_rhs.T_pad
+        self.part2 = alloc_partial(cols, rows, Tp, dev)   # rows = centres
+        if mode == "panel":
+            self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
+            self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
+            self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
+            self.ldp = int(L.odf_pad_rows(cols.n))
+            self.panel = torch.empty((self.chunk, self.ldp), dtype=torch.float32, device=dev)
+            self.part1 = [alloc_partial(v, cols, Tp, dev) for v in self.views[:1] + self.views[-1:]]
+            self.Wc = torch.zeros((self.chunk, Tp), dtype=torch.float32, device=dev)   # padded columns stay 0
+            self.pslabs = [int(L.odf_panel_splits(r1 - r0, cols.n)) for (r0, r1) in self.chunks]
+            self.part3 = torch.empty((sum(self.pslabs), cols.n, Tp), dtype=torch.float32, device=dev)
+        else:
+            self.part1 = alloc_partial(rows, cols, Tp, dev)   # rows = data
 
     def dmmv(self, v, w, out, scale=1.0, w_scale=1.0):
         """out = scale * K^T (K v + w_scale * w)   (local rows only; caller all-reduces)."""
-        if v is not None:
-            self.v_rhs.fill(v)
-            mmv_partial(self.rows, self.cols, self.v_rhs, self.sigma, self.part1)
-            if w is not None and w_scale != 1.0:
-                w = w * w_scale
-            finish_split(self.part1, self.T, self.w_rhs, 1.0, w)
-        else:
+        if v is None:
             self.w_rhs.fill(w, w_scale)
-        mmv_partial(self.cols, self.rows, self.w_rhs, self.sigma, self.part2)
-        finish_rows(self.part2, self.T, out, scale)
-        return out
-
-
+            mmv_partial(self.cols, self.rows, self.w_rhs, self.sigma, self.part2)
+            return finish_rows(self.part2, self.T, out, scale)
+        if w is not None and w_scale != 1.0:
+            w = w * w_scale
+        self.v_rhs.fill(v)
+        if self.mode != "panel":
+            mmv_partial(self.rows, self.cols, self.v_rhs, self.sigma, self.part1)
+            finish_split(self.part1, self.T, self.w_rhs, 1.0, w)
+            mmv_partial(self.cols, self.rows, self.w_rhs, self.sigma, self.part2)
+            return finish_rows(self.part2, self.T, out, scale)
+        slab = 0
+        for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
+            n = r1 - r0
+            part1 = self.part1[0] if n == self.part1[0].shape[1] else self.part1[-1]
+            mmv_partial(view, self.cols, self.v_rhs, self.sigma, part1, panel=self.panel)
+            finish_rows(part1, self.T, self.Wc[:n], 1.0, None if w is None else w[r0:r1])
+            S = self.pslabs[i]
+            panel_tmm(self.panel, self.Wc[:n], n, self.cols.n, self.part3[slab:slab + S])
+            slab += S
+        return finish_rows(self.part3, self.T, out, scale)

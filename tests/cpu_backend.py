@@ -47,7 +47,7 @@ def precond_apply(Inv, Bin, Bout, transposed):
 
 
 class Sweeper:
-    def __init__(self, rows, cols, sigma, T):
+    def __init__(self, rows, cols, sigma, T, mode="panel"):
         self.rows, self.cols, self.sigma, self.T = rows, cols, sigma, T
 
     def dmmv(self, v, w, out, scale=1.0, w_scale=1.0):

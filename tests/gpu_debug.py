@@ -12,7 +12,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "online-detection_b200"))
 
-STAGES = ["prepare", "kmm_small", "kmm", "mmv_small", "mmv", "dmmv", "precision", "precond", "cg", "perf"]
+STAGES = ["prepare", "kmm_small", "kmm", "mmv_small", "mmv", "dmmv", "panel", "precision", "precond", "cg", "perf"]
 
 
 def _ref_kernel(X, C, sigma):
@@ -200,6 +200,35 @@ def run_stage(stage):
             ms = e0.elapsed_time(e1) / 3
             fl = 2.0 * n * M * (d + T)
             print(f"perf mmv kind={kind} n={n} M={M} d={d} T={T} S={part.shape[0]}: {ms:.2f} ms  alg={fl / ms / 1e9:.1f} TFLOP/s")
+    elif stage == "panel":
+        from odf import ops
+        for (n, M, d, T) in [(300, 200, 40, 21), (5000, 1000, 256, 30), (4096, 777, 64, 5), (131072, 10000, 1024, 30)]:
+            sigma = 15.0
+            X = _data(n, d, 5); C = _data(M, d, 6)
+            V = torch.randn(M, T, device="cuda")
+            px, pc = ops.Prepared(X), ops.Prepared(C)
+            out = torch.empty(M, T, device="cuda"); out2 = torch.empty(M, T, device="cuda")
+            swp = ops.Sweeper(px, pc, sigma, T, mode="panel"); swr = ops.Sweeper(px, pc, sigma, T, mode="recompute")
+            swp.dmmv(V, None, out); swr.dmmv(V, None, out2)
+            torch.cuda.synchronize()
+            e = rel(out, out2)
+            msg = f"panel n={n} M={M} d={d} T={T}: panel_vs_recompute={e:.3e}"
+            if n <= 5000:
+                Kr = _ref_kernel(X, C, sigma)
+                ref = Kr.T @ (Kr @ V.double())
+                msg += f" panel_vs_ref={rel(out, ref):.3e} recompute_vs_ref={rel(out2, ref):.3e}"
+            ts = []
+            for sw in (swp, swr):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                sw.dmmv(V, None, out); e0.record()
+                for _ in range(3): sw.dmmv(V, None, out)
+                e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / 3)
+            # time the panel kernel alone
+            ops.PANEL_EVENTS = []
+            swp.dmmv(V, None, out); torch.cuda.synchronize()
+            pk = sum(a.elapsed_time(b) for (a, b, *_r) in ops.PANEL_EVENTS); ops.PANEL_EVENTS = None
+            print(msg + f"  sweep_ms panel={ts[0]:.2f} recompute={ts[1]:.2f} panel_kernel_ms={pk:.2f} ({n * swp.ldp * 4 / pk / 1e6:.0f} GB/s panel read)")
+            ok &= e < 2e-5
     elif stage == "precision":
         # near-duplicate pairs: K_MM diagonal and small-distance entries, where the 3-pass product and
         # the truncating tensor-core accumulator matter most

@@ -85,13 +85,14 @@ def test_mmv_out_argument_and_vector_rhs(odf):
     assert rel(k.mmv(X.cuda(), C.cuda(), more.cuda()), orc.mmv(X, C, more, 20.0)) < 5e-5
 
 
-@pytest.mark.parametrize("n,M,d,T", [(3000, 500, 256, 21), (1000, 64, 48, 1), (5000, 1000, 1024, 30)])
-def test_dmmv_matches_oracle(odf, n, M, d, T):
+@pytest.mark.parametrize("mode", ["panel", "recompute"])
+@pytest.mark.parametrize("n,M,d,T", [(3000, 500, 256, 21), (1000, 64, 48, 1), (5000, 1000, 1024, 30), (129, 130, 40, 16)])
+def test_dmmv_matches_oracle(odf, n, M, d, T, mode):
     X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
     C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
     g = torch.Generator().manual_seed(8)
     v, w = torch.randn(M, T, generator=g), torch.randn(n, T, generator=g)
-    k = odf.GaussianKernel(15.0)
+    k = odf.GaussianKernel(15.0, opt=odf.FalkonOptions(sweep_mode=mode))
     Xg, Cg = X.cuda(), C.cuda()
     assert rel(k.dmmv(Xg, Cg, v.cuda(), None), orc.dmmv(X, C, v, None, 15.0)) < 1e-4
     assert rel(k.dmmv(Xg, Cg, None, w.cuda()), orc.dmmv(X, C, None, w, 15.0)) < 1e-4
@@ -104,8 +105,12 @@ def test_kmm_matches_oracle(odf, M, d, sigma, kind):
     C, _, _ = orc.make_synthetic(M, d, 2, seed=9)
     K = odf.GaussianKernel(sigma, opt=odf.FalkonOptions(operand_kind=kind))(C.cuda())
     Kr = orc.gaussian_kernel(C, C, sigma)
-    assert float((K.double().cpu() - Kr).abs().max()) < 1e-5
-    assert float(K.max()) <= 1.0 and float(K.diag().min()) > 0.99999
+    # The tensor core accumulates in fp32 with truncation: the squared distance of near-duplicate
+    # points carries an absolute error of about 2e-3 * d/1024 at |x| = 20, i.e. a
+    # relative kernel error of that over 2 sigma^2.
+    tol = 6e-3 * max(d, 256) / 1024 / (2 * sigma * sigma) + 2e-6
+    assert float((K.double().cpu() - Kr).abs().max()) < tol
+    assert float(K.max()) <= 1.0 and float(K.diag().min()) > 1 - tol
 
 
 def test_duplicate_points_give_unit_kernel(odf):
@@ -114,7 +119,8 @@ def test_duplicate_points_give_unit_kernel(odf):
     C = X[[5, 5, 17, 200]]
     v = torch.eye(4)
     out = odf.GaussianKernel(5.0).mmv(X.cuda(), C.cuda(), v.cuda()).cpu()
-    assert abs(float(out[5, 0]) - 1) < 1e-5 and abs(float(out[5, 1]) - 1) < 1e-5 and abs(float(out[200, 3]) - 1) < 1e-5
+    tol = 6e-3 / 50 + 2e-6                                         # see test_kmm_matches_oracle
+    assert abs(float(out[5, 0]) - 1) < tol and abs(float(out[5, 1]) - 1) < tol and abs(float(out[200, 3]) - 1) < tol
     assert float(out.max()) <= 1.0
 
 
@@ -157,6 +163,27 @@ def test_config1_fit_matches_oracle(odf, N, M, sigma, lam, noise, kind):
     pos = ct > 0                                                  # true objects: the decision that matters
     assert torch.equal(s_gpu[pos].argmax(1), s_ref[pos].argmax(1))
     assert float((s_ref[pos].argmax(1) + 1 == ct[pos]).double().mean()) > 0.9
+
+
+def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
+    """The spilled-panel sweep walks the rows in chunks; force several (ragged) chunks."""
+    from odf import ops
+    monkeypatch.setattr(ops, "PANEL_ROWS", 1024)
+    X, _, _ = orc.make_synthetic(3333, 64, 3, seed=6)
+    C = X[::11].contiguous()
+    g = torch.Generator().manual_seed(8)
+    v, w = torch.randn(C.shape[0], 7, generator=g), torch.randn(3333, 7, generator=g)
+    k = odf.GaussianKernel(15.0)
+    assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), w.cuda()), orc.dmmv(X, C, v, w, 15.0)) < 1e-4
+    assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), None), orc.dmmv(X, C, v, None, 15.0)) < 1e-4
+
+
+def test_recompute_and_trsm_options_agree_with_default(odf):
+    X, c, Y = orc.make_synthetic(5000, 128, 3, seed=2)
+    C = X[orc.shared_centres(c, 300, seed=1)]
+    base = _gpu_fit(odf, X, Y, C, 15.0, 1e-4).predict(X[:1000].cuda())
+    alt = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(sweep_mode="recompute", precond_apply="trsm"))
+    assert rel(alt.predict(X[:1000].cuda()), base) < 2e-4
 
 
 def test_per_class_mode_with_duplicate_centres(odf):
