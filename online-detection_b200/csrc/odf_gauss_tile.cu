@@ -35,6 +35,7 @@
 //   warp 2         : TMEM allocator
 //   warp 3  lane 0 : TMA producer for the V^T tiles
 //   warps 4..7     : epilogue (one TMEM lane == one row per thread)
+#include <cstdlib>
 #include "odf_ptx.cuh"
 #include "odf_internal.h"
 
@@ -116,9 +117,16 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
             B_PVDONE = 2 * NS + 3, B_VFULL = 2 * NS + 4, B_VEMPTY = 2 * NS + 5,
             B_WFULL = 2 * NS + 6, B_WEMPTY = 2 * NS + 7;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: tells ptxas it is warp-uniform (role branches stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const bool mode_mmv = (p.mode == MODE_MMV);
+  long long dbg_c0 = 0;
+  unsigned long long dbg_t0 = 0;
+  if ((p.dbg & 16) && threadIdx.x == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmRh);
@@ -159,129 +167,167 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
   const int T_pad = p.T_pad;
   constexpr int BK = (KIND == KIND_F16) ? 64 : 32;      // elements per k-block
 
-  if (warp == 0 && lane == 0) {
+  // Producer / issuer roles: ONE elected lane of the warp runs the whole role loop.  `elect_one()`
+  // (elect.sync) rather than `lane == 0` lets ptxas keep descriptors and barrier addresses in uniform
+  // registers; with `lane == 0` it wrapped every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST retry
+  // loop and the issuing thread, not the tensor pipe, set the pace (~100 cycles per 64-cycle MMA).
+  if (warp == 0) {
     // ======================= operand TMA producer =======================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const WorkItem w = decode_item(p, it);
-      for (int j = w.jt0; j < w.jt1; ++j) {
-        const int col0 = j * BN;
-        for (int kb = -1; kb < KB; ++kb) {
-          mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
-          const uint32_t full = BAR(B_FULL + stage);
-          const uint32_t dst = smem_u32(stage_base + stage * STAGE_BYTES);
-          if (kb < 0) {
-            // seed block: rows bring [-|x|^2/2 hi, lo, 0...], columns bring [1, 1, 0...]
-            mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
-            tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, KB * BK, w.row0);
-            tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, (KB + 1) * BK, col0);
-          } else {
-            mbar_arrive_expect_tx(full, STAGE_BYTES);
-            tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, kb * BK, w.row0);
-            tma_load_2d(dst + 1 * TILE_BYTES, &tmRl, full, kb * BK, w.row0);
-            tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, kb * BK, col0);
-            tma_load_2d(dst + 3 * TILE_BYTES, &tmQl, full, kb * BK, col0);
+    if (elect_one()) {
+      const bool no_tma = (p.dbg & 1) != 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WorkItem w = decode_item(p, it);
+        for (int j = w.jt0; j < w.jt1; ++j) {
+          const int col0 = j * BN;
+          for (int kb = -1; kb < KB; ++kb) {
+            mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
+            const uint32_t full = BAR(B_FULL + stage);
+            const uint32_t dst = smem_u32(stage_base) + stage * STAGE_BYTES;
+            if (no_tma) {
+              mbar_arrive(full);
+            } else if (kb < 0) {
+              // seed block: rows bring [-|x|^2/2 hi, lo, 0...], columns bring [1, 1, 0...]
+              mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+              tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, KB * BK, w.row0);
+              tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, (KB + 1) * BK, col0);
+            } else {
+              mbar_arrive_expect_tx(full, STAGE_BYTES);
+              tma_load_2d(dst + 0 * TILE_BYTES, &tmRh, full, kb * BK, w.row0);
+              tma_load_2d(dst + 1 * TILE_BYTES, &tmRl, full, kb * BK, w.row0);
+              tma_load_2d(dst + 2 * TILE_BYTES, &tmQh, full, kb * BK, col0);
+              tma_load_2d(dst + 3 * TILE_BYTES, &tmQl, full, kb * BK, col0);
+            }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
-          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 3 && lane == 0 && mode_mmv) {
+    __syncwarp();
+  } else if (warp == 3 && mode_mmv && !(p.dbg & 64)) {
     // ======================= V^T tile TMA producer =======================
-    uint32_t n = 0;  // tile counter
-    const uint32_t atom_bytes = T_pad * 128;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const WorkItem w = decode_item(p, it);
-      for (int j = w.jt0; j < w.jt1; ++j, ++n) {
-        mbar_wait(BAR(B_VEMPTY), (n & 1) ^ 1);
-        const uint32_t full = BAR(B_VFULL);
-        mbar_arrive_expect_tx(full, 8 * atom_bytes);
-        const uint32_t dst = smem_u32(v_base);
+    if (elect_one()) {
+      uint32_t n = 0;  // tile counter
+      const uint32_t atom_bytes = T_pad * 128;
+      const uint32_t full = BAR(B_VFULL);
+      const uint32_t dst = smem_u32(v_base);
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WorkItem w = decode_item(p, it);
+        for (int j = w.jt0; j < w.jt1; ++j, ++n) {
+          mbar_wait(BAR(B_VEMPTY), (n & 1) ^ 1);
+          mbar_arrive_expect_tx(full, 8 * atom_bytes);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          tma_load_2d(dst + a * atom_bytes, &tmVh, full, j * BN + a * 32, 0);
-          tma_load_2d(dst + (4 + a) * atom_bytes, &tmVl, full, j * BN + a * 32, 0);
+          for (int a = 0; a < 4; ++a) {
+            tma_load_2d(dst + a * atom_bytes, &tmVh, full, j * BN + a * 32, 0);
+            tma_load_2d(dst + (4 + a) * atom_bytes, &tmVl, full, j * BN + a * 32, 0);
+          }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+    __syncwarp();
+  } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    const uint32_t idesc_s = (KIND == KIND_F16) ? make_idesc_f16(BM, BN) : make_idesc_tf32(BM, BN);
-    const uint32_t idesc_pv = make_idesc_tf32(BM, T_pad);
-    const uint32_t atom_bytes = T_pad * 128;
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t n = 0;         // tiles whose S-MMAs have been issued
-    uint32_t item_cnt = 0;  // items whose first PV has been issued
-    bool pend = false, pend_first = false, pend_last = false;
+    if (elect_one()) {
+      const uint32_t idesc_s = (KIND == KIND_F16) ? make_idesc_f16(BM, BN) : make_idesc_tf32(BM, BN);
+      const uint32_t idesc_pv = make_idesc_tf32(BM, T_pad);
+      const uint32_t atom_bytes = T_pad * 128;
+      const bool no_smma = (p.dbg & 2) != 0, no_pv = (p.dbg & 8) != 0;
+      // descriptor low words: (address >> 4); tiles at fixed offsets add (offset >> 4)
+      const uint32_t sdesc_stage0 = (smem_u32(stage_base) & 0x3FFFFu) >> 4;
+      const uint32_t sdesc_v = (smem_u32(v_base) & 0x3FFFFu) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t n = 0;         // tiles whose S-MMAs have been issued
+      uint32_t item_cnt = 0;  // items whose first PV has been issued
+      bool pend = false, pend_first = false, pend_last = false;
 
-    // second contraction (or, in MODE_STORE, just the hand-back of the S buffer) for tile n-1
-    auto finish_prev = [&](uint32_t tile) {
-      mbar_wait(BAR(B_PREADY), tile & 1);
-      if (mode_mmv) {
-        mbar_wait(BAR(B_VFULL), tile & 1);
-        if (pend_first) {
-          mbar_wait(BAR(B_WEMPTY), (item_cnt & 1) ^ 1);
-          ++item_cnt;
-        }
-        tc_fence_after();
-        const uint32_t t_hi = tmem_base + ((tile & 1) ? TM_S1 : TM_S0);
-        const uint32_t t_lo = tmem_base + TM_PLO;
-        const uint32_t t_w = tmem_base + TM_W;
-        const uint32_t vb = smem_u32(v_base);
-#pragma unroll
-        for (int ks = 0; ks < BN / 8; ++ks) {
-          const uint32_t off = (ks >> 2) * atom_bytes + (ks & 3) * 32;
-          const uint64_t b_hi = make_sdesc_sw128(vb + off);
-          const uint64_t b_lo = make_sdesc_sw128(vb + 4 * atom_bytes + off);
-          mma_tf32_ts(t_w, t_hi + ks * 8, b_hi, idesc_pv, (pend_first && ks == 0) ? 0u : 1u);
-          mma_tf32_ts(t_w, t_lo + ks * 8, b_hi, idesc_pv, 1u);
-          mma_tf32_ts(t_w, t_hi + ks * 8, b_lo, idesc_pv, 1u);
-        }
-        tc_commit(BAR(B_VEMPTY));
-        tc_commit(BAR(B_PVDONE));
-        if (pend_last) tc_commit(BAR(B_WFULL));
-      }
-    };
-
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const WorkItem w = decode_item(p, it);
-      for (int j = w.jt0; j < w.jt1; ++j) {
-        const uint32_t t_s = tmem_base + ((n & 1) ? TM_S1 : TM_S0);
-        for (int kb = -1; kb < KB; ++kb) {
-          mbar_wait(BAR(B_FULL + stage), phase);
+      // second contraction (or, in MODE_STORE, just the hand-back of the S buffer) for tile n-1
+      auto finish_prev = [&](uint32_t tile) {
+        if (p.dbg & 64) return;                       // timing experiment: issuer + producer only
+        mbar_wait(BAR(B_PREADY), tile & 1);
+        if (mode_mmv) {
+          mbar_wait(BAR(B_VFULL), tile & 1);
+          if (pend_first) {
+            mbar_wait(BAR(B_WEMPTY), (item_cnt & 1) ^ 1);
+            ++item_cnt;
+          }
           tc_fence_after();
-          const uint32_t sb = smem_u32(stage_base + stage * STAGE_BYTES);
-          if (kb < 0) {
-            // rank-1 seed: acc = (-|x|^2/2) * 1   (first k-step of the seed block only)
-            mma_ss<KIND>(t_s, make_sdesc_sw128(sb + 0 * TILE_BYTES), make_sdesc_sw128(sb + 2 * TILE_BYTES),
-                         idesc_s, 0u);
-          } else {
+          const uint32_t t_hi = tmem_base + ((tile & 1) ? TM_S1 : TM_S0);
+          const uint32_t t_lo = tmem_base + TM_PLO;
+          const uint32_t t_w = tmem_base + TM_W;
+          if (!no_pv) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {       // 4 k-steps of 32 bytes per 128-byte k-block
-              const uint64_t a_hi = make_sdesc_sw128(sb + 0 * TILE_BYTES + ks * 32);
-              const uint64_t a_lo = make_sdesc_sw128(sb + 1 * TILE_BYTES + ks * 32);
-              const uint64_t b_hi = make_sdesc_sw128(sb + 2 * TILE_BYTES + ks * 32);
-              const uint64_t b_lo = make_sdesc_sw128(sb + 3 * TILE_BYTES + ks * 32);
+            for (int ks = 0; ks < BN / 8; ++ks) {
+              const uint32_t off = (ks >> 2) * atom_bytes + (ks & 3) * 32;
+              const uint64_t b_hi = kSdescSw128Hi | static_cast<uint64_t>(sdesc_v + (off >> 4));
+              const uint64_t b_lo = kSdescSw128Hi | static_cast<uint64_t>(sdesc_v + ((4 * atom_bytes + off) >> 4));
+              mma_tf32_ts(t_w, t_hi + ks * 8, b_hi, idesc_pv, (pend_first && ks == 0) ? 0u : 1u);
+              mma_tf32_ts(t_w, t_lo + ks * 8, b_hi, idesc_pv, 1u);
+              mma_tf32_ts(t_w, t_hi + ks * 8, b_lo, idesc_pv, 1u);
+            }
+          }
+          tc_commit(BAR(B_VEMPTY));
+          tc_commit(BAR(B_PVDONE));
+          if (pend_last) tc_commit(BAR(B_WFULL));
+        }
+      };
+
+      // The probe for the NEXT k-block's stage sits between the MMAs of the current one: the tensor
+      // pipe holds only a few queued MMAs, so a full-barrier poll + descriptor set-up at the k-block
+      // boundary (~300 cycles of dependent scalar work) would otherwise drain it every 12 MMAs
+      // (measured with tools/umma_probe.cu: 81 -> 72 cycles per 64-cycle MMA).
+      bool ready = false;     // has the current k-block's stage already been seen full?
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WorkItem w = decode_item(p, it);
+        const bool last_item = (it + static_cast<int>(gridDim.x) >= n_items);
+        for (int j = w.jt0; j < w.jt1; ++j) {
+          const uint32_t t_s = tmem_base + ((n & 1) ? TM_S1 : TM_S0);
+          for (int kb = -1; kb < KB; ++kb) {
+            const uint32_t sd = sdesc_stage0 + stage * (STAGE_BYTES >> 4);
+            int nstage = stage + 1;
+            uint32_t nphase = phase;
+            if (nstage == NS) { nstage = 0; nphase ^= 1; }
+            const bool more = !(last_item && j == w.jt1 - 1 && kb == KB - 1);
+            if (!ready) mbar_wait(BAR(B_FULL + stage), phase);
+            tc_fence_after();
+            auto step = [&](int ks) {               // one 32-byte k-step: lo.hi + hi.lo + hi.hi
+              const uint64_t a_hi = kSdescSw128Hi | static_cast<uint64_t>(sd + ((0 * TILE_BYTES + ks * 32) >> 4));
+              const uint64_t a_lo = kSdescSw128Hi | static_cast<uint64_t>(sd + ((1 * TILE_BYTES + ks * 32) >> 4));
+              const uint64_t b_hi = kSdescSw128Hi | static_cast<uint64_t>(sd + ((2 * TILE_BYTES + ks * 32) >> 4));
+              const uint64_t b_lo = kSdescSw128Hi | static_cast<uint64_t>(sd + ((3 * TILE_BYTES + ks * 32) >> 4));
               mma_ss<KIND>(t_s, a_lo, b_hi, idesc_s, 1u);      // small terms first
               mma_ss<KIND>(t_s, a_hi, b_lo, idesc_s, 1u);
               mma_ss<KIND>(t_s, a_hi, b_hi, idesc_s, 1u);
+            };
+            if (no_smma) {
+            } else if (kb < 0) {
+              // rank-1 seed: acc = (-|x|^2/2) * 1   (first k-step of the seed block only)
+              mma_ss<KIND>(t_s, kSdescSw128Hi | static_cast<uint64_t>(sd),
+                           kSdescSw128Hi | static_cast<uint64_t>(sd + ((2 * TILE_BYTES) >> 4)), idesc_s, 0u);
+            } else {
+              step(0); step(1); step(2);
             }
+            // one non-blocking probe: when the feed keeps up (the usual case) the next k-block starts
+            // without a poll at its head; when it does not, this stage is still released first
+            ready = more && mbar_test_wait(BAR(B_FULL + nstage), nphase) != 0;
+            if (!no_smma && kb >= 0) step(3);
+            tc_commit(BAR(B_EMPTY + stage));
+            stage = nstage;
+            phase = nphase;
           }
-          tc_commit(BAR(B_EMPTY + stage));
-          if (++stage == NS) { stage = 0; phase ^= 1; }
+          tc_commit(BAR(B_SFULL + (n & 1)));
+          if (pend) finish_prev(n - 1);
+          pend = true;
+          pend_first = (j == w.jt0);
+          pend_last = (j == w.jt1 - 1);
+          ++n;
         }
-        tc_commit(BAR(B_SFULL + (n & 1)));
-        if (pend) finish_prev(n - 1);
-        pend = true;
-        pend_first = (j == w.jt0);
-        pend_last = (j == w.jt1 - 1);
-        ++n;
       }
+      if (pend) finish_prev(n - 1);
     }
-    if (pend) finish_prev(n - 1);
-  } else if (warp >= 4) {
+    __syncwarp();
+  } else if (warp >= 4 && !(p.dbg & 64)) {
     // ======================= epilogue =======================
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;          // row inside the block
@@ -299,7 +345,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
       const float rn = ((grow < p.n_rows) ? __ldg(p.rnorm + grow) : 0.f) * one_m_rho;
       for (int j = w.jt0; j < w.jt1; ++j, ++n) {
         const uint32_t b = n & 1;
-        mbar_wait(BAR(B_SFULL + b), (n >> 1) & 1);
+        mbar_wait_warp(BAR(B_SFULL + b), (n >> 1) & 1);
         tc_fence_after();
         const uint32_t t_s = tmem_base + lane_off + (b ? TM_S1 : TM_S0);
         const uint32_t t_lo = tmem_base + lane_off + TM_PLO;
@@ -317,7 +363,8 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
             qn[4 * v + 0] = t.x; qn[4 * v + 1] = t.y; qn[4 * v + 2] = t.z; qn[4 * v + 3] = t.w;
           }
           tc_wait_ld();
-          if (mode_mmv) {
+          if (p.dbg & 4) {
+          } else if (mode_mmv) {
             uint32_t lo[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -328,7 +375,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
               s[c] = __float_as_uint(hi);
               lo[c] = __float_as_uint(tf32_rn(kv - hi));
             }
-            if (ch == 0 && n > 0) mbar_wait(BAR(B_PVDONE), (n - 1) & 1);  // K_lo buffer free
+            if (ch == 0 && n > 0) mbar_wait_warp(BAR(B_PVDONE), (n - 1) & 1);  // K_lo buffer free
             tmem_st32(t_s + ch * 32, s);
             tmem_st32(t_lo + ch * 32, lo);
             if (p.panel != nullptr && grow < p.n_rows) {
@@ -377,7 +424,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
       }
       if (mode_mmv) {
         // W for this item is complete once the last tile's contraction has retired.
-        mbar_wait(BAR(B_WFULL), item_cnt & 1);
+        mbar_wait_warp(BAR(B_WFULL), item_cnt & 1);
         tc_fence_after();
         const uint32_t t_w = tmem_base + lane_off + TM_W;
         float* orow = p.out + static_cast<int64_t>(w.split) * p.split_stride +
@@ -406,6 +453,13 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TM_COLS);
+  if ((p.dbg & 16) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("tile dbg[%d]: cta %d cycles=%lld ns=%llu  => %.1f MHz\n", p.dbg, blockIdx.x, c1 - dbg_c0, t1 - dbg_t0,
+           1e3 * double(c1 - dbg_c0) / double(t1 - dbg_t0));
+  }
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -449,6 +503,26 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64
   }
   return ODF_OK;
 }
+
+}  // namespace
+
+// Plain (un-swizzled) 2-D fp32 map: box = [box_rows x box_cols]; out-of-bounds elements read as 0.
+int make_map_plain_f32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled (plain fp32 map) failed");
+  return ODF_OK;
+}
+
+namespace {
 
 int g_num_sms = 0;
 int num_sms() {
@@ -544,6 +618,10 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
   if (L.panel != nullptr && (L.mode != MODE_MMV || L.ldpanel < static_cast<int64_t>(p.n_coltiles) * BN ||
                              L.ldpanel % 4 != 0 || (reinterpret_cast<uintptr_t>(L.panel) & 15) != 0))
     return set_error(ODF_ERR_ARG, "panel must be 16-byte aligned with pitch >= round_up(n_cols, 128)");
+  {
+    const char* e = getenv("ODF_TILE_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   p.store_vec4 = (L.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) ? 1 : 0;
   const int n_items = p.n_rowblocks * p.n_splits;
   const int grid = n_items < sms ? n_items : sms;

@@ -6,6 +6,8 @@
 
 #include "../../include/odf.h"
 
+struct CUtensorMap_st;   // <cuda.h>
+
 namespace odf {
 
 enum : int { MODE_MMV = 0, MODE_STORE = 1 };
@@ -30,6 +32,8 @@ struct TileParams {
   int64_t split_stride;    // MODE_MMV: elements between split slabs
   float* panel;            // optional (MODE_MMV): spill K tiles here, [n_rows x ldpanel] fp32
   int64_t ldpanel;
+  int dbg;                 // bring-up timing experiments (env ODF_TILE_DEBUG; results are garbage when set):
+                           // 1 = no TMA refills, 2 = no S MMAs, 4 = no epilogue math, 8 = no K.V MMAs, 16 = print clocks
 };
 
 // Host-side launch description.
@@ -56,6 +60,8 @@ struct TileLaunch {
 };
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream);
+int make_map_plain_f32(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols);
 int panel_splits(int64_t n_rows, int64_t M);
 int launch_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, int64_t M, int T_pad,
                      int n_splits, float* out_partial, cudaStream_t st);

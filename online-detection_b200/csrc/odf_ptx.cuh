@@ -13,6 +13,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (the same lane every time).  Code that issues TMA / tcgen05
+// instructions sits in `if (elect_one())` inside WARP-UNIFORM control flow: ptxas can then keep
+// descriptors and addresses in uniform registers; under a `lane == 0` branch it cannot prove
+// uniformity and wraps every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST retry loop, which made
+// the single issuing thread the bottleneck of the whole tile (~100 cycles per 64-cycle MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -43,6 +60,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Non-blocking probe of a phase (mbarrier.test_wait never suspends the thread).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Spin on a phase with a watchdog: a protocol bug traps (reported as a CUDA error by the
 // next API call) instead of hanging the device until an external timeout kills the box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -52,6 +83,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && (clock64() - t0) > 4000000000LL) __trap();
   }
+}
+
+// Whole-warp wait with ONE polling lane: 128 epilogue threads spinning on try_wait saturate the
+// mbarrier unit and delay the producer / issuer hand-shakes of the same CTA (measured: ~200 cycles
+// exposed per k-block).  Lane 0 polls, the warp barrier publishes the completed phase to the rest.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // ----------------------------------------------------------------------------- TMA
@@ -147,6 +186,18 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 template <int KIND>
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                        uint32_t idesc, uint32_t accumulate) {
@@ -169,6 +220,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
 // Shared-memory matrix descriptor for a K-major operand stored as 128-byte rows with the
 // 128B swizzle (exactly what a TMA box of {32 fp32, rows} with CU_TENSOR_MAP_SWIZZLE_128B
 // writes): 8-row groups are 1024 B apart (SBO), LBO unused, version 1, layout SWIZZLE_128B.
+// Everything but the start address of the descriptor below; descriptors of tiles at a fixed byte
+// offset from a base differ only by (offset >> 4) in the low word (shared memory is < 256 KB, so
+// the 14-bit address field never carries).
+constexpr uint64_t kSdescSw128Hi = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                   (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
 __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address  [0,14)

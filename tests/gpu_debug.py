@@ -12,7 +12,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "online-detection_b200"))
 
-STAGES = ["prepare", "kmm_small", "kmm", "mmv_small", "mmv", "dmmv", "panel", "precision", "precond", "cg", "perf"]
+STAGES = ["prepare", "kmm_small", "kmm", "mmv_small", "mmv", "dmmv", "panel", "precision", "precond", "cg", "perf"]   # + "bottleneck" (timing experiments, on request)
 
 
 def _ref_kernel(X, C, sigma):
@@ -103,7 +103,7 @@ def run_stage(stage):
                 dd = (out.double() - ref).abs()
                 print("   worst rows", dd.max(1).values.topk(5).indices.tolist(), "worst cols", dd.max(0).values.topk(min(5, T)).indices.tolist())
                 print("   out[0,:4]", out[0, :4].tolist(), "ref[0,:4]", ref[0, :4].tolist())
-            ok &= e < 2e-5
+            ok &= rel(out, ref) < 2e-5
     elif stage == "dmmv":
         for (n, M, d, T) in [(3000, 500, 256, 21), (20000, 1000, 1024, 30)]:
             sigma = 15.0
@@ -213,10 +213,11 @@ def run_stage(stage):
             torch.cuda.synchronize()
             e = rel(out, out2)
             msg = f"panel n={n} M={M} d={d} T={T}: panel_vs_recompute={e:.3e}"
-            if n <= 5000:
-                Kr = _ref_kernel(X, C, sigma)
-                ref = Kr.T @ (Kr @ V.double())
-                msg += f" panel_vs_ref={rel(out, ref):.3e} recompute_vs_ref={rel(out2, ref):.3e}"
+            ref = torch.zeros(M, T, device="cuda", dtype=torch.float64)
+            for r0 in range(0, n, 8192):
+                Kr = _ref_kernel(X[r0:r0 + 8192], C, sigma)
+                ref += Kr.T @ (Kr @ V.double())
+            msg += f" panel_vs_ref={rel(out, ref):.3e} recompute_vs_ref={rel(out2, ref):.3e}"
             ts = []
             for sw in (swp, swr):
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -229,6 +230,55 @@ def run_stage(stage):
             pk = sum(a.elapsed_time(b) for (a, b, *_r) in ops.PANEL_EVENTS); ops.PANEL_EVENTS = None
             print(msg + f"  sweep_ms panel={ts[0]:.2f} recompute={ts[1]:.2f} panel_kernel_ms={pk:.2f} ({n * swp.ldp * 4 / pk / 1e6:.0f} GB/s panel read)")
             ok &= e < 2e-5
+    elif stage == "bottleneck":
+        # timing-only experiments (results are garbage under the debug flags)
+        from odf import ops
+        for kind in (1, 0):
+            for (n, M, d, T) in [(131072, 10000, 1024, 30)]:
+                X = _data(n, d, 1); C = _data(M, d, 2)
+                px, pc = ops.Prepared(X, kind=kind), ops.Prepared(C, kind=kind)
+                rhs = ops.SplitRhs(M, T, "cuda").fill(torch.randn(M, T, device="cuda"))
+                part = ops.alloc_partial(px, pc, rhs.T_pad, "cuda")
+                res = []
+                for flags in (0,):
+                    os.environ["ODF_TILE_DEBUG"] = str(flags)
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    for it in range(4):
+                        if it == 1: e0.record()
+                        ops.mmv_partial(px, pc, rhs, 20.0, part)
+                    e1.record(); torch.cuda.synchronize()
+                    res.append("%d:%.2f" % (flags, e0.elapsed_time(e1) / 3))
+                os.environ["ODF_TILE_DEBUG"] = "0"
+                # SM clock while the plain kernel runs back to back for ~1.5 s
+                import pynvml, threading
+                pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
+                clk, pw, stop = [], [], threading.Event()
+                def sample():
+                    while not stop.is_set():
+                        clk.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)); pw.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                        time.sleep(0.05)
+                th = threading.Thread(target=sample); 
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                reps = 20
+                for it in range(20): ops.mmv_partial(px, pc, rhs, 20.0, part)
+                th.start(); e0.record()
+                for it in range(reps): ops.mmv_partial(px, pc, rhs, 20.0, part)
+                e1.record(); torch.cuda.synchronize(); stop.set(); th.join()
+                os.environ["ODF_TILE_DEBUG"] = "16"
+                ops.mmv_partial(px, pc, rhs, 20.0, part); torch.cuda.synchronize()     # in-kernel clock, hot chip
+                os.environ["ODF_TILE_DEBUG"] = "0"
+                time.sleep(2.0)
+                os.environ["ODF_TILE_DEBUG"] = "16"
+                ops.mmv_partial(px, pc, rhs, 20.0, part); torch.cuda.synchronize()     # in-kernel clock, after idling
+                os.environ["ODF_TILE_DEBUG"] = "17"
+                ops.mmv_partial(px, pc, rhs, 20.0, part); torch.cuda.synchronize()     # no TMA
+                for fl in (17, 25, 89, 88):                              # no TMA, no PV; S-MMA N = 128, 64, 192, 256
+                    os.environ["ODF_TILE_DEBUG"] = str(fl)
+                    ops.mmv_partial(px, pc, rhs, 20.0, part); torch.cuda.synchronize()
+                os.environ["ODF_TILE_DEBUG"] = "0"
+                clk.sort(); pw.sort()
+                print(f"sustained: {e0.elapsed_time(e1) / reps:.2f} ms/launch  sm_mhz median={clk[len(clk) // 2]} min={clk[0]} max={clk[-1]}  power median={pw[len(pw) // 2]:.0f} W max={pw[-1]:.0f} W")
+                print(f"bottleneck kind={kind} n={n} M={M} d={d} T={T} ms by flags(1=noTMA,2=noSMMA,4=noEpi,8=noPV): " + " ".join(res))
     elif stage == "precision":
         # near-duplicate pairs: K_MM diagonal and small-distance entries, where the 3-pass product and
         # the truncating tensor-core accumulator matter most
