@@ -30,6 +30,8 @@ WORKLOADS = {
     "c2": (1_000_000, 1024, 10_000, 30, 20.0, 1e-3),
     "c1": (20_000, 1024, 1_000, 21, 15.0, 1e-3),
     "c4": (5_000_000, 256, 5_000, 15, 50.0, 1e-3),
+    "c3": (20_000_000, 256, 30_000, 21, 10.0, 1e-6),     # per-pixel mask head; needs --gpus 8 (or --n for one GPU's share)
+    "c5": (1_000_000, 1024, 10_000, 30, 20.0, 1e-3),     # batched predict K(X, C) alpha (--workload c5 times predict, not fit)
 }
 CPU_SAMPLE = (20_000, 1_000)        # rows / centres of the CPU-baseline sample
 
@@ -233,6 +235,9 @@ def run_ours(args):
     Yd.copy_(Yh)
     group = None if world > 1 else False
 
+    if args.workload == "c5":
+        return run_predict(args, odf, ops, dist, world, rank, dev, Xh, Xd, centres, mean, scale, N, d, M, T, sigma, n_local)
+
     def one_fit():
         m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=group)
         m.fit(Xd, Yd, centres=centres, zscore=(mean, scale))
@@ -356,6 +361,95 @@ def run_ours(args):
                        "parallelism": "rows sharded over %d GPU(s), 1 all-reduce of M x T per sweep" % world},
             "fit_s": ms_dev * 1e-3, "phases_ms": phase, "sweeps_per_fit": 23,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_predict(args, odf, ops, dist, world, rank, dev, Xh, Xd, centres, mean, scale, N, d, M, T, sigma, n_local):
+    """BASELINE config 5: batched FALKON predict, scores = K(X, C) alpha for N test RoIs x M centres x T classes
+    (the `kernel.mmv(X, nystrom_parallel, alpha_parallel)` call of roi_box_predictors.py:158).  Rows are sharded
+    over the ranks, no collective.  One step = all N rows scored once."""
+    import torch
+    g = torch.Generator().manual_seed(7)
+    alpha = (torch.randn(M, T, generator=g) * 0.1).to(dev)
+    model = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=1e-3, M=M)
+    Cn = ops.zscore_(centres.clone(), mean, scale)
+    model.ny_points_, model.alpha_ = Cn, alpha
+    Xn = ops.zscore_(Xd.clone(), mean, scale)
+    out = torch.empty((n_local, T), device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def mx(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step():
+        return model.predict(Xn)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    ops.TILE_EVENTS = []
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        scores = step()
+    e1.record()
+    sync_all()
+    launches = ops.LAUNCHES - l0
+    ev, ops.TILE_EVENTS = ops.TILE_EVENTS, None
+    clocks = sampler.stop()
+    ms = mx(e0.elapsed_time(e1)) / args.steps
+    F = 2.0 * N * M * (d + T)
+    tile_ms = sum(a.elapsed_time(b) for (a, b, *_r) in ev)
+    tile_alg = sum(2.0 * r * c_ * (dd + tt) for (_a, _b, r, c_, dd, tt) in ev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    # e2e: raw host features in, scores back on the host
+    Xd.copy_(Xh, non_blocking=True)
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        Xd.copy_(Xh, non_blocking=True)
+        Xz = ops.zscore_(Xd, mean, scale)
+        host_scores = model.predict(Xz).cpu()
+    t1.record()
+    sync_all()
+    ms_e2e = mx(t0.elapsed_time(t1)) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "falkon_predict_gflops", "value": F / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (3-pass split-fp16 tensor-core products, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "c5: batched FALKON predict N=%d d=%d M=%d T=%d sigma=%g (BASELINE config 5)" % (N, d, M, T, sigma),
+                       "rows_per_gpu": n_local, "l2_policy": "inputs far larger than L2; no flush needed",
+                       "parallelism": "rows sharded over %d GPU(s), no collective" % world},
+            "rois_per_s": N / (ms * 1e-3), "clocks": clocks,
+            "e2e": {"value": F / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(N) * d * 4, "d2h_bytes_per_step": int(N) * T * 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gauss_tile_kernel<f16 split operands>", "achieved": tile_alg / max(tile_ms, 1e-9) / 1e9,
+                         "peak": peak, "unit": "TFLOP/s", "frac": tile_alg / max(tile_ms, 1e-9) / 1e9 / peak, "traffic": None,
+                         "tile_share_of_step": tile_ms / args.steps / ms,
+                         "note": "3 tensor passes per product: frac is capped at 1/3"},
+            "cpu_baseline": None}))
     if world > 1:
         dist.destroy_process_group()
 

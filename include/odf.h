@@ -178,6 +178,34 @@ int odf_axpby(float* out, float alpha, const float* A, float beta, const float* 
               int64_t T, int64_t ld, void* stream);
 size_t odf_cg_workspace_bytes(int64_t M, int64_t T);
 
+/* ---- index / integer side: minibootstrap selection, box decode, detection post-processing ---- */
+/* Stable stream compaction: idx_out[0..*count_out) = ascending indices i in [0, n) with
+ * scores[i * stride] > thresh (strict != 0) or >= thresh (strict == 0) -- bit-identical to
+ * `torch.where(scores > thr)[0]`, the hard- / easy-negative selection of the minibootstrap
+ * (src/modules/region-classifier/OnlineRegionClassifier_incore.py:117-118, 133-134).  idx_out holds n
+ * entries; count_out is a DEVICE int; ws >= odf_select_workspace_bytes(n).                        */
+size_t odf_select_workspace_bytes(int64_t n);
+int odf_select_indices(const float* scores, int64_t n, int64_t stride, float thresh, int strict, int64_t* idx_out,
+                       int* count_out, void* ws, size_t ws_bytes, void* stream);
+/* dst[k, 0:d] = src[idx[k], 0:d] for k < *count (device count, at most max_rows): `X[idx]` appended to a
+ * pre-allocated cache instead of torch.cat (same file, :119, :135).                                 */
+int odf_gather_rows(const float* src, int64_t ld_src, const int64_t* idx, const int* count, int64_t max_rows, int64_t d,
+                    float* dst, int64_t ld_dst, void* stream);
+/* py_od_utils.decode_boxes_detector (src/py_od_utils.py:247-274): ex_boxes [R x 4], deltas / out [R x 4*Tc],
+ * legacy +1 widths, x2 = ctr + w/2 - 1, clamped to [0, img-1].                                      */
+int odf_decode_boxes(const float* ex_boxes, const float* deltas, int64_t R, int64_t Tc, float img_w, float img_h, float* out,
+                     void* stream);
+/* OnlineDetectionPostProcessor.filter_results (src/modules/accuracy-evaluator/OnlineDetectionPostProcessor.py:35-79):
+ * boxes [R x 4*Tc], scores [R x Tc] (column 0 = background); per class 1..Tc-1: score > score_thresh,
+ * greedy NMS in descending score order, suppress when IoU(+1 convention) > nms_thresh (maskrcnn-benchmark
+ * boxlist_nms / _C.nms semantics, kept boxes in ascending RoI order); classes concatenated; if more than
+ * dets_per_img survive keep those with score >= the dets_per_img-th largest (kthvalue rule, ties kept).
+ * Outputs hold R*(Tc-1) entries; out_rois = source RoI index; out_count is a DEVICE int.           */
+size_t odf_postprocess_workspace_bytes(int64_t R, int64_t Tc);
+int odf_detect_postprocess(const float* boxes, const float* scores, int64_t R, int64_t Tc, float score_thresh,
+                           float nms_thresh, int dets_per_img, float* out_boxes, float* out_scores, int64_t* out_labels,
+                           int64_t* out_rois, int* out_count, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -548,6 +548,10 @@ int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t row_bytes) {
   // (b) row blocks too fat for L2 when every SM streams its own: make ~12 CTAs share one
   const int64_t rb_bytes = static_cast<int64_t>(BM) * row_bytes * 2;
   if (rb_bytes * sms > (48ll << 20) && splits < 12) splits = 12;
+  // (c) the W accumulator lives in TMEM across the column tiles of one item and the tensor core adds with
+  // truncation: the bias grows with the chain length (measured 1.3e-4 relative at 235 tiles, 5e-6 at 7),
+  // so a chain is at most 8 tiles; the partial slabs are summed in fp32 round-to-nearest by odf_finish_*
+  if (splits * 8 < n_ct) splits = (n_ct + 7) / 8;
   // keep at least 4 column tiles per item so the pipeline fill/drain stays amortised
   const int64_t max_splits = n_ct >= 4 ? n_ct / 4 : 1;
   if (splits > max_splits) splits = max_splits;

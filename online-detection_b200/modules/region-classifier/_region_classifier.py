@@ -85,6 +85,97 @@ class OnlineRegionClassifierBase(rcA.RegionClassifierAbstract):
     def _stage(self, t):
         return t.cpu() if self.HOST_CACHE else t
 
+    # ------------------------------------------------------------------ GPU-resident cache (in-core flavour)
+    # The reference grows / prunes the per-class cache with torch.where + indexing + torch.cat
+    # (…_incore.py:117-119, 133-135), i.e. a fresh allocation and copy of the whole cache per step.  Here the
+    # cache is ONE pre-allocated buffer [positives | negatives] (capacity = all batches of the class) with a
+    # twin for pruning; hard / easy rows are picked by odf_select_indices (stable compaction, identical to
+    # torch.where) and moved by odf_gather_rows straight into place; X = buffer[:P + n] needs no torch.cat.
+    def _gpu_cache_ok(self, positives_i, negatives_i):
+        if self.HOST_CACHE or not torch.is_tensor(positives_i) or not positives_i.is_cuda:
+            return False
+        return all(torch.is_tensor(b) and b.is_cuda and b.dtype == torch.float32 and b.dim() == 2 for b in negatives_i) \
+            and positives_i.dtype == torch.float32
+
+    class _GpuCache:
+        def __init__(self, pos, neg_batches):
+            from odf import ops
+            self.ops = ops
+            self.P, self.d = int(pos.shape[0]), int(pos.shape[1])
+            cap = self.P + sum(int(b.shape[0]) for b in neg_batches)
+            self.buf = [torch.empty((cap, self.d), dtype=torch.float32, device=pos.device) for _ in range(2)]
+            self.cur = 0
+            self.buf[0][:self.P].copy_(pos)
+            self.buf[1][:self.P].copy_(pos)
+            self.n = 0
+
+        @property
+        def X(self):
+            return self.buf[self.cur][:self.P + self.n]
+
+        @property
+        def neg(self):
+            return self.buf[self.cur][self.P:self.P + self.n]
+
+        def append_all(self, batch):
+            k = int(batch.shape[0])
+            self.buf[self.cur][self.P + self.n:self.P + self.n + k].copy_(batch)
+            self.n += k
+
+        def append_selected(self, batch, scores, thresh):
+            idx, cnt = self.ops.select_indices(scores, thresh, strict=True)          # scores > HARD_THRESH
+            self.ops.gather_rows(batch, idx, cnt, self.buf[self.cur][self.P + self.n:], max_rows=int(batch.shape[0]))
+            k = int(cnt.item())
+            self.n += k
+            return k, idx[:k]
+
+        def keep_selected(self, scores, thresh):
+            idx, cnt = self.ops.select_indices(scores, thresh, strict=False)         # scores >= EASY_THRESH
+            other = 1 - self.cur
+            self.ops.gather_rows(self.neg, idx, cnt, self.buf[other][self.P:], max_rows=self.n)
+            k = int(cnt.item())
+            removed = self.n - k
+            self.cur, self.n = other, k
+            return removed, idx[:k]
+
+    def _train_class_gpu_cache(self, i, positives_i, negatives_i):
+        """One class of trainWithMinibootstrap on the pre-allocated GPU cache (same decisions, same order of
+        rows, same prints as the generic path below)."""
+        cache = self._GpuCache(positives_i, negatives_i)
+        model = None
+        n_batches = len(negatives_i)
+        ones = torch.ones(cache.P, device=positives_i.device)
+        for j in range(n_batches):
+            t_iter = time.time()
+            last = j == n_batches - 1
+            if j == 0:
+                cache.append_all(negatives_i[0])
+            else:
+                t_hard = time.time()
+                scores = self.classifier.predict(model, negatives_i[j])
+                k, _ = cache.append_selected(negatives_i[j], scores, self.hard_tresh)
+                print("Hard negatives selected in {} seconds".format(time.time() - t_hard))
+                print("Chosen {} hard negatives from the {}th batch".format(k, j))
+            print("Traning with {} positives and {} negatives".format(cache.P, cache.n))
+            t_update = time.time()
+            y = torch.cat((ones, -torch.ones(cache.n, device=ones.device)), 0)
+            if self.sigma is not None and self.lam is not None:
+                print("Updating model with lambda: {} and sigma: {}".format(self.lam, self.sigma))
+                model = self.classifier.train(cache.X, y, sigma=self.sigma, lam=self.lam)
+            else:
+                print("Updating model with default lambda and sigma")
+                model = self.classifier.train(cache.X, y)
+            print("Model updated in {} seconds".format(time.time() - t_update))
+            t_easy = time.time()
+            if cache.n != 0 and not last:
+                scores = self.classifier.predict(model, cache.neg)
+                removed, _ = cache.keep_selected(scores, self.easy_tresh)
+                print("Easy negatives selected in {} seconds".format(time.time() - t_easy))
+                print("Removed {} easy negatives. {} Remaining".format(removed, cache.n))
+                print("Iteration {}th done in {} seconds".format(j, time.time() - t_iter))
+        out_cache = {"pos": positives_i, "neg": cache.neg.clone()} if self.return_caches else None
+        return model, out_cache
+
     # ------------------------------------------------------------------ minibootstrap
     def trainWithMinibootstrap(self, negatives, positives, output_dir=None):
         caches, model = [], []
@@ -95,6 +186,11 @@ class OnlineRegionClassifierBase(rcA.RegionClassifierAbstract):
                 caches.append({})
                 continue
             print("---------------------- Training Class number {} ----------------------".format(i))
+            if self._gpu_cache_ok(positives[i], negatives[i]):
+                m, c = self._train_class_gpu_cache(i, positives[i], negatives[i])
+                model.append(m)
+                caches.append(c)
+                continue
             n_batches = len(negatives[i])
             for j in range(n_batches):
                 t_iter = time.time()

@@ -54,6 +54,13 @@ SIGNATURES = {
     "odf_cg_xpby_b": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_fp, c_fp]),
     "odf_axpby": (c_int, [c_fp, c_f, c_fp, c_f, c_fp, c_i64, c_i64, c_i64, c_fp]),
     "odf_cg_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "odf_select_workspace_bytes": (c_sz, [c_i64]),
+    "odf_select_indices": (c_int, [c_fp, c_i64, c_i64, c_f, c_int, c_fp, c_fp, c_fp, c_sz, c_fp]),
+    "odf_gather_rows": (c_int, [c_fp, c_i64, c_fp, c_fp, c_i64, c_i64, c_fp, c_i64, c_fp]),
+    "odf_decode_boxes": (c_int, [c_fp, c_fp, c_i64, c_i64, c_f, c_f, c_fp, c_fp]),
+    "odf_postprocess_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "odf_detect_postprocess": (c_int, [c_fp, c_fp, c_i64, c_i64, c_f, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                       c_sz, c_fp]),
 }
 
 ODF_OP_MMV, ODF_OP_DMMV, ODF_OP_KMM, ODF_OP_PRECOND = 0, 1, 2, 3

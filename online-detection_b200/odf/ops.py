@@ -396,3 +396,71 @@ class Sweeper:
             panel_tmm(self.panel, self.Wc[:n], n, self.cols.n, self.part3[slab:slab + S])
             slab += S
         return finish_rows(self.part3, self.T, out, scale)
+
+
+# ---- index side: selection / gather (minibootstrap), box decode, detection post-processing ----
+def select_indices(scores, thresh, strict=True):
+    """Stable compaction: (idx, count) with idx[:count] == torch.where(scores > thresh)[0] (>= when not
+    strict).  `count` stays on the device (int32 tensor); idx has len(scores) entries."""
+    L = _lib.load()
+    s = _req(scores, "scores")
+    if s.dim() == 2 and s.shape[1] == 1:
+        s = s[:, 0]
+    assert s.dim() == 1
+    n = int(s.shape[0])
+    idx = torch.empty((max(n, 1),), dtype=torch.int64, device=s.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=s.device)
+    wsb = int(L.odf_select_workspace_bytes(n))
+    ws = torch.empty((max(wsb, 8),), dtype=torch.uint8, device=s.device)
+    check(L.odf_select_indices(ptr(s), n, s.stride(0) if n else 1, float(thresh), 1 if strict else 0, ptr(idx),
+                               ptr(count), ptr(ws), wsb, _stream()), "odf_select_indices")
+    _count(3)
+    return idx, count
+
+
+def gather_rows(src, idx, count, dst, max_rows=None):
+    """dst[k] = src[idx[k]] for k < count (device count)."""
+    L = _lib.load()
+    src = _req(src, "src", 2)
+    assert src.stride(1) == 1 and dst.stride(1) == 1 and dst.shape[1] >= src.shape[1]
+    mr = int(min(idx.shape[0], dst.shape[0]) if max_rows is None else max_rows)
+    check(L.odf_gather_rows(ptr(src), src.stride(0), ptr(idx), ptr(count), mr, src.shape[1], ptr(dst), dst.stride(0),
+                            _stream()), "odf_gather_rows")
+    _count(1)
+    return dst
+
+
+def decode_boxes(ex_boxes, deltas, img_w, img_h):
+    L = _lib.load()
+    ex = _req(ex_boxes, "boxes", 2).contiguous()
+    dl = _req(deltas, "deltas", 2).contiguous()
+    R, Tc = int(dl.shape[0]), int(dl.shape[1]) // 4
+    out = torch.empty_like(dl)
+    check(L.odf_decode_boxes(ptr(ex), ptr(dl), R, Tc, float(img_w), float(img_h), ptr(out), _stream()), "odf_decode_boxes")
+    _count(1)
+    return out
+
+
+def detect_postprocess(boxes, scores, score_thresh, nms_thresh, dets_per_img):
+    """filter_results on the GPU.  Returns (boxes [k,4], scores [k], labels [k], rois [k]) trimmed to the
+    surviving detections (one device->host read of the count)."""
+    L = _lib.load()
+    b = _req(boxes, "boxes", 2).contiguous()
+    s = _req(scores, "scores", 2).contiguous()
+    R, Tc = int(s.shape[0]), int(s.shape[1])
+    assert b.shape[0] == R and b.shape[1] == 4 * Tc
+    cap = max(R * (Tc - 1), 1)
+    dev = s.device
+    ob = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+    os_ = torch.empty((cap,), dtype=torch.float32, device=dev)
+    ol = torch.empty((cap,), dtype=torch.int64, device=dev)
+    orr = torch.empty((cap,), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    wsb = int(L.odf_postprocess_workspace_bytes(R, Tc))
+    ws = torch.empty((max(wsb, 8),), dtype=torch.uint8, device=dev)
+    check(L.odf_detect_postprocess(ptr(b), ptr(s), R, Tc, float(score_thresh), float(nms_thresh), int(dets_per_img),
+                                   ptr(ob), ptr(os_), ptr(ol), ptr(orr), ptr(cnt), ptr(ws), wsb, _stream()),
+          "odf_detect_postprocess")
+    _count(6)
+    k = int(cnt.item())
+    return ob[:k], os_[:k], ol[:k], orr[:k]

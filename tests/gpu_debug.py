@@ -202,7 +202,7 @@ def run_stage(stage):
             print(f"perf mmv kind={kind} n={n} M={M} d={d} T={T} S={part.shape[0]}: {ms:.2f} ms  alg={fl / ms / 1e9:.1f} TFLOP/s")
     elif stage == "panel":
         from odf import ops
-        for (n, M, d, T) in [(300, 200, 40, 21), (5000, 1000, 256, 30), (4096, 777, 64, 5), (131072, 10000, 1024, 30)]:
+        for (n, M, d, T) in [(300, 200, 40, 21), (5000, 1000, 256, 30), (4096, 777, 64, 5), (131072, 10000, 1024, 30), (262144, 5000, 256, 15), (131072, 30000, 256, 21)]:
             sigma = 15.0
             X = _data(n, d, 5); C = _data(M, d, 6)
             V = torch.randn(M, T, device="cuda")
