@@ -178,6 +178,15 @@ int odf_axpby(float* out, float alpha, const float* A, float beta, const float* 
               int64_t T, int64_t ld, void* stream);
 size_t odf_cg_workspace_bytes(int64_t M, int64_t T);
 
+/* Pieces of odf_precond_init for the row-sharded multi-GPU fit, where the O(M^3) steps are split over the
+ * ranks (column blocks of T T^T and of the two explicit inverses, all-gathered by the host side):
+ * in-place Cholesky A = U^T U of a row-major symmetric matrix (upper factor left in A, strict lower triangle
+ * zeroed; synchronises the stream to read cuSOLVER's info), diagonal shift, triangle clear.
+ * ws >= odf_workspace_bytes(ODF_OP_PRECOND, 0, M, 0, 1).                                              */
+int odf_potrf_upper(float* A, int64_t M, void* ws, size_t ws_bytes, void* stream);
+int odf_add_diag(float* A, int64_t M, float value, void* stream);
+int odf_zero_strict_lower(float* A, int64_t M, void* stream);
+
 /* ---- index / integer side: minibootstrap selection, box decode, detection post-processing ---- */
 /* Stable stream compaction: idx_out[0..*count_out) = ascending indices i in [0, n) with
  * scores[i * stride] > thresh (strict != 0) or >= thresh (strict == 0) -- bit-identical to

@@ -341,6 +341,40 @@ int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void
   return ODF_OK;
 }
 
+/* Building blocks of the same preconditioner for the row-sharded multi-GPU fit, where the O(M^3) pieces are
+ * split over the ranks (odf/falkon.py::_build_preconditioner): in-place Cholesky of a row-major symmetric
+ * matrix into its upper factor, diagonal shift, triangle clear. */
+int odf_potrf_upper(float* A, int64_t M, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= 0 || M > 0x7fffffff) return set_error(ODF_ERR_ARG, "potrf_upper: bad M");
+  int rc;
+  if ((rc = ensure_handles(st))) return rc;
+  const int m = static_cast<int>(M);
+  int lwork = 0;
+  if (cusolverDnSpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_LOWER, m, A, m, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf_bufferSize failed");
+  Arena a(ws, ws_bytes);
+  int* info = a.take<int>(2);
+  float* work = a.take<float>(static_cast<size_t>(lwork));
+  if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "potrf_upper: workspace too small");
+  // row-major upper U == column-major lower L = U^T
+  if (cusolverDnSpotrf(g_cusolver, CUBLAS_FILL_MODE_LOWER, m, A, m, work, lwork, info) != CUSOLVER_STATUS_SUCCESS)
+    return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf failed to launch");
+  if ((rc = zero_lower(A, M, st))) return rc;
+  int hinfo = 0;
+  cudaError_t e = cudaMemcpyAsync(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_cuda_error(e, "potrf_upper");
+  if (hinfo != 0) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "Cholesky failed: info=%d (matrix not positive definite)", hinfo);
+    return set_error(ODF_ERR_LINALG, buf);
+  }
+  return ODF_OK;
+}
+int odf_add_diag(float* A, int64_t M, float value, void* stream) { return add_diag(A, M, value, static_cast<cudaStream_t>(stream)); }
+int odf_zero_strict_lower(float* A, int64_t M, void* stream) { return zero_lower(A, M, static_cast<cudaStream_t>(stream)); }
+
 int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t ldb, int which, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;

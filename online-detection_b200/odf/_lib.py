@@ -54,6 +54,9 @@ SIGNATURES = {
     "odf_cg_xpby_b": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_fp, c_fp]),
     "odf_axpby": (c_int, [c_fp, c_f, c_fp, c_f, c_fp, c_i64, c_i64, c_i64, c_fp]),
     "odf_cg_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "odf_potrf_upper": (c_int, [c_fp, c_i64, c_fp, c_sz, c_fp]),
+    "odf_add_diag": (c_int, [c_fp, c_i64, c_f, c_fp]),
+    "odf_zero_strict_lower": (c_int, [c_fp, c_i64, c_fp]),
     "odf_select_workspace_bytes": (c_sz, [c_i64]),
     "odf_select_indices": (c_int, [c_fp, c_i64, c_i64, c_f, c_int, c_fp, c_fp, c_fp, c_sz, c_fp]),
     "odf_gather_rows": (c_int, [c_fp, c_i64, c_fp, c_fp, c_i64, c_i64, c_fp, c_i64, c_fp]),

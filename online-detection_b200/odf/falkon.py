@@ -46,6 +46,8 @@ class FalkonOptions:
         # "panel": K is evaluated once per sweep, its tiles are spilled to a transient row panel and
         # contracted by the panel kernel; "recompute": evaluate K twice (no panel workspace)
         self.sweep_mode = ignored.pop("sweep_mode", "panel")
+        # multi-GPU fits split T T^T and the explicit inverses over the ranks (False: every rank builds all)
+        self.distributed_precond = ignored.pop("distributed_precond", True)
         self.ignored = dict(ignored)
 
 
@@ -160,9 +162,9 @@ class _TriFactor:
 class _InvFactor:
     """Upper-triangular factor applied through its explicit inverse (one GEMM per application)."""
 
-    def __init__(self, be, Tri):
+    def __init__(self, be, Tri, Inv=None):
         self.be = be
-        self.Inv = be.precond_invert(Tri)
+        self.Inv = be.precond_invert(Tri) if Inv is None else Inv
 
     def solve(self, b, out, transposed):
         return self.be.precond_apply(self.Inv, b, out, transposed)
@@ -264,13 +266,8 @@ class Falkon:
             centres = be.zscore_(centres.clone(), zs[0], zs[1])     # ny_points_ live in normalised space
         tm.mark()
 
-        # ---- preconditioner (built once per fit, replicated on every rank) --------------------
-        Kmm = be.kmm(pc, sigma)
-        Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
-        if opt.precond_apply == "inverse":
-            Tm, Am = _InvFactor(be, Tm), _InvFactor(be, Am)
-        else:
-            Tm, Am = _TriFactor(be, Tm), _TriFactor(be, Am)
+        # ---- preconditioner (built once per fit; the factors end up replicated on every rank) ----
+        Tm, Am = self._build_preconditioner(be, pc, sigma, lam, dist if world > 1 else None, group, world)
         tm.mark()
 
         alpha = torch.empty((M, T), dtype=torch.float32, device=dev)
@@ -289,6 +286,65 @@ class Falkon:
         self.fit_times_ = {"prepare_ms": tm.ms(0, 1), "precond_ms": tm.ms(1, 2), "cg_ms": tm.ms(2, 3),
                            "cg_iters": iters, "sweeps": self._sweeps, "N": N, "M": M, "T": T}
         return self
+
+    def _build_preconditioner(self, be, pc, sigma, lam, dist, group, world):
+        """T = chol(K_MM + eps M I), A = chol(T T^T / M + lam I) and (default) their explicit inverses
+        (SURVEY Appendix A.3).  Single rank: one odf_precond_init call.  Row-sharded fit: the two Cholesky
+        factorisations stay replicated (sequential, ~M^3/3 each), but T T^T and the two inverses -- three of
+        the five O(M^3) steps -- are computed as COLUMN BLOCKS, one per rank, and all-gathered, so the
+        serial fraction of the multi-GPU fit shrinks with the world size.  Every rank ends with bitwise
+        identical factors (each block is computed once and broadcast by the gather)."""
+        opt = self.options
+        Kmm = be.kmm(pc, sigma)
+        M = Kmm.shape[0]
+        split = dist is not None and world > 1 and getattr(opt, "distributed_precond", True) and M >= 4 * world \
+            and hasattr(be, "potrf_upper_")
+        if not split:
+            Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
+            if opt.precond_apply == "inverse":
+                return _InvFactor(be, Tm), _InvFactor(be, Am)
+            return _TriFactor(be, Tm), _TriFactor(be, Am)
+        rank = dist.get_rank(group)
+        dev, dt = Kmm.device, Kmm.dtype
+        Mc = -(-M // world)
+        Mc = -(-Mc // 4) * 4                                  # equal, 16-byte aligned blocks (the last may be short)
+        c0, c1 = min(M, rank * Mc), min(M, (rank + 1) * Mc)
+
+        def gather_columns(block):                            # block: (M x Mc), my columns first
+            flat = torch.empty((world * M, Mc), dtype=dt, device=dev)
+            dist.all_gather_into_tensor(flat, block.contiguous(), group=group)
+            parts = flat.view(world, M, Mc)
+            full = torch.empty((M, M), dtype=dt, device=dev)
+            for r in range(world):
+                a, b = min(M, r * Mc), min(M, (r + 1) * Mc)
+                if b > a:
+                    full[:, a:b].copy_(parts[r, :, :b - a])
+            return full
+
+        be.add_diag_(Kmm, opt.pc_epsilon_32 * M)
+        Tri_T = be.potrf_upper_(Kmm)                          # replicated
+        # my columns of T T^T: (T T^T)[:, c0:c1] = T . (T[c0:c1, :])^T
+        rows_t = torch.zeros((M, Mc), dtype=dt, device=dev)
+        if c1 > c0:
+            rows_t[:, :c1 - c0].copy_(Tri_T[c0:c1, :].t())
+        G = torch.empty_like(rows_t)
+        be.precond_apply(Tri_T, rows_t, G, False)
+        A0 = gather_columns(G)
+        be.axpby(A0, 1.0 / M, A0)
+        be.add_diag_(A0, lam)
+        Tri_A = be.potrf_upper_(A0)                           # replicated
+        if opt.precond_apply != "inverse":
+            return _TriFactor(be, Tri_T), _TriFactor(be, Tri_A)
+        factors = []
+        for Tri in (Tri_T, Tri_A):
+            E = torch.zeros((M, Mc), dtype=dt, device=dev)    # my columns of the identity
+            if c1 > c0:
+                E[c0:c1, :c1 - c0].fill_diagonal_(1.0)
+            be.precond_solve_(Tri, E, SOLVE_T)                # Tri^-1 I[:, c0:c1]
+            Inv = gather_columns(E)
+            be.zero_lower_(Inv)
+            factors.append(_InvFactor(be, Tri, Inv))
+        return factors[0], factors[1]
 
     def _solve_block(self, px, pc, Yb, Tm, Am, N, sigma, lam, alpha_out, dist, group):
         be = self._be

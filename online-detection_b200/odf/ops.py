@@ -249,6 +249,30 @@ def precond_init(Tm, lam, eps):
     return Tm, Am
 
 
+def potrf_upper_(A):
+    """In-place Cholesky of a symmetric row-major matrix into its upper factor (A = U^T U)."""
+    L = _lib.load()
+    M = A.shape[0]
+    assert A.is_contiguous()
+    wsb = int(L.odf_workspace_bytes(_lib.ODF_OP_PRECOND, 0, M, 0, 1))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=A.device)
+    check(L.odf_potrf_upper(ptr(A), M, ptr(ws), wsb, _stream()), "odf_potrf_upper")
+    _count(1)
+    return A
+
+
+def add_diag_(A, value):
+    check(_lib.load().odf_add_diag(ptr(A), A.shape[0], float(value), _stream()), "odf_add_diag")
+    _count(1)
+    return A
+
+
+def zero_lower_(A):
+    check(_lib.load().odf_zero_strict_lower(ptr(A), A.shape[0], _stream()), "odf_zero_strict_lower")
+    _count(1)
+    return A
+
+
 def precond_solve_(Tri, B, which):
     L = _lib.load()
     assert B.stride(1) == 1

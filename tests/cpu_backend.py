@@ -30,6 +30,21 @@ def precond_init(K, lam, eps):
     return T, A
 
 
+def potrf_upper_(A):
+    A.copy_(torch.linalg.cholesky(A, upper=True))
+    return A
+
+
+def add_diag_(A, value):
+    A.diagonal().add_(value)
+    return A
+
+
+def zero_lower_(A):
+    A.triu_()
+    return A
+
+
 def precond_solve_(Tri, B, which):
     tr = which in (1, 3)
     sol = torch.linalg.solve_triangular(Tri.T if tr else Tri, B.to(DT), upper=not tr)

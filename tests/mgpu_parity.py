@@ -1,0 +1,69 @@
+"""Multi-GPU parity script (run under torchrun on a GPU box; not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_parity.py
+
+Row-sharded NCCL fit (distributed and replicated preconditioner) vs the single-GPU fit of the same data on
+rank 0 and vs the fp64 CPU oracle: alpha and scores must agree within the 1e-3 parity bar."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "online-detection_b200")):
+    sys.path.insert(0, p)
+import odf  # noqa: E402
+from oracle import falkon_oracle as orc  # noqa: E402
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    N, d, T, M, sigma, lam = 40000, 256, 7, 1500, 15.0, 1e-4
+    X, c, Y = orc.make_synthetic(N, d, T, seed=0)
+    C = X[orc.shared_centres(c, M, seed=1)]
+    lo, hi = (N * rank) // world, (N * (rank + 1)) // world
+    ok = True
+    res = {}
+    for name, opts in (("distributed_precond", {}), ("replicated_precond", {"distributed_precond": False})):
+        m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=None,
+                             options=odf.FalkonOptions(**opts))
+        m.fit(X[lo:hi].to(dev), Y[lo:hi].to(dev), centres=C.to(dev))
+        res[name] = (m.alpha_.clone(), dict(m.fit_times_))
+        # every rank must hold the same alpha
+        a0 = m.alpha_.clone()
+        dist.broadcast(a0, src=0)
+        same = bool(torch.equal(a0, m.alpha_))
+        flag = torch.tensor([1.0 if same else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("%s: alpha bitwise identical on all ranks: %s   precond_ms=%.1f cg_ms=%.1f" % (
+                name, bool(flag.item()), m.fit_times_["precond_ms"], m.fit_times_["cg_ms"]))
+        ok &= bool(flag.item())
+    if rank == 0:
+        single = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M)
+        single.fit(X.to(dev), Y.to(dev), centres=C.to(dev))
+        alpha64 = orc.falkon_fit(X, Y, C, sigma, lam, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+        Xt = X[:3000]
+        s_ref = orc.falkon_predict(Xt, C, alpha64, sigma)
+        for name, (alpha, _) in res.items():
+            mm = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M)
+            mm.ny_points_, mm.alpha_ = C.to(dev), alpha
+            e_single = rel(mm.predict(Xt.to(dev)), single.predict(Xt.to(dev)))
+            e_oracle = rel(mm.predict(Xt.to(dev)).cpu(), s_ref)
+            print("%s (world %d): scores vs single-GPU fit %.2e, vs fp64 oracle %.2e" % (name, world, e_single, e_oracle))
+            ok &= e_single < 1e-3 and e_oracle < 1e-3
+        print("MGPU_PARITY_PASS" if ok else "MGPU_PARITY_FAIL")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
