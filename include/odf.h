@@ -100,6 +100,28 @@ int odf_gauss_mmv_prepared_spill(int kind, const void* r_hi, const void* r_lo, c
 int odf_panel_splits(int64_t n_rows, int64_t M);
 int odf_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, int64_t M, int T_pad,
                   int n_splits, float* out_partial, void* stream);
+/* Tensor-core variant of the spill + panel pair (the default sweep): the tile writes its K tiles as two fp16
+ * planes, hi = rn16(K) and lo = rn16((K - hi) 2^12), tile-blocked
+ * [plane][column tile][row block][half][128 rows][64 centres] (odf_panel16_bytes(n_rows, n_cols) bytes,
+ * 128-byte aligned); odf_finish_w16 reduces the partial slabs of the first contraction into W = K v (+ addend)
+ * [n_rows x T_pad] and splits it into W16 [round_up(n_rows,128) x 64] fp16 (hi | lo, common power-of-two scale
+ * derived from max|W|, left in *absmax); odf_panel16_tmm streams the planes once from HBM and contracts
+ * out_partial[s][c][0..T_pad) = sum_r K[r][c] W[r][.] with tcgen05 kind::f16 MMAs on MN-major operands
+ * (three split products, fp32 accumulation chains of 2048 rows).  n_splits = odf_panel16_splits(n_rows, M).
+ * Replaces the K_blk^T w half of falkon GaussianKernel.dmmv (...incore.py:68).                               */
+size_t odf_panel16_bytes(int64_t n_rows, int64_t n_cols);
+int odf_gauss_mmv_prepared_spill16(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
+                                   const float* r_opscale, int64_t n_rows, const void* q_hi,
+                                   const void* q_lo, const float* q_sqnorm, const float* q_opscale,
+                                   int64_t n_cols, int64_t d, const float* vt_hi, const float* vt_lo,
+                                   int64_t ldvt, int T_pad, int n_splits, float sigma, float* partial,
+                                   void* panel16, void* stream);
+int odf_finish_w16(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T,
+                   const float* addend, int64_t ld_add, float* w_f32, void* absmax, void* w16,
+                   void* stream);
+int odf_panel16_splits(int64_t n_rows, int64_t M);
+int odf_panel16_tmm(const void* panel16, int64_t n_rows, int64_t M, const void* w16, const void* absmax,
+                    int T_pad, int n_splits, float* out_partial, void* stream);
 /* out[r, t] = scale * sum_s partial[s][r][t] + addend[r, t]   (addend may be NULL) */
 int odf_finish_rows(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T,
                     float scale, const float* addend, int64_t ld_add, float* out, int64_t ldo,

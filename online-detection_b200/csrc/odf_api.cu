@@ -168,6 +168,37 @@ int odf_gauss_mmv_prepared_spill(int kind, const void* r_hi, const void* r_lo, c
   return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
 }
 
+size_t odf_panel16_bytes(int64_t n_rows, int64_t n_cols) { return panel16_bytes(n_rows, n_cols); }
+int odf_panel16_splits(int64_t n_rows, int64_t M) { return panel16_splits(n_rows, M); }
+int odf_gauss_mmv_prepared_spill16(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
+                                   const float* r_opscale, int64_t n_rows, const void* q_hi, const void* q_lo,
+                                   const float* q_sqnorm, const float* q_opscale, int64_t n_cols, int64_t d,
+                                   const float* vt_hi, const float* vt_lo, int64_t ldvt, int T_pad, int n_splits,
+                                   float sigma, float* partial, void* panel16, void* stream) {
+  if (!(sigma > 0.f)) return set_error(ODF_ERR_ARG, "sigma must be positive");
+  if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
+  if (panel16 == nullptr) return set_error(ODF_ERR_ARG, "panel16 must not be NULL");
+  TileLaunch L{};
+  L.kind = kind;
+  L.r_hi = r_hi; L.r_lo = r_lo; L.r_norm = r_sqnorm; L.r_scale = r_opscale; L.n_rows = n_rows;
+  L.q_hi = q_hi; L.q_lo = q_lo; L.q_norm = q_sqnorm; L.q_scale = q_opscale; L.n_cols = n_cols;
+  L.d_pad = round_up(d, kblock_elems(kind)); L.vt_hi = vt_hi; L.vt_lo = vt_lo; L.ldvt = ldvt; L.T_pad = T_pad;
+  L.mode = MODE_MMV; L.n_splits = n_splits; L.sigma = sigma;
+  L.out = partial; L.ldo = T_pad; L.split_stride = n_rows * T_pad;
+  L.panel16 = panel16;
+  return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
+}
+int odf_finish_w16(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T, const float* addend,
+                   int64_t ld_add, float* w_f32, void* absmax, void* w16, void* stream) {
+  return finish_w16(partial, n_splits, n_rows, T_pad, T, addend, ld_add, w_f32, static_cast<uint32_t*>(absmax), w16,
+                    static_cast<cudaStream_t>(stream));
+}
+int odf_panel16_tmm(const void* panel16, int64_t n_rows, int64_t M, const void* w16, const void* absmax, int T_pad,
+                    int n_splits, float* out_partial, void* stream) {
+  return launch_panel16_tmm(panel16, n_rows, M, w16, static_cast<const uint32_t*>(absmax), T_pad, n_splits, out_partial,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int odf_finish_rows(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T, float scale,
                     const float* addend, int64_t ld_add, float* out, int64_t ldo, void* stream) {
   return finish_rows(partial, n_splits, n_rows, T_pad, T, scale, addend, ld_add, out, ldo, static_cast<cudaStream_t>(stream));

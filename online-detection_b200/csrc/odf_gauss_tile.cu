@@ -36,6 +36,7 @@
 //   warp 3  lane 0 : TMA producer for the V^T tiles
 //   warps 4..7     : epilogue (one TMEM lane == one row per thread)
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "odf_ptx.cuh"
 #include "odf_internal.h"
 
@@ -96,7 +97,9 @@ __device__ __forceinline__ WorkItem decode_item(const TileParams& p, int idx) {
 
 }  // namespace
 
-template <int KIND>
+// SPILL16 = 1: the epilogue also writes every K tile as two fp16 planes (hi = rn16(K), lo = rn16((K - hi) * 2^12))
+// in the tile-blocked layout odf_panel16.cu streams back with TMA: [plane][column tile][row block][16 groups][128 rows][8].
+template <int KIND, int SPILL16>
 __global__ void __launch_bounds__(256, 1)
 gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
                   const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
@@ -366,19 +369,48 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
           if (p.dbg & 4) {
           } else if (mode_mmv) {
             uint32_t lo[32];
+            uint32_t ph[SPILL16 ? 16 : 1], pl[SPILL16 ? 16 : 1];
+            // tf32 split on the integer pipe: hi = K rounded to 11 bits (add half an ulp, clear 13 bits), lo = K - hi
+            // exactly; the tensor core reads only the upper 19 bits of lo (2^-21 K).  Two cvt.rna per element
+            // would share the 16-lane XU pipe with ex2 and made the epilogue the bottleneck at d <= 256.
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float d2 = fmaf(m2inv, __uint_as_float(s[c]), rn + qn[c]);
-              d2 = fmaxf(d2, 0.f);
-              const float kv = ex2_approx(d2 * nsl2);
-              const float hi = tf32_rn(kv);
-              s[c] = __float_as_uint(hi);
-              lo[c] = __float_as_uint(tf32_rn(kv - hi));
+            for (int c = 0; c < 32; c += 2) {
+              float d0 = fmaf(m2inv, __uint_as_float(s[c]), rn + qn[c]);
+              float d1 = fmaf(m2inv, __uint_as_float(s[c + 1]), rn + qn[c + 1]);
+              d0 = fmaxf(d0, 0.f);
+              d1 = fmaxf(d1, 0.f);
+              const float k0 = ex2_approx(d0 * nsl2), k1 = ex2_approx(d1 * nsl2);
+              const uint32_t h0 = (__float_as_uint(k0) + 0x1000u) & 0xFFFFE000u;
+              const uint32_t h1 = (__float_as_uint(k1) + 0x1000u) & 0xFFFFE000u;
+              s[c] = h0;
+              s[c + 1] = h1;
+              lo[c] = __float_as_uint(k0 - __uint_as_float(h0));
+              lo[c + 1] = __float_as_uint(k1 - __uint_as_float(h1));
+              if (SPILL16) {
+                const __half2 h = __floats2half2_rn(k0, k1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn((k0 - hf.x) * 4096.f, (k1 - hf.y) * 4096.f);
+                ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+              }
             }
             if (ch == 0 && n > 0) mbar_wait_warp(BAR(B_PVDONE), (n - 1) & 1);  // K_lo buffer free
             tmem_st32(t_s + ch * 32, s);
             tmem_st32(t_lo + ch * 32, lo);
-            if (p.panel != nullptr && grow < p.n_rows) {
+            if (SPILL16) {
+              // [plane][column tile][row block][group of 8 centres][128 rows][8]: a warp store covers 32 rows x 16 B =
+              // 512 contiguous bytes (with one row per thread and row-major tiles every STG touched 32 lines and the
+              // LSU, not HBM, bounded the spill).  Rows past n_rows of the last block come from zero-filled
+              // operands (finite K) and are written too; the matching W16 rows are zero.
+              __half* dst = p.panel16 + (((static_cast<int64_t>(j) * p.n_rowblocks + (w.row0 >> 7)) * 16 + ch * 4) * 128 + row) * 8;
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                *reinterpret_cast<uint4*>(dst + v * 1024) = make_uint4(ph[4 * v], ph[4 * v + 1], ph[4 * v + 2], ph[4 * v + 3]);
+                *reinterpret_cast<uint4*>(dst + p.panel16_plane + v * 1024) =
+                    make_uint4(pl[4 * v], pl[4 * v + 1], pl[4 * v + 2], pl[4 * v + 3]);
+              }
+            }
+            if (!SPILL16 && p.panel != nullptr && grow < p.n_rows) {
               // spill K = K_hi + K_lo (exactly what the contraction above uses) to the row panel
               float* prow = p.panel + static_cast<int64_t>(grow) * p.ldpanel + col0 + ch * 32;
 #pragma unroll
@@ -506,6 +538,26 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64
 
 }  // namespace
 
+// [rows x cols] of fp16 / fp32 with row pitch ld (elements); box = [box_rows x 128 bytes], SWIZZLE_128B.
+int make_map_sw128(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int esize) {
+  return make_map(m, base, rows, cols, ld, box_rows, esize);
+}
+
+// Un-swizzled 2-D fp16 map: [rows x cols] with pitch ld (elements), box = [box_rows x box_cols].
+int make_map_plain_f16(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled (plain fp16 map) failed");
+  return ODF_OK;
+}
+
 // Plain (un-swizzled) 2-D fp32 map: box = [box_rows x box_cols]; out-of-bounds elements read as 0.
 int make_map_plain_f32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                        int box_cols) {
@@ -573,9 +625,13 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
     return set_error(ODF_ERR_ARG, "T_pad must be 16 or 32");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_TF32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_F16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_TF32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gauss_tile_kernel)");
     attr_set = true;
   }
@@ -622,6 +678,10 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
   if (L.panel != nullptr && (L.mode != MODE_MMV || L.ldpanel < static_cast<int64_t>(p.n_coltiles) * BN ||
                              L.ldpanel % 4 != 0 || (reinterpret_cast<uintptr_t>(L.panel) & 15) != 0))
     return set_error(ODF_ERR_ARG, "panel must be 16-byte aligned with pitch >= round_up(n_cols, 128)");
+  p.panel16 = static_cast<__half*>(L.panel16);
+  p.panel16_plane = static_cast<int64_t>(p.n_coltiles) * p.n_rowblocks * 16384;
+  if (L.panel16 != nullptr && (L.mode != MODE_MMV || L.panel != nullptr || (reinterpret_cast<uintptr_t>(L.panel16) & 127) != 0))
+    return set_error(ODF_ERR_ARG, "panel16 must be 128-byte aligned, MODE_MMV only, and excludes the fp32 panel");
   {
     const char* e = getenv("ODF_TILE_DEBUG");
     p.dbg = e ? atoi(e) : 0;
@@ -629,10 +689,14 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
   p.store_vec4 = (L.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) ? 1 : 0;
   const int n_items = p.n_rowblocks * p.n_splits;
   const int grid = n_items < sms ? n_items : sms;
-  if (L.kind == KIND_F16)
-    gauss_tile_kernel<KIND_F16><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  if (L.kind == KIND_F16 && L.panel16 != nullptr)
+    gauss_tile_kernel<KIND_F16, 1><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  else if (L.kind == KIND_F16)
+    gauss_tile_kernel<KIND_F16, 0><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  else if (L.panel16 != nullptr)
+    gauss_tile_kernel<KIND_TF32, 1><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
   else
-    gauss_tile_kernel<KIND_TF32><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+    gauss_tile_kernel<KIND_TF32, 0><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "gauss_tile_kernel launch");
   return ODF_OK;

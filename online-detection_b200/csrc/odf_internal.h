@@ -2,7 +2,9 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #include "../../include/odf.h"
 
@@ -32,6 +34,8 @@ struct TileParams {
   int64_t split_stride;    // MODE_MMV: elements between split slabs
   float* panel;            // optional (MODE_MMV): spill K tiles here, [n_rows x ldpanel] fp32
   int64_t ldpanel;
+  __half* panel16;         // optional (MODE_MMV, SPILL16 kernels): fp16 hi / lo planes of the K tiles, tile-blocked
+  int64_t panel16_plane;   // elements between the hi and the lo plane (n_coltiles * n_rowblocks * 128 * 128)
   int dbg;                 // bring-up timing experiments (env ODF_TILE_DEBUG; results are garbage when set):
                            // 1 = no TMA refills, 2 = no S MMAs, 4 = no epilogue math, 8 = no K.V MMAs, 16 = print clocks
 };
@@ -57,12 +61,39 @@ struct TileLaunch {
   int64_t split_stride;
   float* panel;                // optional K spill (MODE_MMV)
   int64_t ldpanel;
+  void* panel16;               // optional fp16-plane K spill for odf_panel16_tmm (see odf_panel16.cu)
 };
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream);
 int make_map_plain_f32(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                        int box_cols);
+int make_map_sw128(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int esize);
+int make_map_plain_f16(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 int panel_splits(int64_t n_rows, int64_t M);
+// fp16-plane panel (tensor-core contraction, odf_panel16.cu)
+size_t panel16_bytes(int64_t n_rows, int64_t M);
+int panel16_splits(int64_t n_rows, int64_t M);
+int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W16, const uint32_t* absmax, int T_pad,
+                       int n_splits, float* out_partial, cudaStream_t st);
+int finish_w16(const float* partial, int S, int64_t n, int T_pad, int64_t T, const float* addend, int64_t ld_add,
+               float* Wf, uint32_t* absmax, void* W16, cudaStream_t st);
+// power-of-two scaling of W for the fp16 split: s * max|W| in [2^14, 2^15)
+__host__ __device__ inline float w16_scale_from_bits(uint32_t absmax_bits, bool inverse) {
+  const int e = static_cast<int>((absmax_bits >> 23) & 0xffu);
+  if (e == 0 || e == 255) return 1.f;
+  int se = 127 + 14 - (e - 127);
+  if (se < 1) se = 1;
+  if (se > 253) se = 253;
+  if (inverse) se = 254 - se;
+  const uint32_t bits = static_cast<uint32_t>(se) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(bits);
+#else
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+#endif
+}
 int launch_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, int64_t M, int T_pad,
                      int n_splits, float* out_partial, cudaStream_t st);
 int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t row_bytes);

@@ -192,7 +192,7 @@ split_rhs_kernel(const float* __restrict__ V, int64_t m, int T, int64_t ldv, flo
 __global__ void __launch_bounds__(128)
 finish_rows_kernel(const float* __restrict__ partial, int S, int64_t n, int T_pad, int T,
                    float scale, const float* __restrict__ addend, int64_t ld_add,
-                   float* __restrict__ out, int64_t ldo) {
+                   float* __restrict__ out, int64_t ldo, uint32_t* __restrict__ absmax) {
   __shared__ float tile[128][33];
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 128;
   const int64_t r = r0 + threadIdx.x;
@@ -215,14 +215,44 @@ finish_rows_kernel(const float* __restrict__ partial, int S, int64_t n, int T_pa
   for (int t = 0; t < 32; ++t) tile[threadIdx.x][t] = acc[t] * scale;
   __syncthreads();
   // coalesced store along rows of out
+  float amax = 0.f;
   for (int idx = threadIdx.x; idx < 128 * T; idx += 128) {
     const int rr = idx / T, t = idx - rr * T;
     if (r0 + rr < n) {
       float v = tile[rr][t];
       if (addend) v += __ldg(addend + (r0 + rr) * ld_add + t);
       out[(r0 + rr) * ldo + t] = v;
+      amax = fmaxf(amax, fabsf(v));
     }
   }
+  if (absmax != nullptr) {                     // max |out| of the launch (bit pattern of a non-negative float orders as uint)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(absmax, __float_as_uint(amax));
+  }
+}
+
+// W [n x ldw] fp32 -> W16 [round_up(n,128) x 64] fp16: columns 0..31 hi = rn16(s W), 32..63 lo = rn16((s W - hi) 2^11),
+// s = w16_scale(max|W|) a power of two; rows >= n and columns >= T are zero (the B operand of odf_panel16.cu).
+__global__ void __launch_bounds__(256)
+split_w16_kernel(const float* __restrict__ W, int64_t n, int64_t n_pad, int ldw, int T, const uint32_t* __restrict__ absmax,
+                 __half* __restrict__ W16) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;     // one thread: one row, 8 columns
+  const int64_t r = idx >> 2;
+  const int t0 = static_cast<int>(idx & 3) * 8;
+  if (r >= n_pad) return;
+  const float sc = w16_scale_from_bits(__ldg(absmax), false);
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = t0 + i;
+    const float v = (r < n && t < T) ? __ldg(W + r * ldw + t) * sc : 0.f;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
+  }
+  *reinterpret_cast<uint4*>(W16 + r * 64 + t0) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(W16 + r * 64 + 32 + t0) = *reinterpret_cast<const uint4*>(lo);
 }
 
 __global__ void __launch_bounds__(128)
@@ -479,8 +509,23 @@ int split_rhs(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, fl
 int finish_rows(const float* partial, int S, int64_t n, int T_pad, int64_t T, float scale,
                 const float* addend, int64_t ld_add, float* out, int64_t ldo, cudaStream_t st) {
   if (S <= 0 || n <= 0 || T <= 0 || T > T_pad || T_pad > 32) return set_error(ODF_ERR_ARG, "finish_rows: bad shape");
-  finish_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(partial, S, n, T_pad, static_cast<int>(T), scale, addend, ld_add, out, ldo);
+  finish_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(partial, S, n, T_pad, static_cast<int>(T), scale, addend, ld_add, out, ldo, nullptr);
   return check_launch("finish_rows_kernel");
+}
+
+// W = sum of the partial slabs (+ addend) as finish_rows, then its fp16 hi/lo split for odf_panel16_tmm.
+// Wf: fp32 scratch [n x T_pad]; absmax: one device word (reset here); W16: [round_up(n,128) x 64] fp16.
+int finish_w16(const float* partial, int S, int64_t n, int T_pad, int64_t T, const float* addend, int64_t ld_add,
+               float* Wf, uint32_t* absmax, void* W16, cudaStream_t st) {
+  if (S <= 0 || n <= 0 || T <= 0 || T > T_pad || T_pad > 32 || !Wf || !absmax || !W16 ||
+      (reinterpret_cast<uintptr_t>(W16) & 127) != 0)
+    return set_error(ODF_ERR_ARG, "finish_w16: bad shape or alignment");
+  cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(uint32_t), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "finish_w16: memset");
+  finish_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(partial, S, n, T_pad, static_cast<int>(T), 1.f, addend, ld_add, Wf, T_pad, absmax);
+  const int64_t n_pad = (n + 127) / 128 * 128;
+  split_w16_kernel<<<static_cast<unsigned>((n_pad * 4 + 255) / 256), 256, 0, st>>>(Wf, n, n_pad, T_pad, static_cast<int>(T), absmax, static_cast<__half*>(W16));
+  return check_launch("finish_w16");
 }
 
 int finish_split(const float* partial, int S, int64_t n, int T_pad, int64_t T, float scale,

@@ -32,6 +32,12 @@ SIGNATURES = {
                                              c_fp, c_fp, c_i64, c_int, c_int, c_f, c_fp, c_fp, c_i64, c_fp]),
     "odf_panel_splits": (c_int, [c_i64, c_i64]),
     "odf_panel_tmm": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_int, c_fp, c_fp]),
+    "odf_panel16_bytes": (c_sz, [c_i64, c_i64]),
+    "odf_gauss_mmv_prepared_spill16": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64,
+                                               c_i64, c_fp, c_fp, c_i64, c_int, c_int, c_f, c_fp, c_fp, c_fp]),
+    "odf_finish_w16": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp]),
+    "odf_panel16_splits": (c_int, [c_i64, c_i64]),
+    "odf_panel16_tmm": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),
     "odf_finish_rows": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_i64, c_fp]),
     "odf_finish_split": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_fp,
                                  c_i64, c_fp]),

@@ -43,9 +43,10 @@ class FalkonOptions:
         # "inverse": apply T^-1 / A^-1 as GEMMs with explicit inverses built once per fit (default);
         # "trsm": four triangular solves per CG iteration, as upstream does
         self.precond_apply = ignored.pop("precond_apply", "inverse")
-        # "panel": K is evaluated once per sweep, its tiles are spilled to a transient row panel and
-        # contracted by the panel kernel; "recompute": evaluate K twice (no panel workspace)
-        self.sweep_mode = ignored.pop("sweep_mode", "panel")
+        # "panel16": K is evaluated once per sweep, its tiles are spilled as fp16 hi/lo planes to a transient panel
+        # and contracted by the tensor-core panel kernel; "panel": fp32 panel + fp32-FMA panel kernel;
+        # "recompute": evaluate K twice (no panel workspace)
+        self.sweep_mode = ignored.pop("sweep_mode", "panel16")
         # multi-GPU fits split T T^T and the explicit inverses over the ranks (False: every rank builds all)
         self.distributed_precond = ignored.pop("distributed_precond", True)
         self.ignored = dict(ignored)
@@ -99,7 +100,7 @@ class GaussianKernel:
             out = torch.empty((M, T), dtype=torch.float32, device=dev)
         cols = self._prep(X2, like=X1)
         rows = self._prep(X1, like=cols)
-        mode = getattr(self.opt, "sweep_mode", "panel") if self.opt is not None else "panel"
+        mode = getattr(self.opt, "sweep_mode", "panel16") if self.opt is not None else "panel16"
         sw = ops.Sweeper(rows, cols, self.sigma, min(T, 32), mode=mode)
         for t0 in range(0, T, 32):
             t1 = min(T, t0 + 32)

@@ -135,12 +135,29 @@ class RowView:
         self.opscale, self.n, self.d, self.kind, self.pitch = prep.opscale, r1 - r0, prep.d, prep.kind, prep.pitch
 
 
-def mmv_partial(rows, cols, rhs, sigma, partial, panel=None):
+def mmv_partial(rows, cols, rhs, sigma, partial, panel=None, panel16=None):
     """partial[s] = K(rows, cols restricted to split s) @ rhs  — the fused tcgen05 tile.
-    With `panel` ([rows.n x pad_rows(cols.n)] fp32) the K tiles are also spilled for panel_tmm."""
+    With `panel` ([rows.n x pad_rows(cols.n)] fp32) the K tiles are also spilled for panel_tmm; with `panel16`
+    (uint8 buffer of odf_panel16_bytes) they are spilled as fp16 hi/lo planes for panel16_tmm."""
     L = _lib.load()
     assert rows.d == cols.d and rows.kind == cols.kind and rhs.m == cols.n
     S = int(partial.shape[0])
+    if panel16 is not None:
+        assert panel is None and panel16.numel() * panel16.element_size() >= int(L.odf_panel16_bytes(rows.n, cols.n))
+        ev = None
+        if TILE_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        check(L.odf_gauss_mmv_prepared_spill16(rows.kind, ptr(rows.hi), ptr(rows.lo), ptr(rows.sqn), ptr(rows.opscale),
+                                               rows.n, ptr(cols.hi), ptr(cols.lo), ptr(cols.sqn), ptr(cols.opscale),
+                                               cols.n, rows.d, ptr(rhs.hi), ptr(rhs.lo), rhs.ld, rhs.T_pad, S,
+                                               float(sigma), ptr(partial), ptr(panel16), _stream()),
+              "odf_gauss_mmv_prepared_spill16")
+        if ev is not None:
+            ev[1].record()
+            TILE_EVENTS.append((ev[0], ev[1], rows.n, cols.n, rows.d, rhs.T))
+        _count(1)
+        return
     if panel is not None:
         assert panel.shape[0] >= rows.n and panel.stride(1) == 1
         ev = None
@@ -182,6 +199,38 @@ def panel_tmm(panel, W, n_rows, M, out_partial):
         ev[0].record()
     check(L.odf_panel_tmm(ptr(panel), panel.stride(0), ptr(W), n_rows, M, T_pad, S, ptr(out_partial), _stream()),
           "odf_panel_tmm")
+    if ev is not None:
+        ev[1].record()
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad))
+    _count(1)
+
+
+def finish_w16(partial, T, Wf, absmax, W16, addend=None):
+    """W = sum_s partial[s] (+ addend) -> Wf (fp32 scratch) and its fp16 hi|lo split W16 (B operand of panel16_tmm)."""
+    L = _lib.load()
+    S, n, T_pad = partial.shape
+    assert Wf.shape[0] >= n and Wf.shape[1] == T_pad and Wf.is_contiguous()
+    assert W16.dtype == torch.float16 and W16.shape[1] == 64 and W16.shape[0] >= (n + 127) // 128 * 128 and W16.is_contiguous()
+    ld_add = 0
+    if addend is not None:
+        addend, ld_add = _rowmajor(_req(addend, "addend", 2))
+    check(L.odf_finish_w16(ptr(partial), S, n, T_pad, T, ptr(addend), ld_add, ptr(Wf), ptr(absmax), ptr(W16), _stream()),
+          "odf_finish_w16")
+    _count(2)
+    return W16
+
+
+def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial):
+    """out_partial[s] = K[rows of range s]^T @ W from the fp16-plane panel (tcgen05 kind::f16, HBM-streaming)."""
+    L = _lib.load()
+    S, M_, T_pad = out_partial.shape
+    assert M_ == M and S == int(L.odf_panel16_splits(n_rows, M)) and out_partial.is_contiguous()
+    ev = None
+    if PANEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(L.odf_panel16_tmm(ptr(panel16), n_rows, M, ptr(W16), ptr(absmax), T_pad, S, ptr(out_partial), _stream()),
+          "odf_panel16_tmm")
     if ev is not None:
         ev[1].record()
         PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad))
@@ -370,12 +419,14 @@ def mmv_into(rows, cols, v, sigma, out):
 class Sweeper:
     """Pre-allocated buffers for repeated K_nm^T (K_nm V + W) sweeps with T <= 32 columns.
 
-    mode "panel" (default): rows go through in chunks; the fused tile computes K_chunk V and spills
-    its K tiles to a transient panel, then the panel kernel forms K_chunk^T (K_chunk V + W).  K is
-    evaluated once per sweep.  mode "recompute": the second half re-evaluates K in the transposed
-    orientation with the same fused tile (no panel workspace, 2x tensor work)."""
+    mode "panel16" (default): rows go through in chunks; the fused tile computes K_chunk V and spills
+    its K tiles as fp16 hi/lo planes to a transient panel, then the tensor-core panel kernel forms
+    K_chunk^T (K_chunk V + W) streaming the panel once at HBM speed.  K is evaluated once per sweep.
+    mode "panel": same with an fp32 panel and the fp32-FMA panel kernel.  mode "recompute": the second
+    half re-evaluates K in the transposed orientation with the same fused tile (no panel workspace,
+    2x tensor work)."""
 
-    def __init__(self, rows, cols, sigma, T, mode="panel"):
+    def __init__(self, rows, cols, sigma, T, mode="panel16"):
         L = _lib.load()
         dev = rows.hi.device
         self.rows, self.cols, self.sigma, self.T, self.mode = rows, cols, sigma, int(T), mode
@@ -383,7 +434,18 @@ class Sweeper:
         self.w_rhs = SplitRhs(rows.n, T, dev)       # W^T  (T_pad x n), used by "recompute" and by the v=None sweep
         Tp = self.v_rhs.T_pad
         self.part2 = alloc_partial(cols, rows, Tp, dev)   # rows = centres
-        if mode == "panel":
+        if mode == "panel16":
+            self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
+            self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
+            self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
+            self.panel16 = torch.empty((int(L.odf_panel16_bytes(self.chunk, cols.n)),), dtype=torch.uint8, device=dev)
+            self.part1 = [alloc_partial(v, cols, Tp, dev) for v in self.views[:1] + self.views[-1:]]
+            self.Wf = torch.empty((self.chunk, Tp), dtype=torch.float32, device=dev)
+            self.W16 = torch.empty(((self.chunk + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
+            self.absmax = torch.zeros((1,), dtype=torch.int32, device=dev)
+            self.pslabs = [int(L.odf_panel16_splits(r1 - r0, cols.n)) for (r0, r1) in self.chunks]
+            self.part3 = torch.empty((sum(self.pslabs), cols.n, Tp), dtype=torch.float32, device=dev)
+        elif mode == "panel":
             self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
             self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
             self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
@@ -405,6 +467,17 @@ class Sweeper:
         if w is not None and w_scale != 1.0:
             w = w * w_scale
         self.v_rhs.fill(v)
+        if self.mode == "panel16":
+            slab = 0
+            for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
+                n = r1 - r0
+                part1 = self.part1[0] if n == self.part1[0].shape[1] else self.part1[-1]
+                mmv_partial(view, self.cols, self.v_rhs, self.sigma, part1, panel16=self.panel16)
+                finish_w16(part1, self.T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
+                S = self.pslabs[i]
+                panel16_tmm(self.panel16, self.W16, self.absmax, n, self.cols.n, self.part3[slab:slab + S])
+                slab += S
+            return finish_rows(self.part3, self.T, out, scale)
         if self.mode != "panel":
             mmv_partial(self.rows, self.cols, self.v_rhs, self.sigma, self.part1)
             finish_split(self.part1, self.T, self.w_rhs, 1.0, w)

@@ -230,6 +230,41 @@ def run_stage(stage):
             pk = sum(a.elapsed_time(b) for (a, b, *_r) in ops.PANEL_EVENTS); ops.PANEL_EVENTS = None
             print(msg + f"  sweep_ms panel={ts[0]:.2f} recompute={ts[1]:.2f} panel_kernel_ms={pk:.2f} ({n * swp.ldp * 4 / pk / 1e6:.0f} GB/s panel read)")
             ok &= e < 2e-5
+    elif stage == "panel16":
+        from odf import ops
+        shapes = [(300, 200, 40, 21), (5000, 1000, 256, 30), (4096, 777, 64, 5), (131072, 10000, 1024, 30),
+                  (262144, 5000, 256, 15), (131072, 30000, 256, 21)]
+        if os.environ.get("ODF_DEBUG_SMALL"):
+            shapes = shapes[:3]
+        for (n, M, d, T) in shapes:
+            sigma = 15.0
+            X = _data(n, d, 5); C = _data(M, d, 6)
+            V = torch.randn(M, T, device="cuda")
+            px, pc = ops.Prepared(X), ops.Prepared(C)
+            ref = torch.zeros(M, T, device="cuda", dtype=torch.float64)
+            for r0 in range(0, n, 8192):
+                Kr = _ref_kernel(X[r0:r0 + 8192], C, sigma)
+                ref += Kr.T @ (Kr @ V.double())
+            msg = f"panel16 n={n} M={M} d={d} T={T}:"
+            for mode in ("panel16", "panel", "recompute"):
+                sw = ops.Sweeper(px, pc, sigma, T, mode=mode)
+                out = torch.empty(M, T, device="cuda")
+                sw.dmmv(V, None, out); torch.cuda.synchronize()
+                err = rel(out, ref)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3): sw.dmmv(V, None, out)
+                e1.record(); torch.cuda.synchronize()
+                ops.PANEL_EVENTS = []; ops.TILE_EVENTS = []
+                sw.dmmv(V, None, out); torch.cuda.synchronize()
+                pk = sum(a.elapsed_time(b) for (a, b, *_r) in ops.PANEL_EVENTS)
+                tk = sum(a.elapsed_time(b) for (a, b, *_r) in ops.TILE_EVENTS)
+                ops.PANEL_EVENTS = None; ops.TILE_EVENTS = None
+                gbs = (n * ((M + 127) // 128 * 128) * 4 / pk / 1e6) if pk > 0 else 0.0
+                msg += f"\n    {mode:9s} err_vs_fp64={err:.2e} sweep_ms={e0.elapsed_time(e1) / 3:.2f} tile_ms={tk:.2f} panel_ms={pk:.2f} ({gbs:.0f} GB/s)"
+                ok &= err < 2e-5
+                del sw
+            print(msg, flush=True)
     elif stage == "bottleneck":
         # timing-only experiments (results are garbage under the debug flags)
         from odf import ops

@@ -85,8 +85,9 @@ def test_mmv_out_argument_and_vector_rhs(odf):
     assert rel(k.mmv(X.cuda(), C.cuda(), more.cuda()), orc.mmv(X, C, more, 20.0)) < 5e-5
 
 
-@pytest.mark.parametrize("mode", ["panel", "recompute"])
-@pytest.mark.parametrize("n,M,d,T", [(3000, 500, 256, 21), (1000, 64, 48, 1), (5000, 1000, 1024, 30), (131, 130, 40, 16)])
+@pytest.mark.parametrize("mode", ["panel16", "panel", "recompute"])
+@pytest.mark.parametrize("n,M,d,T", [(3000, 500, 256, 21), (1000, 64, 48, 1), (5000, 1000, 1024, 30), (131, 130, 40, 16),
+                                     (70000, 300, 64, 30)])
 def test_dmmv_matches_oracle(odf, n, M, d, T, mode):
     X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
     C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
@@ -165,6 +166,43 @@ def test_config1_fit_matches_oracle(odf, N, M, sigma, lam, noise, kind):
     assert float((s_ref[pos].argmax(1) + 1 == ct[pos]).double().mean()) > 0.9
 
 
+def test_panel16_kernel_matches_fp64_product(odf):
+    """The tensor-core panel contraction alone: spill K(X, C) as fp16 planes with the fused tile, contract with an
+    arbitrary W (wide dynamic range across columns) and compare with the fp64 product K^T W.  Rows are ragged
+    (not a multiple of 64) and long enough for several 2048-row accumulation chains and several row ranges."""
+    from odf import ops
+    n, M, d, T = 9000, 333, 64, 21
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
+    C = X[::27][:M].contiguous()
+    g = torch.Generator().manual_seed(8)
+    W = torch.randn(n, T, generator=g) * torch.logspace(-3, 3, T)[None, :]
+    k = odf.GaussianKernel(15.0)
+    cols = k._prep(C.cuda())
+    rows = k._prep(X.cuda(), like=cols)
+    dev = torch.device("cuda")
+    rhs = ops.SplitRhs(M, T, dev).fill(torch.zeros(M, T, device=dev))
+    part1 = ops.alloc_partial(rows, cols, rhs.T_pad, dev)
+    L = ops._lib.load()
+    p16 = torch.empty((int(L.odf_panel16_bytes(n, M)),), dtype=torch.uint8, device=dev)
+    ops.mmv_partial(rows, cols, rhs, 15.0, part1, panel16=p16)
+    Wf = torch.empty((n, rhs.T_pad), device=dev)
+    W16 = torch.empty(((n + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
+    absmax = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.finish_w16(part1, T, Wf, absmax, W16, addend=W.cuda())        # K.0 + W = W
+    assert torch.equal(Wf[:, :T].cpu(), W)
+    S = int(L.odf_panel16_splits(n, M))
+    out_p = torch.empty((S, M, rhs.T_pad), device=dev)
+    ops.panel16_tmm(p16, W16, absmax, n, M, out_p)
+    out = out_p.sum(0)[:, :T].double().cpu()
+    K = orc.gaussian_kernel(X, C, 15.0)
+    ref = K.T @ W.double()
+    # per column: the error is relative to sum_r K |W| of that column (cancellation between rows is the data's)
+    scale = (K.T @ W.double().abs())
+    assert float(((out - ref).abs() / scale).max()) < 2e-5
+    # the common power-of-two scale follows the largest column; small columns keep 2^-22 of the largest
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
 def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
     """The spilled-panel sweep walks the rows in chunks; force several (ragged) chunks."""
     from odf import ops
@@ -173,9 +211,10 @@ def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
     C = X[::11].contiguous()
     g = torch.Generator().manual_seed(8)
     v, w = torch.randn(C.shape[0], 7, generator=g), torch.randn(3333, 7, generator=g)
-    k = odf.GaussianKernel(15.0)
-    assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), w.cuda()), orc.dmmv(X, C, v, w, 15.0)) < 1e-4
-    assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), None), orc.dmmv(X, C, v, None, 15.0)) < 1e-4
+    for mode in ("panel16", "panel"):
+        k = odf.GaussianKernel(15.0, opt=odf.FalkonOptions(sweep_mode=mode))
+        assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), w.cuda()), orc.dmmv(X, C, v, w, 15.0)) < 1e-4
+        assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), None), orc.dmmv(X, C, v, None, 15.0)) < 1e-4
 
 
 def test_recompute_and_trsm_options_agree_with_default(odf):

@@ -1,4 +1,4 @@
-// Bring-up probe: tcgen05.mma kind::tf32 with MN-major A and B straight from row-major fp32 tiles
+// Bring-up probe: tcgen05.mma kind::f16 with MN-major A and B straight from row-major fp16 tiles
 // (the layout of a spilled K panel [rows x centres] and of W [rows x T]): D[m, n] = sum_k A[k][m] B[k][n].
 // Verifies the shared-memory descriptor (LBO / SBO roles) against a CPU product.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bin/mn_probe tools/mn_probe.cu -lcuda
@@ -67,8 +67,8 @@ probe(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorM
     for (int j = 0; j < 1; ++j) tma_load_2d(smem_u32(b_s + j * R * 128), &tmB, smem_u32(bars), j * 64, 0);
     mbar_wait(smem_u32(bars), 0);
     tc_fence_after();
-    // kind::tf32, fp32 accumulate, A and B MN-major (bits 15 / 16), N = 64, M = 128
-    const uint32_t idesc = (1u << 4) | (0u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((NT >> 3) << 17) | ((MT >> 4) << 24);
+    // kind::f16 (fp16 x fp16), fp32 accumulate, A and B MN-major (bits 15 / 16), N = 64, M = 128
+    const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((NT >> 3) << 17) | ((MT >> 4) << 24);
     const uint32_t chunk = R * 128, grp = 1024;
     for (int kk = 0; kk < R / 16; ++kk) {      // K = 16 per fp16 MMA = two 8-row k-groups
       uint64_t da, db;
@@ -95,18 +95,18 @@ probe(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorM
 }
 
 int main() {
-  std::vector<float> A(R * MT), B(R * NT); std::vector<__half> Ah(R * MT); std::vector<__nv_bfloat16> Bh(R * NT);
+  std::vector<float> A(R * MT), B(R * NT); std::vector<__half> Ah(R * MT); std::vector<__half> Bh(R * NT);
   for (int k = 0; k < R; ++k) {
     for (int m = 0; m < MT; ++m) A[k * MT + m] = float((k * 7 + m * 3) % 11 - 5);
     for (int n = 0; n < NT; ++n) B[k * NT + n] = float((k * 5 + n * 13) % 9 - 4);
   }
   for (size_t i = 0; i < A.size(); ++i) Ah[i] = __float2half(A[i]);
-  for (size_t i = 0; i < B.size(); ++i) Bh[i] = __float2bfloat16(B[i]);
-  __half *dA; __nv_bfloat16* dB; float* dO;
+  for (size_t i = 0; i < B.size(); ++i) Bh[i] = __float2half(B[i]);
+  __half *dA; __half* dB; float* dO;
   cudaMalloc(&dA, A.size() * 2); cudaMalloc(&dB, B.size() * 2); cudaMalloc(&dO, MT * NT * 4);
   cudaMemcpy(dA, Ah.data(), A.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, Bh.data(), B.size() * 2, cudaMemcpyHostToDevice);
-  CUtensorMap tA = make_map(dA, R, MT, MT), tB = make_map(dB, R, NT, NT, true);
+  CUtensorMap tA = make_map(dA, R, MT, MT), tB = make_map(dB, R, NT, NT);
   const int smem = 6 * R * 128 + 1024 + 64;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int variant = 0; variant < 2; ++variant) {
