@@ -299,7 +299,7 @@ def run_ours(args):
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else \
         "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
-    roofline = {"bound": "tensor", "kernel": "gauss_tile_kernel<f16 split operands>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "launches_timed": len(tile_ms),
                 "tile_share_of_step": sum(tile_ms) / args.steps / ms_dev,
@@ -446,7 +446,7 @@ def run_predict(args, odf, ops, dist, world, rank, dev, Xh, Xd, centres, mean, s
             "e2e": {"value": F / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(N) * d * 4, "d2h_bytes_per_step": int(N) * T * 4},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gauss_tile_kernel<f16 split operands>", "achieved": tile_alg / max(tile_ms, 1e-9) / 1e9,
+            "roofline": {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": tile_alg / max(tile_ms, 1e-9) / 1e9,
                          "peak": peak, "unit": "TFLOP/s", "frac": tile_alg / max(tile_ms, 1e-9) / 1e9 / peak, "traffic": None,
                          "tile_share_of_step": tile_ms / args.steps / ms,
                          "note": "3 tensor passes per product: frac is capped at 1/3"},

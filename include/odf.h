@@ -104,12 +104,26 @@ int odf_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, i
  * planes, hi = rn16(K) and lo = rn16((K - hi) 2^12), tile-blocked
  * [plane][column tile][row block][half][128 rows][64 centres] (odf_panel16_bytes(n_rows, n_cols) bytes,
  * 128-byte aligned); odf_finish_w16 reduces the partial slabs of the first contraction into W = K v (+ addend)
- * [n_rows x T_pad] and splits it into W16 [round_up(n_rows,128) x 64] fp16 (hi | lo, common power-of-two scale
- * derived from max|W|, left in *absmax); odf_panel16_tmm streams the planes once from HBM and contracts
+ * [n_rows x T_pad] and splits it into W16 [round_up(n_rows,128) x 64] fp16 (hi | lo, per-column power-of-two
+ * scales derived from max|W[:, t]|, left in absmax[32]); odf_panel16_tmm streams the planes once from HBM and contracts
  * out_partial[s][c][0..T_pad) = sum_r K[r][c] W[r][.] with tcgen05 kind::f16 MMAs on MN-major operands
  * (three split products, fp32 accumulation chains of 2048 rows).  n_splits = odf_panel16_splits(n_rows, M).
  * Replaces the K_blk^T w half of falkon GaussianKernel.dmmv (...incore.py:68).                               */
 size_t odf_panel16_bytes(int64_t n_rows, int64_t n_cols);
+/* CTA-pair variant of the fused tile (cta_group::2, M = 256 per MMA: each CTA of a 2-CTA cluster loads half of every
+ * column tile): same operator and outputs as odf_gauss_mmv_prepared / _spill16 (panel16 may be NULL), for launches
+ * with odf_tile_pair_eligible(n_rows) != 0.  Its K.V contraction runs on fp16 hi/lo pairs, so the right-hand sides
+ * come from odf_split_rhs16: vt_hi16 / vt_lo16 [T_pad x ldvt] fp16 (ldvt = odf_pad_rows(m)), hi = rn16(s_t v),
+ * lo = rn16((s_t v - hi) 2^11), s_t the per-column power-of-two scale fixed by absmax[32] (written there).      */
+int odf_tile_pair_eligible(int64_t n_rows);
+int odf_split_rhs16(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, void* absmax,
+                    void* vt_hi16, void* vt_lo16, int64_t ldvt, int T_pad, void* stream);
+int odf_gauss_mmv_pair(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
+                       const float* r_opscale, int64_t n_rows, const void* q_hi, const void* q_lo,
+                       const float* q_sqnorm, const float* q_opscale, int64_t n_cols, int64_t d,
+                       const void* vt_hi16, const void* vt_lo16, int64_t ldvt, const void* v_absmax,
+                       int T_pad, int n_splits, float sigma, float* partial, void* panel16,
+                       void* stream);
 int odf_gauss_mmv_prepared_spill16(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,
                                    const float* r_opscale, int64_t n_rows, const void* q_hi,
                                    const void* q_lo, const float* q_sqnorm, const float* q_opscale,

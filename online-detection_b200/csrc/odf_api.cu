@@ -168,6 +168,32 @@ int odf_gauss_mmv_prepared_spill(int kind, const void* r_hi, const void* r_lo, c
   return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
 }
 
+int odf_tile_pair_eligible(int64_t n_rows) { return tile2_rows_eligible(n_rows) ? 1 : 0; }
+int odf_split_rhs16(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, void* absmax, void* vt_hi16,
+                    void* vt_lo16, int64_t ldvt, int T_pad, void* stream) {
+  return split_rhs16(V, m, T, ldv, scale, static_cast<uint32_t*>(absmax), vt_hi16, vt_lo16, ldvt, T_pad,
+                     static_cast<cudaStream_t>(stream));
+}
+int odf_gauss_mmv_pair(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm, const float* r_opscale,
+                       int64_t n_rows, const void* q_hi, const void* q_lo, const float* q_sqnorm, const float* q_opscale,
+                       int64_t n_cols, int64_t d, const void* vt_hi16, const void* vt_lo16, int64_t ldvt,
+                       const void* v_absmax, int T_pad, int n_splits, float sigma, float* partial, void* panel16,
+                       void* stream) {
+  if (!(sigma > 0.f)) return set_error(ODF_ERR_ARG, "sigma must be positive");
+  if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
+  if (!tile2_rows_eligible(n_rows)) return set_error(ODF_ERR_ARG, "too few rows for the CTA-pair tile (odf_tile_pair_eligible)");
+  TileLaunch L{};
+  L.kind = kind;
+  L.r_hi = r_hi; L.r_lo = r_lo; L.r_norm = r_sqnorm; L.r_scale = r_opscale; L.n_rows = n_rows;
+  L.q_hi = q_hi; L.q_lo = q_lo; L.q_norm = q_sqnorm; L.q_scale = q_opscale; L.n_cols = n_cols;
+  L.d_pad = round_up(d, kblock_elems(kind)); L.T_pad = T_pad;
+  L.vt16_hi = vt_hi16; L.vt16_lo = vt_lo16; L.ldvt16 = ldvt; L.v_absmax = static_cast<const uint32_t*>(v_absmax);
+  L.mode = MODE_MMV; L.n_splits = n_splits; L.sigma = sigma;
+  L.out = partial; L.ldo = T_pad; L.split_stride = n_rows * T_pad;
+  L.panel16 = panel16;
+  return launch_gauss_tile2(L, static_cast<cudaStream_t>(stream));
+}
+
 size_t odf_panel16_bytes(int64_t n_rows, int64_t n_cols) { return panel16_bytes(n_rows, n_cols); }
 int odf_panel16_splits(int64_t n_rows, int64_t M) { return panel16_splits(n_rows, M); }
 int odf_gauss_mmv_prepared_spill16(int kind, const void* r_hi, const void* r_lo, const float* r_sqnorm,

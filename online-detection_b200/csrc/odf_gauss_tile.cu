@@ -616,6 +616,7 @@ int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t row_bytes) {
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
   if (L.kind != KIND_TF32 && L.kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
+  if (tile2_eligible(L)) return launch_gauss_tile2(L, stream);
   const int64_t BK = kblock_elems(L.kind);
   const int esize = L.kind == KIND_F16 ? 2 : 4;
   const int64_t pitch = L.d_pad + 2 * BK;

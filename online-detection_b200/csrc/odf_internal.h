@@ -34,6 +34,7 @@ struct TileParams {
   int64_t split_stride;    // MODE_MMV: elements between split slabs
   float* panel;            // optional (MODE_MMV): spill K tiles here, [n_rows x ldpanel] fp32
   int64_t ldpanel;
+  const uint32_t* v_absmax; // pair kernel: 32 words fixing the per-column scales of the fp16 V^T split
   __half* panel16;         // optional (MODE_MMV, SPILL16 kernels): fp16 hi / lo planes of the K tiles, tile-blocked
   int64_t panel16_plane;   // elements between the hi and the lo plane (n_coltiles * n_rowblocks * 128 * 128)
   int dbg;                 // bring-up timing experiments (env ODF_TILE_DEBUG; results are garbage when set):
@@ -62,9 +63,18 @@ struct TileLaunch {
   float* panel;                // optional K spill (MODE_MMV)
   int64_t ldpanel;
   void* panel16;               // optional fp16-plane K spill for odf_panel16_tmm (see odf_panel16.cu)
+  const void *vt16_hi, *vt16_lo;   // optional fp16 split of V^T [T_pad x ldvt16] (odf_split_rhs16): enables the pair kernel
+  int64_t ldvt16;
+  const uint32_t* v_absmax;
 };
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream);
+// CTA-pair (cta_group::2) variant for large MODE_MMV launches (odf_gauss_tile2.cu)
+bool tile2_eligible(const TileLaunch& L);
+bool tile2_rows_eligible(int64_t n_rows);
+int split_rhs16(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, uint32_t* absmax, void* vt_hi, void* vt_lo,
+                int64_t ldvt, int T_pad, cudaStream_t st);
+int launch_gauss_tile2(const TileLaunch& L, cudaStream_t stream);
 int make_map_plain_f32(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                        int box_cols);
 int make_map_sw128(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int esize);

@@ -11,8 +11,8 @@
 // panel from HBM once, at copy speed; the fp32-FMA version (odf_panel.cu) was bound by the FMA pipe at 2.6 TB/s.
 // Here the centres are the M dimension of a tcgen05.mma kind::f16 (A = P^T, MN-major: a [8 rows x 8 centres] block of
 // the layout above is exactly one un-swizzled 128-byte core matrix), the rows are its K dimension, and
-// B = W16 [row][hi(s W) 0..31 | lo 32..63] (MN-major SWIZZLE_128B, one 128-byte row per panel row, s a power of two
-// so that s max|W| < 2^15):
+// B = W16 [row][hi(s_t W) 0..31 | lo 32..63] (MN-major SWIZZLE_128B, one 128-byte row per panel row, s_t a power of two
+// per column so that s_t max|W[:, t]| < 2^15):
 //     acc1 [128 x 64] += P_hi^T . W16      (columns 0..31: hi.hi      32..63: hi.lo, scaled 2^11)
 //     acc2 [128 x 64] += P_lo^T . W16      (columns 0..31: lo.hi, scaled 2^12;  32..63 unused)
 // fp32 in TMEM.  The tensor core adds with truncation, so an accumulation chain is cut every 512 rows: the epilogue
@@ -62,7 +62,7 @@ struct Panel16Params {
   int M, T_pad;
   int plane_rows;         // rows of the [.. x 1024] fp16 view (one per (j, rb, g)) between the hi and the lo plane
   int swap_lbo_sbo;       // bring-up switch (env ODF_P16_SWAP)
-  const uint32_t* absmax; // bits of max|W| (fixes the power-of-two scale of W16)
+  const uint32_t* absmax; // 32 words: bits of max|W[:, t]| (fix the per-column power-of-two scales of W16)
   float* out;             // [n_rsplit][M][T_pad]
 };
 
@@ -178,7 +178,6 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     const int q = warp & 3;
     const int row = q * 32 + lane;                        // centre inside the column tile (= TMEM lane)
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const float inv_s = w16_scale_from_bits(__ldg(p.absmax), true);
     uint32_t g = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int s = it / p.n_ct, j = it - s * p.n_ct;
@@ -217,9 +216,10 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           if (4 * v < p.T_pad) {
+            const uint4 mx = __ldg(reinterpret_cast<const uint4*>(p.absmax) + v);     // per-column scales of W16
             float4 t4;
-            t4.x = acc[4 * v + 0] * inv_s; t4.y = acc[4 * v + 1] * inv_s;
-            t4.z = acc[4 * v + 2] * inv_s; t4.w = acc[4 * v + 3] * inv_s;
+            t4.x = acc[4 * v + 0] * w16_scale_from_bits(mx.x, true); t4.y = acc[4 * v + 1] * w16_scale_from_bits(mx.y, true);
+            t4.z = acc[4 * v + 2] * w16_scale_from_bits(mx.z, true); t4.w = acc[4 * v + 3] * w16_scale_from_bits(mx.w, true);
             *reinterpret_cast<float4*>(orow + 4 * v) = t4;
           }
         }
@@ -270,7 +270,7 @@ int panel16_splits(int64_t n_rows, int64_t M) {
 int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W16, const uint32_t* absmax, int T_pad,
                        int n_splits, float* out_partial, cudaStream_t st) {
   if (n_rows <= 0 || M <= 0 || (T_pad != 16 && T_pad != 32) || (reinterpret_cast<uintptr_t>(P16) & 127) != 0 ||
-      (reinterpret_cast<uintptr_t>(W16) & 127) != 0 || (reinterpret_cast<uintptr_t>(out_partial) & 15) != 0 || !absmax)
+      (reinterpret_cast<uintptr_t>(W16) & 127) != 0 || (reinterpret_cast<uintptr_t>(out_partial) & 15) != 0 || !absmax || (reinterpret_cast<uintptr_t>(absmax) & 15) != 0)
     return set_error(ODF_ERR_ARG, "panel16_tmm: bad shape or alignment (P16, W16 128-byte aligned; T_pad 16 or 32)");
   if (n_splits != panel16_splits(n_rows, M)) return set_error(ODF_ERR_ARG, "panel16_tmm: n_splits must come from odf_panel16_splits");
   static bool attr_set = false;

@@ -186,6 +186,49 @@ split_rhs_kernel(const float* __restrict__ V, int64_t m, int T, int64_t ldv, flo
   }
 }
 
+// V [m x T] -> per-column max |scale V| (bits) for the fp16 split below
+__global__ void __launch_bounds__(256)
+col_absmax_kernel(const float* __restrict__ V, int64_t m, int T, int64_t ldv, float scale, uint32_t* __restrict__ absmax) {
+  __shared__ float red[8][32];
+  const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float amax = 0.f;
+  if (t < T)
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + w; r < m; r += static_cast<int64_t>(gridDim.x) * 8)
+      amax = fmaxf(amax, fabsf(__ldg(V + r * ldv + t) * scale));
+  red[w][t] = amax;
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i][t]);
+    if (t < T && amax > 0.f) atomicMax(absmax + t, __float_as_uint(amax));
+  }
+}
+
+// V [m x T] -> vt_hi16 / vt_lo16 [T_pad x ldvt] fp16 (transposed): hi = rn16(s_t v), lo = rn16((s_t v - hi) 2^11) with the
+// per-column power-of-two scale s_t = w16_scale(absmax[t]); the B operand of the pair tile's K.V contraction.
+__global__ void __launch_bounds__(128)
+split_rhs16_kernel(const float* __restrict__ V, int64_t m, int T, int64_t ldv, float scale, const uint32_t* __restrict__ absmax,
+                   __half* __restrict__ vt_hi, __half* __restrict__ vt_lo, int64_t ldvt, int T_pad) {
+  __shared__ float tile[32][129];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 128;
+  for (int idx = threadIdx.x; idx < 128 * T_pad; idx += 128) {
+    const int r = idx / T_pad, t = idx - r * T_pad;
+    float v = 0.f;
+    if (t < T && r0 + r < m) v = __ldg(V + (r0 + r) * ldv + t) * scale * w16_scale_from_bits(__ldg(absmax + t), false);
+    tile[t][r] = v;
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r0 + r < ldvt) {
+    for (int t = 0; t < T_pad; ++t) {
+      const float v = tile[t][r];
+      const __half h = __float2half_rn(v);
+      vt_hi[t * ldvt + r0 + r] = h;
+      vt_lo[t * ldvt + r0 + r] = __float2half_rn((v - __half2float(h)) * 2048.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ finish (split-slab reduce)
 // partial [S][n][T_pad] -> out[n x T]: each thread owns one row (a full 64/128-byte line per
 // slab), sums the slabs in index order.
@@ -215,25 +258,29 @@ finish_rows_kernel(const float* __restrict__ partial, int S, int64_t n, int T_pa
   for (int t = 0; t < 32; ++t) tile[threadIdx.x][t] = acc[t] * scale;
   __syncthreads();
   // coalesced store along rows of out
-  float amax = 0.f;
   for (int idx = threadIdx.x; idx < 128 * T; idx += 128) {
     const int rr = idx / T, t = idx - rr * T;
+    float v = 0.f;
     if (r0 + rr < n) {
-      float v = tile[rr][t];
+      v = tile[rr][t];
       if (addend) v += __ldg(addend + (r0 + rr) * ld_add + t);
       out[(r0 + rr) * ldo + t] = v;
-      amax = fmaxf(amax, fabsf(v));
     }
+    if (absmax != nullptr) tile[rr][t] = fabsf(v);
   }
-  if (absmax != nullptr) {                     // max |out| of the launch (bit pattern of a non-negative float orders as uint)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(absmax, __float_as_uint(amax));
+  if (absmax != nullptr) {                     // per-column max |out| (bit pattern of a non-negative float orders as uint)
+    __syncthreads();
+    if (threadIdx.x < T) {
+      float amax = 0.f;
+      for (int rr = 0; rr < 128; ++rr) amax = fmaxf(amax, tile[rr][threadIdx.x]);
+      if (amax > 0.f) atomicMax(absmax + threadIdx.x, __float_as_uint(amax));
+    }
   }
 }
 
-// W [n x ldw] fp32 -> W16 [round_up(n,128) x 64] fp16: columns 0..31 hi = rn16(s W), 32..63 lo = rn16((s W - hi) 2^11),
-// s = w16_scale(max|W|) a power of two; rows >= n and columns >= T are zero (the B operand of odf_panel16.cu).
+// W [n x ldw] fp32 -> W16 [round_up(n,128) x 64] fp16: columns 0..31 hi = rn16(s_t W), 32..63 lo = rn16((s_t W - hi) 2^11),
+// s_t = w16_scale(max|W[:, t]|) a power of two per column; rows >= n and columns >= T are zero (the B operand of
+// odf_panel16.cu).
 __global__ void __launch_bounds__(256)
 split_w16_kernel(const float* __restrict__ W, int64_t n, int64_t n_pad, int ldw, int T, const uint32_t* __restrict__ absmax,
                  __half* __restrict__ W16) {
@@ -241,12 +288,11 @@ split_w16_kernel(const float* __restrict__ W, int64_t n, int64_t n_pad, int ldw,
   const int64_t r = idx >> 2;
   const int t0 = static_cast<int>(idx & 3) * 8;
   if (r >= n_pad) return;
-  const float sc = w16_scale_from_bits(__ldg(absmax), false);
   __align__(16) __half hi[8], lo[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int t = t0 + i;
-    const float v = (r < n && t < T) ? __ldg(W + r * ldw + t) * sc : 0.f;
+    const float v = (r < n && t < T) ? __ldg(W + r * ldw + t) * w16_scale_from_bits(__ldg(absmax + t), false) : 0.f;
     const __half h = __float2half_rn(v);
     hi[i] = h;
     lo[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
@@ -506,6 +552,20 @@ int split_rhs(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, fl
   return check_launch("split_rhs_kernel");
 }
 
+int split_rhs16(const float* V, int64_t m, int64_t T, int64_t ldv, float scale, uint32_t* absmax, void* vt_hi, void* vt_lo,
+                int64_t ldvt, int T_pad, cudaStream_t st) {
+  if (m <= 0 || T <= 0 || T > T_pad || T_pad > 32 || ldvt < m || ldvt % 128 != 0 || !absmax)
+    return set_error(ODF_ERR_ARG, "split_rhs16: bad shape");
+  cudaError_t e = cudaMemsetAsync(absmax, 0, 32 * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "split_rhs16: memset");
+  int64_t nb = (m + 63) / 64;
+  if (nb > 592) nb = 592;
+  col_absmax_kernel<<<static_cast<unsigned>(nb), 256, 0, st>>>(V, m, static_cast<int>(T), ldv, scale, absmax);
+  split_rhs16_kernel<<<static_cast<unsigned>(ldvt / 128), 128, 0, st>>>(V, m, static_cast<int>(T), ldv, scale, absmax,
+                                                                        static_cast<__half*>(vt_hi), static_cast<__half*>(vt_lo), ldvt, T_pad);
+  return check_launch("split_rhs16");
+}
+
 int finish_rows(const float* partial, int S, int64_t n, int T_pad, int64_t T, float scale,
                 const float* addend, int64_t ld_add, float* out, int64_t ldo, cudaStream_t st) {
   if (S <= 0 || n <= 0 || T <= 0 || T > T_pad || T_pad > 32) return set_error(ODF_ERR_ARG, "finish_rows: bad shape");
@@ -514,13 +574,13 @@ int finish_rows(const float* partial, int S, int64_t n, int T_pad, int64_t T, fl
 }
 
 // W = sum of the partial slabs (+ addend) as finish_rows, then its fp16 hi/lo split for odf_panel16_tmm.
-// Wf: fp32 scratch [n x T_pad]; absmax: one device word (reset here); W16: [round_up(n,128) x 64] fp16.
+// Wf: fp32 scratch [n x T_pad]; absmax: 32 device words (per-column max |W| bits, reset here); W16: [round_up(n,128) x 64] fp16.
 int finish_w16(const float* partial, int S, int64_t n, int T_pad, int64_t T, const float* addend, int64_t ld_add,
                float* Wf, uint32_t* absmax, void* W16, cudaStream_t st) {
   if (S <= 0 || n <= 0 || T <= 0 || T > T_pad || T_pad > 32 || !Wf || !absmax || !W16 ||
       (reinterpret_cast<uintptr_t>(W16) & 127) != 0)
     return set_error(ODF_ERR_ARG, "finish_w16: bad shape or alignment");
-  cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(uint32_t), st);
+  cudaError_t e = cudaMemsetAsync(absmax, 0, 32 * sizeof(uint32_t), st);
   if (e != cudaSuccess) return set_cuda_error(e, "finish_w16: memset");
   finish_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(partial, S, n, T_pad, static_cast<int>(T), 1.f, addend, ld_add, Wf, T_pad, absmax);
   const int64_t n_pad = (n + 127) / 128 * 128;

@@ -33,6 +33,10 @@ SIGNATURES = {
     "odf_panel_splits": (c_int, [c_i64, c_i64]),
     "odf_panel_tmm": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_int, c_fp, c_fp]),
     "odf_panel16_bytes": (c_sz, [c_i64, c_i64]),
+    "odf_tile_pair_eligible": (c_int, [c_i64]),
+    "odf_split_rhs16": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_fp, c_i64, c_int, c_fp]),
+    "odf_gauss_mmv_pair": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64,
+                                   c_fp, c_fp, c_i64, c_fp, c_int, c_int, c_f, c_fp, c_fp, c_fp]),
     "odf_gauss_mmv_prepared_spill16": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64,
                                                c_i64, c_fp, c_fp, c_i64, c_int, c_int, c_f, c_fp, c_fp, c_fp]),
     "odf_finish_w16": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp]),

@@ -92,7 +92,7 @@ class Prepared:
 class SplitRhs:
     """Transposed, split right-hand side block [T_pad x pad_rows(m)] (odf_split_rhs)."""
 
-    __slots__ = ("hi", "lo", "ld", "T", "T_pad", "m")
+    __slots__ = ("hi", "lo", "ld", "T", "T_pad", "m", "hi16", "lo16", "absmax")
 
     def __init__(self, m, T, device):
         L = _lib.load()
@@ -101,8 +101,12 @@ class SplitRhs:
         if self.T_pad < 0:
             raise ValueError("at most 32 right-hand sides per block")
         self.ld = int(L.odf_pad_rows(m))
+        # tf32 hi/lo for the single-CTA tile, fp16 hi/lo (+ per-column scales) for the CTA-pair tile
         self.hi = torch.empty((self.T_pad, self.ld), dtype=torch.float32, device=device)
         self.lo = torch.empty((self.T_pad, self.ld), dtype=torch.float32, device=device)
+        self.hi16 = torch.empty((self.T_pad, self.ld), dtype=torch.float16, device=device)
+        self.lo16 = torch.empty((self.T_pad, self.ld), dtype=torch.float16, device=device)
+        self.absmax = torch.zeros((32,), dtype=torch.int32, device=device)
 
     def fill(self, V, scale=1.0):
         L = _lib.load()
@@ -110,7 +114,9 @@ class SplitRhs:
         assert V.shape[0] == self.m and V.shape[1] == self.T
         check(L.odf_split_rhs(ptr(V), self.m, self.T, ldv, float(scale), ptr(self.hi), ptr(self.lo), self.ld,
                               self.T_pad, _stream()), "odf_split_rhs")
-        _count(1)
+        check(L.odf_split_rhs16(ptr(V), self.m, self.T, ldv, float(scale), ptr(self.absmax), ptr(self.hi16),
+                                ptr(self.lo16), self.ld, self.T_pad, _stream()), "odf_split_rhs16")
+        _count(3)
         return self
 
 
@@ -142,6 +148,23 @@ def mmv_partial(rows, cols, rhs, sigma, partial, panel=None, panel16=None):
     L = _lib.load()
     assert rows.d == cols.d and rows.kind == cols.kind and rhs.m == cols.n
     S = int(partial.shape[0])
+    if panel is None and int(L.odf_tile_pair_eligible(rows.n)):
+        # CTA-pair tile (cta_group::2): large launches, with or without the fp16-plane spill
+        if panel16 is not None:
+            assert panel16.numel() * panel16.element_size() >= int(L.odf_panel16_bytes(rows.n, cols.n))
+        ev = None
+        if TILE_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        check(L.odf_gauss_mmv_pair(rows.kind, ptr(rows.hi), ptr(rows.lo), ptr(rows.sqn), ptr(rows.opscale), rows.n,
+                                   ptr(cols.hi), ptr(cols.lo), ptr(cols.sqn), ptr(cols.opscale), cols.n, rows.d,
+                                   ptr(rhs.hi16), ptr(rhs.lo16), rhs.ld, ptr(rhs.absmax), rhs.T_pad, S, float(sigma),
+                                   ptr(partial), ptr(panel16), _stream()), "odf_gauss_mmv_pair")
+        if ev is not None:
+            ev[1].record()
+            TILE_EVENTS.append((ev[0], ev[1], rows.n, cols.n, rows.d, rhs.T))
+        _count(1)
+        return
     if panel16 is not None:
         assert panel is None and panel16.numel() * panel16.element_size() >= int(L.odf_panel16_bytes(rows.n, cols.n))
         ev = None
@@ -442,7 +465,7 @@ class Sweeper:
             self.part1 = [alloc_partial(v, cols, Tp, dev) for v in self.views[:1] + self.views[-1:]]
             self.Wf = torch.empty((self.chunk, Tp), dtype=torch.float32, device=dev)
             self.W16 = torch.empty(((self.chunk + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
-            self.absmax = torch.zeros((1,), dtype=torch.int32, device=dev)
+            self.absmax = torch.zeros((32,), dtype=torch.int32, device=dev)
             self.pslabs = [int(L.odf_panel16_splits(r1 - r0, cols.n)) for (r0, r1) in self.chunks]
             self.part3 = torch.empty((sum(self.pslabs), cols.n, Tp), dtype=torch.float32, device=dev)
         elif mode == "panel":
@@ -457,6 +480,7 @@ class Sweeper:
             self.part3 = torch.empty((sum(self.pslabs), cols.n, Tp), dtype=torch.float32, device=dev)
         else:
             self.part1 = alloc_partial(rows, cols, Tp, dev)   # rows = data
+            self.Wfull = torch.empty((rows.n, int(T)), dtype=torch.float32, device=dev)
 
     def dmmv(self, v, w, out, scale=1.0, w_scale=1.0):
         """out = scale * K^T (K v + w_scale * w)   (local rows only; caller all-reduces)."""
@@ -480,7 +504,8 @@ class Sweeper:
             return finish_rows(self.part3, self.T, out, scale)
         if self.mode != "panel":
             mmv_partial(self.rows, self.cols, self.v_rhs, self.sigma, self.part1)
-            finish_split(self.part1, self.T, self.w_rhs, 1.0, w)
+            finish_rows(self.part1, self.T, self.Wfull, 1.0, w)
+            self.w_rhs.fill(self.Wfull)          # both operand formats (tf32 for the single-CTA tile, fp16 for the pair)
             mmv_partial(self.cols, self.rows, self.w_rhs, self.sigma, self.part2)
             return finish_rows(self.part2, self.T, out, scale)
         slab = 0

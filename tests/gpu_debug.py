@@ -265,6 +265,28 @@ def run_stage(stage):
                 ok &= err < 2e-5
                 del sw
             print(msg, flush=True)
+    elif stage == "epi":
+        # timing-only: which part of the tile bounds a launch (results are garbage under the debug flags)
+        from odf import ops
+        L2 = _lib.load()
+        for (n, M, d, T) in [(131072, 30000, 256, 21), (131072, 10000, 1024, 30)]:
+            X = _data(n, d, 1); C = _data(M, d, 2)
+            px, pc = ops.Prepared(X, kind=1), ops.Prepared(C, kind=1)
+            rhs = ops.SplitRhs(M, T, "cuda").fill(torch.randn(M, T, device="cuda"))
+            part = ops.alloc_partial(px, pc, rhs.T_pad, "cuda")
+            p16 = torch.empty((int(L2.odf_panel16_bytes(n, M)),), dtype=torch.uint8, device="cuda")
+            for spill in (None, p16):
+                res = []
+                for flags in (0, 32, 10, 42, 4, 14):
+                    os.environ["ODF_TILE_DEBUG"] = str(flags)
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    for it in range(3):
+                        if it == 1: e0.record()
+                        ops.mmv_partial(px, pc, rhs, 20.0, part, panel16=spill)
+                    e1.record(); torch.cuda.synchronize()
+                    res.append("%d:%.2f" % (flags, e0.elapsed_time(e1) / 2))
+                os.environ["ODF_TILE_DEBUG"] = "0"
+                print(f"epi n={n} M={M} d={d} T={T} spill16={spill is not None} ms by flags(1=noTMA,2=noSMMA,4=noEpiMath,8=noPV): " + " ".join(res), flush=True)
     elif stage == "bottleneck":
         # timing-only experiments (results are garbage under the debug flags)
         from odf import ops

@@ -187,7 +187,7 @@ def test_panel16_kernel_matches_fp64_product(odf):
     ops.mmv_partial(rows, cols, rhs, 15.0, part1, panel16=p16)
     Wf = torch.empty((n, rhs.T_pad), device=dev)
     W16 = torch.empty(((n + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
-    absmax = torch.zeros(1, dtype=torch.int32, device=dev)
+    absmax = torch.zeros(32, dtype=torch.int32, device=dev)
     ops.finish_w16(part1, T, Wf, absmax, W16, addend=W.cuda())        # K.0 + W = W
     assert torch.equal(Wf[:, :T].cpu(), W)
     S = int(L.odf_panel16_splits(n, M))
