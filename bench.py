@@ -299,8 +299,19 @@ def run_ours(args):
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else \
         "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
+    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of the same launch shape
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v3_traffic.json")))
+        tk = tj["gauss_tile2_kernel"]
+        if any((r, c_, dd) == (tk["rows"], tk["cols"], tk["d"]) for (_a, _b, r, c_, dd, _t) in tile_events):
+            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+            traffic_src = tj["source"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "launches_timed": len(tile_ms),
                 "tile_share_of_step": sum(tile_ms) / args.steps / ms_dev,
                 "executed_tensor_tflops": executed, "executed_frac_of_peak": executed / peak,
