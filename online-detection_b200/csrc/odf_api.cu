@@ -98,6 +98,82 @@ int ensure_handles(cudaStream_t st) {
   return ODF_OK;
 }
 
+// Row-major C (m x n) = alpha op(A) op(B) + beta C, true fp32 (cuBLAS SIMT sgemm, ~67 TFLOP/s on B200).
+// cuBLAS 12.9 can emulate this GEMM on the bf16 tensor cores (CUBLAS_COMPUTE_32F_EMULATED_16BFX9: 175-200 TFLOP/s with
+// better-than-sgemm accuracy, tools/emu_probe.cu), but inside a PyTorch process the cuBLAS that is already loaded is
+// torch's own 12.8 build, which rejects that compute type -- so the preconditioner gets its speed from doing less work
+// (triangle-aware products, recursive inverse) instead.  ODF_PRECOND_TRACE=1 prints every call with its timing.
+int gemm_rm(bool ta, bool tb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda, const float* B,
+            int64_t ldb, float beta, float* C, int64_t ldc) {
+  static int trace = -1;
+  if (trace < 0) {
+    const char* e = getenv("ODF_PRECOND_TRACE");
+    trace = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t cst = nullptr;
+  if (trace) {
+    cublasGetStream(g_cublas, &cst);
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, cst);
+  }
+  // row-major C = op(A) op(B)  <=>  column-major C' = op(B') op(A')
+  cublasStatus_t st = cublasSgemm(g_cublas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, static_cast<int>(n),
+                                  static_cast<int>(m), static_cast<int>(k), &alpha, B, static_cast<int>(ldb), A,
+                                  static_cast<int>(lda), &beta, C, static_cast<int>(ldc));
+  if (trace) {
+    cudaEventRecord(ev1, cst);
+    cudaEventSynchronize(ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    printf("gemm_rm %c%c m=%lld n=%lld k=%lld: %.3f ms  %.1f TFLOP/s  status=%d\n", ta ? 'T' : 'N', tb ? 'T' : 'N', (long long)m,
+           (long long)n, (long long)k, ms, 2.0 * m * n * k / ms / 1e9, (int)st);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  }
+  return st == CUBLAS_STATUS_SUCCESS ? ODF_OK : set_error(ODF_ERR_CUDA, "cublasSgemm (preconditioner) failed");
+}
+
+constexpr int64_t PC_NB = 2048;     // block width of the triangular-aware products
+constexpr int64_t PC_LEAF = 1024;   // diagonal blocks inverted by one TRSM against the identity
+
+// Upper triangle (row-major, block granularity) of A = alpha T T^T for an upper-triangular T (zeros below the diagonal):
+// A[0:(J+1)nb, Jblock] = T[0:(J+1)nb, J nb:] . T[Jblock, J nb:]^T  -- M^3/3 useful flops instead of the 2 M^3 of a full GEMM.
+int ttt_upper(const float* T, float* A, int64_t M, float alpha) {
+  for (int64_t c0 = 0; c0 < M; c0 += PC_NB) {
+    const int64_t nb = (M - c0 < PC_NB) ? (M - c0) : PC_NB;
+    const int rc = gemm_rm(false, true, c0 + nb, nb, M - c0, alpha, T + c0, M, T + c0 * M + c0, M, 0.f, A + c0, M);
+    if (rc) return rc;
+  }
+  return ODF_OK;
+}
+
+// X = T^-1 for an upper-triangular n x n block (row-major, pitch ld).  On entry X holds the identity.  Recursive:
+//   [T11 T12; 0 T22]^-1 = [X11, -X11 T12 X22; 0, X22];  the (otherwise zero) X21 block is the scratch for (T12 X22)^T.
+int inv_upper_rec(const float* T, float* X, int64_t n, int64_t ld, cudaStream_t st) {
+  if (n <= PC_LEAF) {
+    // X' L = I' with L = T^T column-major lower (see odf_precond_solve)
+    const float one = 1.f;
+    if (cublasStrsm(g_cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, static_cast<int>(n),
+                    static_cast<int>(n), &one, T, static_cast<int>(ld), X, static_cast<int>(ld)) != CUBLAS_STATUS_SUCCESS)
+      return set_error(ODF_ERR_CUDA, "cublasStrsm (precond_invert leaf) failed");
+    return ODF_OK;
+  }
+  const int64_t n1 = ((n / 2) + 127) / 128 * 128, n2 = n - n1;
+  const float* T12 = T + n1;
+  const float* T22 = T + n1 * ld + n1;
+  float* X12 = X + n1;
+  float* X21 = X + n1 * ld;
+  float* X22 = X + n1 * ld + n1;
+  int rc;
+  if ((rc = inv_upper_rec(T, X, n1, ld, st))) return rc;
+  if ((rc = inv_upper_rec(T22, X22, n2, ld, st))) return rc;
+  if ((rc = gemm_rm(true, true, n2, n1, n2, 1.f, X22, ld, T12, ld, 0.f, X21, ld))) return rc;     // X21 <- (T12 X22)^T
+  if ((rc = gemm_rm(false, true, n1, n2, n1, -1.f, X, ld, X21, ld, 0.f, X12, ld))) return rc;      // X12 <- -X11 (T12 X22)
+  // the scratch block is part of the (upper-triangular) result of the caller's level: back to exact zeros
+  cudaError_t e = cudaMemset2DAsync(X21, static_cast<size_t>(ld) * 4, 0, static_cast<size_t>(n1) * 4, static_cast<size_t>(n2), st);
+  return e == cudaSuccess ? ODF_OK : set_cuda_error(e, "precond_invert: memset");
+}
+
 }  // namespace
 }  // namespace odf
 
@@ -379,9 +455,7 @@ int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void
     return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf (T) failed to launch");
   if ((rc = zero_lower(Tm, M, st))) return rc;  // row-major strict lower == the triangle potrf left untouched
   // A: (1/M) T T^T + lam I = (1/M) L^T L + lam I
-  const float alpha = 1.f / static_cast<float>(M), beta = 0.f;
-  if (cublasSsyrk(g_cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, m, m, &alpha, Tm, m, &beta, Am, m) != CUBLAS_STATUS_SUCCESS)
-    return set_error(ODF_ERR_CUDA, "cublasSsyrk failed");
+  if ((rc = ttt_upper(Tm, Am, M, 1.f / static_cast<float>(M)))) return rc;
   if ((rc = add_diag(Am, M, lam, st))) return rc;
   if (cusolverDnSpotrf(g_cusolver, CUBLAS_FILL_MODE_LOWER, m, Am, m, work, lwork, info + 1) != CUSOLVER_STATUS_SUCCESS)
     return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf (A) failed to launch");
@@ -451,9 +525,10 @@ int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t 
 int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
+  if ((rc = ensure_handles(st))) return rc;
   if ((rc = set_identity(Inv, M, st))) return rc;
-  if ((rc = odf_precond_solve(Tri, M, Inv, M, M, ODF_SOLVE_T, stream))) return rc;
-  return zero_lower(Inv, M, st);      // exact zeros below the diagonal (TRSM leaves rounding dust there)
+  if ((rc = inv_upper_rec(Tri, Inv, M, M, st))) return rc;
+  return zero_lower(Inv, M, st);      // exact zeros below the diagonal (scratch blocks and TRSM rounding dust)
 }
 
 int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T, int64_t ldb,

@@ -47,8 +47,9 @@ class FalkonOptions:
         # and contracted by the tensor-core panel kernel; "panel": fp32 panel + fp32-FMA panel kernel;
         # "recompute": evaluate K twice (no panel workspace)
         self.sweep_mode = ignored.pop("sweep_mode", "panel16")
-        # multi-GPU fits split T T^T and the explicit inverses over the ranks (False: every rank builds all)
-        self.distributed_precond = ignored.pop("distributed_precond", True)
+        # multi-GPU fits split T T^T and the explicit inverses over the ranks as column blocks (all-gathered); below
+        # 4 ranks the replicated triangle-aware build is as fast and skips the M x M gathers.  None = by world size.
+        self.distributed_precond = ignored.pop("distributed_precond", None)
         self.ignored = dict(ignored)
 
 
@@ -298,8 +299,9 @@ class Falkon:
         opt = self.options
         Kmm = be.kmm(pc, sigma)
         M = Kmm.shape[0]
-        split = dist is not None and world > 1 and getattr(opt, "distributed_precond", True) and M >= 4 * world \
-            and hasattr(be, "potrf_upper_")
+        want = getattr(opt, "distributed_precond", None)
+        want = (world >= 4) if want is None else bool(want)
+        split = dist is not None and world > 1 and want and M >= 4 * world and hasattr(be, "potrf_upper_")
         if not split:
             Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
             if opt.precond_apply == "inverse":

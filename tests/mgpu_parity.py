@@ -32,7 +32,7 @@ def main():
     lo, hi = (N * rank) // world, (N * (rank + 1)) // world
     ok = True
     res = {}
-    for name, opts in (("distributed_precond", {}), ("replicated_precond", {"distributed_precond": False})):
+    for name, opts in (("replicated_precond", {"distributed_precond": False}), ("distributed_precond", {"distributed_precond": True})):
         m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=None,
                              options=odf.FalkonOptions(**opts))
         m.fit(X[lo:hi].to(dev), Y[lo:hi].to(dev), centres=C.to(dev))
