@@ -20,11 +20,15 @@
 // problems stay on the single-CTA kernel.  Reference call sites are those of odf_gauss_tile.cu (falkon
 // GaussianKernel.mmv / dmmv behind FALKONWrapper_with_centers_selection_incore.py:68,75-82).
 //
+// (4 + EPI_WARPS) warps per CTA: warp 0 operand producer, 1 MMA issuer (leader), 2 TMEM allocator + centre-norm ring
+// producer, 3 V^T producer, 4.. epilogue (EPI_WARPS = 8 puts two warps on each TMEM lane quarter, each taking half of a
+// tile's column chunks; measured no faster than 4 once the centre norms came from shared memory).
+//
 // Protocol (barriers at the same shared-memory offset in both CTAs):
 //   FULL[s]   leader's copy only, count 2: each CTA's producer arrives with its own byte count, its TMA loads
 //             complete_tx on the leader's barrier (cp.async.bulk.tensor ... cta_group::2)
 //   EMPTY[s], SFULL[b], VEMPTY, WFULL: one arrival per CTA from the leader's multicast tcgen05.commit
-//   PREADY, WEMPTY: leader's copy only, count 256: the epilogue threads of both CTAs arrive (remote for rank 1)
+//   PREADY, WEMPTY: leader's copy only, count 2 x 32 x EPI_WARPS: the epilogue threads of both CTAs arrive (remote for rank 1)
 //   VFULL     leader's copy only, count 2 (V^T halves)
 //   QFULL[4], QEMPTY[4]: per CTA, the ring of centre norms (producer: warp 2, consumers: the 4 epilogue warps)
 #include <cstdlib>
@@ -47,6 +51,8 @@ constexpr int STAGE_BYTES = 2 * RT_BYTES + 2 * QT_BYTES;   // 48 KB
 constexpr int MAX_TPAD = 32;
 constexpr int V_ATOM_BYTES_MAX = (MAX_TPAD / 2) * 128;     // one [T_pad/2 x 64 fp16] box
 constexpr int V_BYTES = 2 * 2 * V_ATOM_BYTES_MAX;          // hi+lo, 2 atoms each: 8 KB
+constexpr int EPI_WARPS = 4;               // epilogue warps: 4 (one per TMEM lane quarter) or 8 (two; measured no faster)
+constexpr int NTHREADS = (4 + EPI_WARPS) * 32;
 constexpr int QN_SLOTS = 4;
 constexpr int QN_BYTES = QN_SLOTS * BN * 4;                // ring of |c|^2 for 4 column tiles
 constexpr int NUM_BARS = 2 * NS + 7 + 2 * QN_SLOTS;
@@ -112,7 +118,7 @@ __device__ __forceinline__ void mma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem
 
 // In this kernel TileParams::n_rowblocks counts 256-row PAIR blocks; rb128 = number of 128-row blocks (panel layout).
 template <int KIND, int SPILL16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
                    const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                    const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
@@ -154,15 +160,15 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
     }
     mbar_init(BAR(B_SFULL + 0), 1);
     mbar_init(BAR(B_SFULL + 1), 1);
-    mbar_init(BAR(B_PREADY), 256);
+    mbar_init(BAR(B_PREADY), 2 * EPI_WARPS * 32);
     for (int s = 0; s < QN_SLOTS; ++s) {
       mbar_init(BAR(B_QFULL + s), 1);
-      mbar_init(BAR(B_QEMPTY + s), 4);
+      mbar_init(BAR(B_QEMPTY + s), EPI_WARPS);
     }
     mbar_init(BAR(B_VFULL), 2);
     mbar_init(BAR(B_VEMPTY), 1);
     mbar_init(BAR(B_WFULL), 1);
-    mbar_init(BAR(B_WEMPTY), 256);
+    mbar_init(BAR(B_WEMPTY), 2 * EPI_WARPS * 32);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -199,13 +205,15 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
               // seed block: rows bring [-|x|^2/2 hi, lo, 0...], columns bring [1, 1, 0...]
               mbar_arrive_expect_tx_leader(full, RT_BYTES + QT_BYTES);
               tma_load_2d_pair(dst, &tmRh, full, KB * BK, my_row0);
-              tma_load_2d_pair(dst + 2 * RT_BYTES, &tmQh, full, (KB + 1) * BK, my_col0);
+              tma_load_2d_pair_hint(dst + 2 * RT_BYTES, &tmQh, full, (KB + 1) * BK, my_col0, kEvictLast);
             } else {
               mbar_arrive_expect_tx_leader(full, STAGE_BYTES);
               tma_load_2d_pair(dst, &tmRh, full, kb * BK, my_row0);
               tma_load_2d_pair(dst + RT_BYTES, &tmRl, full, kb * BK, my_row0);
-              tma_load_2d_pair(dst + 2 * RT_BYTES, &tmQh, full, kb * BK, my_col0);
-              tma_load_2d_pair(dst + 2 * RT_BYTES + QT_BYTES, &tmQl, full, kb * BK, my_col0);
+              // the column operands (centres) are re-read by every row block of the launch: keep them in L2 against
+              // the panel planes streaming through it
+              tma_load_2d_pair_hint(dst + 2 * RT_BYTES, &tmQh, full, kb * BK, my_col0, kEvictLast);
+              tma_load_2d_pair_hint(dst + 2 * RT_BYTES + QT_BYTES, &tmQl, full, kb * BK, my_col0, kEvictLast);
             }
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
@@ -341,7 +349,10 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
     __syncwarp();
   } else if (warp >= 4) {
     // ======================= epilogue (both CTAs, own 128 rows) =======================
+    // with EPI_WARPS = 8: warps 4-7 take the column chunks 0-1 of every tile, warps 8-11 the chunks 2-3
     const int q = warp & 3;
+    const int set = (warp - 4) >> 2;
+    constexpr int CH_PER_SET = (BN / 32) / (EPI_WARPS / 4);
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float nsl2 = p.neg_scale_log2;
@@ -365,7 +376,7 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
         mbar_wait_warp(BAR(B_QFULL + slot), (n / QN_SLOTS) & 1);
         const float4* qs = reinterpret_cast<const float4*>(qn_base + slot * BN);
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = set * CH_PER_SET; ch < (set + 1) * CH_PER_SET; ++ch) {
           uint32_t s[32];
           __syncwarp();
           tmem_ld32(t_s + ch * 32, s);
@@ -396,9 +407,10 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
             __half* dst = p.panel16 + (((static_cast<int64_t>(j) * rb128 + my_rb) * 16 + ch * 4) * 128 + row) * 8;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-              *reinterpret_cast<uint4*>(dst + v * 1024) = make_uint4(kp[4 * v], kp[4 * v + 1], kp[4 * v + 2], kp[4 * v + 3]);
-              *reinterpret_cast<uint4*>(dst + p.panel16_plane + v * 1024) =
-                  make_uint4(kp[16 + 4 * v], kp[17 + 4 * v], kp[18 + 4 * v], kp[19 + 4 * v]);
+              // st.global.cs: written once, read once by the panel kernel -> first in line for eviction
+              __stcs(reinterpret_cast<uint4*>(dst + v * 1024), make_uint4(kp[4 * v], kp[4 * v + 1], kp[4 * v + 2], kp[4 * v + 3]));
+              __stcs(reinterpret_cast<uint4*>(dst + p.panel16_plane + v * 1024),
+                     make_uint4(kp[16 + 4 * v], kp[17 + 4 * v], kp[18 + 4 * v], kp[19 + 4 * v]));
             }
           }
         }
@@ -413,7 +425,7 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
       tc_fence_after();
       const uint32_t t_w = tmem_base + lane_off + TM_W;
       float* orow = p.out + static_cast<int64_t>(w.split) * p.split_stride + static_cast<int64_t>(grow) * T_pad;
-      for (int c0 = 0; c0 < T_pad; c0 += 16) {
+      for (int c0 = 16 * set; c0 < T_pad; c0 += 16 * (EPI_WARPS / 4)) {
         uint32_t r[16];
         float acc[16];
         __syncwarp();
@@ -543,13 +555,13 @@ int launch_gauss_tile2(const TileLaunch& L, cudaStream_t stream) {
   const int n_pairs = n_items < pairs_max ? n_items : pairs_max;
   const int grid = 2 * n_pairs;
   if (L.kind == KIND_F16 && L.panel16 != nullptr)
-    gauss_tile2_kernel<KIND_F16, 1><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
+    gauss_tile2_kernel<KIND_F16, 1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
   else if (L.kind == KIND_F16)
-    gauss_tile2_kernel<KIND_F16, 0><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
+    gauss_tile2_kernel<KIND_F16, 0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
   else if (L.panel16 != nullptr)
-    gauss_tile2_kernel<KIND_TF32, 1><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
+    gauss_tile2_kernel<KIND_TF32, 1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
   else
-    gauss_tile2_kernel<KIND_TF32, 0><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
+    gauss_tile2_kernel<KIND_TF32, 0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p, rb128);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "gauss_tile2_kernel launch");
   return ODF_OK;

@@ -123,11 +123,12 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
           const int y = (j * p.n_rb + (st >> 1)) * 16;
           const int x = (st & 1) * 512;
           mbar_arrive_expect_tx(full, QSTAGE);
-          tma_load_2d(dst + 0 * QBOX, &tmP, full, x, y);
-          tma_load_2d(dst + 1 * QBOX, &tmP, full, x + 256, y);
-          tma_load_2d(dst + 2 * QBOX, &tmP, full, x, p.plane_rows + y);
-          tma_load_2d(dst + 3 * QBOX, &tmP, full, x + 256, p.plane_rows + y);
-          tma_load_2d(dst + 4 * QBOX, &tmW, full, 0, st * QR);
+          // the planes are read exactly once (evict first); W16 is shared by every column tile (evict last)
+          tma_load_2d_hint(dst + 0 * QBOX, &tmP, full, x, y, kEvictFirst);
+          tma_load_2d_hint(dst + 1 * QBOX, &tmP, full, x + 256, y, kEvictFirst);
+          tma_load_2d_hint(dst + 2 * QBOX, &tmP, full, x, p.plane_rows + y, kEvictFirst);
+          tma_load_2d_hint(dst + 3 * QBOX, &tmP, full, x + 256, p.plane_rows + y, kEvictFirst);
+          tma_load_2d_hint(dst + 4 * QBOX, &tmW, full, 0, st * QR, kEvictLast);
           if (++stage == QNS) { stage = 0; phase ^= 1; }
         }
       }

@@ -361,6 +361,14 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(m), "r"(bar & kPeerBitMask), "r"(x), "r"(y)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(m), "r"(bar & kPeerBitMask), "r"(x), "r"(y), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }

@@ -12,10 +12,18 @@ reference's on-line learners run through the third-party `falkon` package:
                installable offline, so its published algorithm (Rudi, Carratino, Rosasco 2017;
                Meanti et al. 2020) is restated here following SURVEY.md Appendix A.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path and the
-`falkon` package cannot be imported here, so this oracle is pinned only by (i) the closed-form
-Nystrom kernel-ridge solution it must converge to, (ii) fp64-vs-fp32 self-agreement and (iii)
-hand-computed known-answer cases for the integer post-processing (tests/test_oracle.py).
+PARITY UNPINNED for the FALKON arithmetic (Gaussian kernel products, preconditioner, CG): the reference
+ships no tests, golden vectors or fixtures for this path and the `falkon` package cannot be imported
+here, so that part of the oracle is pinned only by (i) the closed-form Nystrom kernel-ridge solution it
+must converge to, (ii) fp64-vs-fp32 self-agreement and (iii) hand-computed known-answer cases for the
+integer post-processing (tests/test_oracle.py).
+
+PINNED against the reference's own first-party code (tests/golden/make_reference_golden.py runs the
+UNMODIFIED py_od_utils.py, FALKONWrapper_with_centers_selection_incore.py, MyCenterSelector.py,
+OnlineRegionClassifier_incore.py and region_refiner.py + trainer on the CPU, with this oracle standing
+in for the absent `falkon` package; tests/test_reference_golden.py): centre selection with the
+reference's RNG draws, z-scoring, the minibootstrap loop (surviving negatives and centres bit-exact),
+feature statistics, COXY normalisation, RLS refiners (mu, T, T_inv, weights, losses), box decode.
 """
 import math
 

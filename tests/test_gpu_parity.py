@@ -101,6 +101,36 @@ def test_dmmv_matches_oracle(odf, n, M, d, T, mode):
 
 
 @pytest.mark.parametrize("kind", ["f16", "tf32"])
+@pytest.mark.parametrize("n,M,d,T", [(9001, 700, 96, 1), (20000, 1300, 1024, 30), (8192, 130, 40, 17)])
+def test_pair_tile_mmv_matches_oracle(odf, n, M, d, T, kind):
+    """Launches with >= 8192 rows run on the CTA-pair tile (cta_group::2, fp16-packed K.V contraction): ragged pair
+    blocks (9001 = 35 x 256 + 41: the second CTA of the last pair has no valid row), both operand kinds, and a wide
+    dynamic range across the right-hand-side columns (per-column fp16 scales)."""
+    from odf import ops
+    assert int(ops._lib.load().odf_tile_pair_eligible(n)) == 1
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=3)
+    C = X[torch.randperm(n, generator=torch.Generator().manual_seed(4))[:M]]
+    v = torch.randn(M, T, generator=torch.Generator().manual_seed(5)) * torch.logspace(-4, 4, T)[None, :]
+    k = odf.GaussianKernel(15.0, opt=odf.FalkonOptions(operand_kind=kind))
+    out = k.mmv(X.cuda(), C.cuda(), v.cuda()).double().cpu()
+    ref = orc.mmv(X, C, v, 15.0)
+    assert float(((out - ref).abs().max(0).values / ref.abs().max(0).values).max()) < 5e-5      # per column
+
+
+def test_recompute_sweep_with_pair_tile_in_both_passes(odf):
+    """sweep_mode="recompute" with >= 8192 centres: the second pass (rows = centres) also runs on the pair tile and
+    needs the fp16 form of W."""
+    n, M, d, T = 9000, 8200, 32, 5
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
+    C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
+    g = torch.Generator().manual_seed(8)
+    v, w = torch.randn(M, T, generator=g), torch.randn(n, T, generator=g)
+    for mode in ("recompute", "panel16"):
+        k = odf.GaussianKernel(15.0, opt=odf.FalkonOptions(sweep_mode=mode))
+        assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), w.cuda()), orc.dmmv(X, C, v, w, 15.0)) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
 @pytest.mark.parametrize("M,d,sigma", [(1000, 1024, 15.0), (333, 100, 5.0), (1500, 256, 50.0), (600, 2048, 5.0)])
 def test_kmm_matches_oracle(odf, M, d, sigma, kind):
     C, _, _ = orc.make_synthetic(M, d, 2, seed=9)

@@ -1,0 +1,218 @@
+"""Parity against golden vectors produced by RUNNING THE REFERENCE'S OWN first-party code
+(tests/golden/make_reference_golden.py: unmodified py_od_utils.py, FALKONWrapper_with_centers_selection_incore.py,
+MyCenterSelector.py, OnlineRegionClassifier_incore.py, region_refiner.py + trainer, executed on the CPU behind a
+`falkon` stub that computes with the oracle, a BoxList stub and a cuda->cpu device shim).
+
+CPU tests: the oracle's restatements and the product's torch-only helpers reproduce the reference's outputs (bit-exact
+where the work is indices / RNG draws / elementwise fp32, to rounding where it is fp64 linear algebra).
+GPU tests: the product modules (drop-in file names, CUDA path through the C ABI) reproduce them too.
+The third-party FALKON arithmetic itself is the oracle's in those fixtures — that part stays "parity unpinned"."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import falkon_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "reference_flow.npz"))
+META = json.load(open(os.path.join(HERE, "golden", "reference_flow.json")))
+CFG = META["cfg"]
+SEEDS = META["seeds"]
+T_CLS, N_BATCH = 3, 4
+
+
+def t(name):
+    return torch.from_numpy(G[name])
+
+
+def inputs():
+    positives = [t("in_pos%d" % i).clone() for i in range(T_CLS)]
+    negatives = [[t("in_neg%d_%d" % (i, j)).clone() for j in range(N_BATCH)] for i in range(T_CLS)]
+    return positives, negatives
+
+
+def cfg_file(tmp_path):
+    p = tmp_path / "cfg.yaml"
+    p.write_text(yaml.dump(CFG))
+    return str(p)
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------------------ CPU: oracle / host helpers
+def test_reference_called_falkon_the_way_the_product_assumes():
+    """What the reference handed to the third-party package (recorded by the stub): in-core flavour, maxiter 20, the
+    six FalkonOptions, y as a flat (N,) vector, M = number of selected centres (<= the configured budget)."""
+    calls = META["third_party_calls"]
+    ctors = [c for c in calls if "ctor" in c]
+    fits = [c for c in calls if "fit" in c]
+    assert len(ctors) == len(fits) == T_CLS * N_BATCH
+    for c in ctors:
+        assert c["ctor"] == "InCoreFalkon" and c["maxiter"] == 20 and c["sigma"] == 12.0 and c["penalty"] == 0.001
+        assert c["M"] <= 60 and c["extra"] == []
+        assert c["options"] == {"min_cuda_iter_size_32": 0, "min_cuda_iter_size_64": 0, "keops_active": "no",
+                                "min_cuda_pc_size_32": 0, "min_cuda_pc_size_64": 0, "store_kernel_d_threshold": 250}
+    for c, f in zip(ctors, fits):
+        assert f["y_shape"] == [f["fit"][0]] and f["centres"] == c["M"]
+
+
+def test_oracle_centre_selection_matches_reference_rng():
+    y = torch.cat((torch.ones(100), -torch.ones(400)))
+    torch.manual_seed(SEEDS["sel_many_pos"])
+    assert orc.compute_indices_selection(y, 60) == G["sel_many_pos"].tolist()
+    y2 = torch.cat((torch.ones(7), -torch.ones(400)))
+    torch.manual_seed(SEEDS["sel_few_pos"])
+    assert orc.compute_indices_selection(y2, 60) == G["sel_few_pos"].tolist()
+
+
+def test_product_wrapper_centre_selection_matches_reference_rng(tmp_path):
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    w = falkon.FALKONWrapper(cfg_file(tmp_path))
+    torch.manual_seed(SEEDS["sel_many_pos"])
+    assert w.compute_indices_selection(torch.cat((torch.ones(100), -torch.ones(400)))) == G["sel_many_pos"].tolist()
+    torch.manual_seed(SEEDS["sel_few_pos"])
+    assert w.compute_indices_selection(torch.cat((torch.ones(7), -torch.ones(400)))) == G["sel_few_pos"].tolist()
+
+
+def test_product_feature_statistics_and_normalisation_match_reference(monkeypatch):
+    import py_od_utils as UT
+    monkeypatch.setattr(UT, "_GPU", "cpu")          # the function ends in .to('cuda') like the reference's; no GPU here
+    positives, negatives = inputs()
+    torch.manual_seed(SEEDS["stats"])
+    stats = UT.computeFeatStatistics_torch(positives, negatives, num_samples=400, features_dim=24, cpu_tensor=True)
+    assert torch.equal(stats["mean"].cpu(), t("stats_mean"))
+    assert torch.equal(stats["std"].cpu(), t("stats_std"))
+    assert torch.equal(stats["mean_norm"].cpu().reshape(1), t("stats_mean_norm"))
+    stats_cpu = {k: v.cpu() for k, v in stats.items()}
+    COXY = {"C": t("in_reg_C").clone(), "O": None, "X": t("in_reg_X").clone(), "Y": t("in_reg_Y").clone()}
+    COXY = UT.normalize_COXY(COXY, stats_cpu, cpu=True)
+    assert torch.equal(COXY["X"], t("coxy_X_norm"))
+    # OnlineRegionClassifier.zScores == oracle zscores == what trainRegionClassifier left in positives[0]
+    z = orc.zscores(positives[0], t("stats_mean"), t("stats_mean_norm")[0])
+    assert torch.equal(z.float(), t("zscored_pos0"))
+
+
+def test_product_shuffle_and_positive_loading_match_reference_rng():
+    import py_od_utils as UT
+    _, negatives = inputs()
+    torch.manual_seed(SEEDS["shuffle"])
+    sh = UT.shuffle_negatives(negatives, batch_size=100, num_batches=3)
+    assert torch.equal(sh[0][0], t("shuffled_0_0")) and torch.equal(sh[2][2], t("shuffled_2_2"))
+    torch.manual_seed(SEEDS["positives_from_coxy"])
+    lp = UT.load_positives_from_COXY({"C": t("in_reg_C").clone(), "X": t("in_reg_X").clone()}, samples_fraction=0.5)
+    assert torch.equal(lp[1], t("coxy_pos_1"))
+
+
+def test_oracle_minibootstrap_reproduces_reference_loop():
+    """The reference's trainRegionClassifier (z-score, minibootstrap over 4 negative batches, 3 classes, its own RNG
+    stream for the centre draws) against the oracle's restatement of the loop: identical caches of surviving
+    negatives, identical centres, alpha equal to rounding (both sides solve with the oracle)."""
+    positives, negatives = inputs()
+    mean, mn = t("stats_mean"), t("stats_mean_norm")[0]
+    sigma, lam, M = 12.0, 0.001, 60
+    torch.manual_seed(SEEDS["minibootstrap"])
+
+    def train(Xc, y):
+        idx = orc.compute_indices_selection(y, M)
+        return (Xc[idx], orc.falkon_fit(Xc, y, Xc[idx], sigma, lam, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7))
+
+    def predict(model, Xq):
+        return orc.falkon_predict(Xq, model[0], model[1].float().double(), sigma).float()
+
+    for i in range(T_CLS):
+        pos = orc.zscores(positives[i], mean, mn).float()
+        neg = [orc.zscores(b, mean, mn).float() for b in negatives[i]]
+        model, cache = orc.minibootstrap(pos, neg, train, predict)
+        assert torch.equal(cache, t("cache%d_neg" % i))
+        assert torch.equal(model[0], t("model%d_centres" % i))
+        assert rel(model[1], t("model%d_alpha" % i)) < 1e-6
+
+
+def test_oracle_rls_matches_reference_trainer():
+    C = t("in_reg_C")[:, 0]
+    X = t("coxy_X_norm")
+    Y = t("in_reg_Y")
+    for i in range(T_CLS):
+        sel = C == (i + 1)
+        m = orc.rls_train_class(X[sel], Y[sel], CFG["REGION_REFINER"]["opts"]["lambda"])
+        W = torch.stack([m["Beta"][str(k)]["weights"] for k in range(4)], 1)
+        L = torch.stack([m["Beta"][str(k)]["losses"] for k in range(4)], 1)
+        assert rel(m["mu"], t("rls%d_mu" % i)) < 1e-6
+        assert rel(m["T"], t("rls%d_T" % i)) < 1e-5 and rel(m["T_inv"], t("rls%d_Tinv" % i)) < 1e-5
+        assert rel(W, t("rls%d_W" % i)) < 1e-5
+        assert float((L - t("rls%d_losses" % i)).abs().max()) < 1e-6
+
+
+def test_oracle_box_decode_matches_reference():
+    dec = orc.decode_boxes(G["in_test_boxes"], G["in_deltas"], 640, 480)
+    # fp32 with one exp per coordinate pair: numpy's and torch's expf may differ in the last bit (1 ulp at 640 = 6e-5)
+    assert float(np.abs(dec - G["decoded"]).max()) <= 1.3e-4
+    clipped = (G["decoded"] == 0) | (G["decoded"] == 639) | (G["decoded"] == 479)
+    assert np.array_equal(dec[clipped], G["decoded"][clipped])
+
+
+# ------------------------------------------------------------------------------------------ GPU: product modules
+@pytest.fixture(scope="module")
+def odf():
+    import odf as _odf
+    return _odf
+
+
+@pytest.mark.gpu
+def test_product_region_classifier_reproduces_reference_flow(odf, tmp_path):
+    """Drop-in OnlineRegionClassifier_incore + FALKONWrapper (CUDA fits through the C ABI) on the reference's inputs,
+    statistics and RNG seed: the same negatives survive the minibootstrap, the same centres are drawn, the test-time
+    score matrix matches within the 1e-3 parity bar."""
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    import OnlineRegionClassifier_incore as ocr
+    positives, negatives = inputs()
+    positives = [p.cuda() for p in positives]
+    negatives = [[b.cuda() for b in bs] for bs in negatives]
+    stats = {"mean": t("stats_mean").cuda(), "std": t("stats_std").cuda(), "mean_norm": t("stats_mean_norm")[0].cuda()}
+    cfg = cfg_file(tmp_path)
+    torch.manual_seed(SEEDS["minibootstrap"])
+    clf = falkon.FALKONWrapper(cfg)
+    rc = ocr.OnlineRegionClassifier(clf, positives, negatives, stats, cfg_path=cfg)
+    models, caches = rc.trainRegionClassifier(opts={"return_caches": True})
+    assert len(models) == T_CLS
+    for i in range(T_CLS):
+        assert torch.equal(caches[i]["neg"].cpu(), t("cache%d_neg" % i))          # same hard / easy decisions
+        assert torch.equal(models[i].ny_points_.cpu(), t("model%d_centres" % i))  # same centre draws
+        assert models[i].M == G["model%d_centres" % i].shape[0]
+    assert torch.equal(positives[0].cpu(), t("zscored_pos0"))                      # z-scored in place, like the reference
+    test = [{"boxes": G["in_test_boxes"], "feat": G["in_test_feat"], "gt": np.zeros(len(G["in_test_boxes"])),
+             "img_size": (640, 480)}]
+    preds = rc.testRegionClassifier(models, test)
+    scores = preds[0].get_field("scores")
+    ref = t("test_scores")
+    assert scores.shape == ref.shape and torch.equal(scores[:, 0].cpu(), ref[:, 0])   # background column = -1
+    assert rel(scores, ref) < 1e-3
+    assert torch.equal(scores[:, 1:].argmax(1).cpu(), ref[:, 1:].argmax(1))
+
+
+@pytest.mark.gpu
+def test_product_region_refiner_matches_reference_trainer(odf, tmp_path):
+    from region_refiner import RegionRefiner
+    COXY = {"C": t("in_reg_C").cuda(), "O": None, "X": t("coxy_X_norm").cuda(), "Y": t("in_reg_Y").cuda()}
+    models = RegionRefiner(cfg_file(tmp_path)).trainRegionRefiner(COXY)
+    assert len(models) == T_CLS
+    for i, m in enumerate(models):
+        W = torch.stack([m["Beta"][str(k)]["weights"] for k in range(4)], 1)
+        assert rel(m["mu"], t("rls%d_mu" % i)) < 1e-6 and rel(m["T"], t("rls%d_T" % i)) < 1e-5
+        assert rel(m["T_inv"], t("rls%d_Tinv" % i)) < 1e-5 and rel(W, t("rls%d_W" % i)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_product_box_decode_matches_reference(odf):
+    import py_od_utils as UT
+    from boxlist import BoxList
+    bl = BoxList(t("in_test_boxes").cuda(), (640, 480), mode="xyxy")
+    dec = UT.decode_boxes_detector(bl, t("in_deltas").cuda())
+    assert float((dec.cpu() - t("decoded")).abs().max()) <= 1.3e-4        # expf: last-bit differences only
