@@ -7,6 +7,7 @@ three absent third-party packages and a hard-coded "cuda" device.  This script i
     src/modules/region-classifier/FALKONWrapper_with_centers_selection_incore.py   (+ MyCenterSelector.py)
     src/modules/region-classifier/OnlineRegionClassifier_incore.py
     src/modules/region-refiner/region_refiner.py  (+ region_refiner_trainer/, region_predictor/)
+    src/modules/feature-extractor/mrcnn_modified/modeling/roi_heads/box_head/roi_box_predictors.py   (inference head)
 
 behind three shims that are defined below and nowhere else:
 
@@ -270,6 +271,37 @@ def main():
             out["rls%d_W" % i] = torch.stack([m["Beta"][str(k)]["weights"] for k in range(4)], 1)
             out["rls%d_losses" % i] = torch.stack([m["Beta"][str(k)]["losses"] for k in range(4)], 1)
 
+        # a10/a11 + RLS apply: the inference head that consumes the models, roi_box_predictors.py:32-160, loaded from its
+        # file with a registry stub (mrcnn_modified/modeling/registry.py only wraps maskrcnn_benchmark's Registry)
+        import importlib.util
+
+        class _Reg:
+            def register(self, name):
+                return lambda cls: cls
+        for name in ("mrcnn_modified", "mrcnn_modified.modeling"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        regmod = types.ModuleType("mrcnn_modified.modeling.registry")
+        regmod.ROI_BOX_PREDICTOR = _Reg()
+        sys.modules["mrcnn_modified.modeling.registry"] = regmod
+        sys.modules["mrcnn_modified.modeling"].registry = regmod
+        head_py = os.path.join(src, "modules", "feature-extractor", "mrcnn_modified", "modeling", "roi_heads", "box_head",
+                               "roi_box_predictors.py")
+        spec = importlib.util.spec_from_file_location("ref_roi_box_predictors", head_py)
+        head_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(head_mod)
+        ns = types.SimpleNamespace
+        for parallel in (True, False):
+            hcfg = ns(MODEL=ns(ROI_BOX_HEAD=ns(NUM_CLASSES=4), CLS_AGNOSTIC_BBOX_REG=False), INFERENCE=ns(PARALLEL_FALKON=parallel))
+            torch.manual_seed(0)
+            head = head_mod.FastRCNNPredictor(hcfg, 24)
+            head.classifiers = [models[0], None, models[2]] if not parallel else list(models)
+            head.regressors = reg
+            head.stats = {"mean": stats["mean"], "mean_norm": stats["mean_norm"]}
+            head.feat_size = 24
+            scores_h, bbox_h = head(inp["test_feat"].clone().reshape(-1, 24, 1, 1))
+            tag = "par" if parallel else "seq"
+            out["head_scores_" + tag], out["head_bbox_" + tag] = scores_h, bbox_h
+
         # box decode with the +1 convention, py_od_utils.py:247-274
         bl = BoxList(inp["test_boxes"], (640, 480))
         out["decoded"] = UT.decode_boxes_detector(bl, inp["deltas"].clone())
@@ -300,7 +332,8 @@ def main():
                                        "src/modules/region-classifier/MyCenterSelector.py",
                                        "src/modules/region-classifier/OnlineRegionClassifier_incore.py",
                                        "src/modules/region-refiner/region_refiner.py",
-                                       "src/modules/region-refiner/region_refiner_trainer/train_region_refiner.py"],
+                                       "src/modules/region-refiner/region_refiner_trainer/train_region_refiner.py",
+                                       "src/modules/feature-extractor/mrcnn_modified/modeling/roi_heads/box_head/roi_box_predictors.py"],
                    "seeds": {"stats": 11, "sel_many_pos": 5, "sel_few_pos": 6, "minibootstrap": 12, "shuffle": 21,
                              "positives_from_coxy": 22},
                    "torch": torch.__version__}, f, indent=1)

@@ -198,6 +198,62 @@ def test_product_region_classifier_reproduces_reference_flow(odf, tmp_path):
 
 
 @pytest.mark.gpu
+def test_product_models_in_the_reference_inference_head(odf, tmp_path):
+    """The reference's RoI box head (roi_box_predictors.py:32-160) ran in the golden script with the reference-flow models;
+    here the SAME call sequence runs on the product's model objects and regressors: the duck type the head relies on
+    (`.M`, `.alpha_`, `.ny_points_`, `.kernel.mmv(features, nystrom_parallel, alpha_parallel)`, `.predict`, truthiness,
+    None entries scoring -2) and the RLS apply `x W blockdiag(T_inv) + mu`."""
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    import OnlineRegionClassifier_incore as ocr
+    from region_refiner import RegionRefiner
+    positives, negatives = inputs()
+    stats = {"mean": t("stats_mean").cuda(), "std": t("stats_std").cuda(), "mean_norm": t("stats_mean_norm")[0].cuda()}
+    cfg = cfg_file(tmp_path)
+    torch.manual_seed(SEEDS["minibootstrap"])
+    clf = falkon.FALKONWrapper(cfg)
+    rc = ocr.OnlineRegionClassifier(clf, [p.cuda() for p in positives], [[b.cuda() for b in bs] for bs in negatives], stats,
+                                    cfg_path=cfg)
+    classifiers = rc.trainRegionClassifier()
+    COXY = {"C": t("in_reg_C").cuda(), "O": None, "X": t("coxy_X_norm").cuda(), "Y": t("in_reg_Y").cuda()}
+    regressors = RegionRefiner(cfg).trainRegionRefiner(COXY)
+    x_raw = t("in_test_feat").cuda()
+
+    # refine_boxes_parallel (:97-124), on the un-normalised features as the head does by default
+    W = torch.zeros((x_raw.shape[1] + 1, 4), device="cuda")
+    Tinv = torch.zeros(((len(regressors) + 1) * 4,) * 2, device="cuda")
+    mu = torch.zeros((1, 4), device="cuda")
+    for j, r in enumerate(regressors):
+        wj = torch.stack([r["Beta"][str(k)]["weights"] for k in range(4)], 0)
+        Tinv[(j + 1) * 4:(j + 2) * 4, (j + 1) * 4:(j + 2) * 4] = r["T_inv"]
+        mu = torch.cat((mu, r["mu"].view(1, 4)), 1)
+        W = torch.cat((W, wj.t()), 1)
+    bbox = (x_raw @ W[:-1] + W[-1]) @ Tinv + mu
+    assert rel(bbox, t("head_bbox_par")) < 1e-4
+
+    x = (x_raw - stats["mean"]) * (20 / stats["mean_norm"])                 # forward(): :47-50
+    # predict_clss_FALKON_parallel (:140-160)
+    assert all(bool(c) for c in classifiers)
+    total = sum(c.M for c in classifiers)
+    alpha_parallel = torch.zeros((total, len(classifiers)), device="cuda")
+    row = 0
+    for i, c in enumerate(classifiers):
+        alpha_parallel[row:row + c.M, i] = c.alpha_.squeeze()
+        row += c.M
+    nystrom_parallel = torch.cat([c.ny_points_ for c in classifiers])
+    scores = classifiers[0].kernel.mmv(x, nystrom_parallel, alpha_parallel)
+    scores = torch.cat((torch.full((x.shape[0], 1), -2.0, device="cuda"), scores), 1)
+    ref = t("head_scores_par")
+    assert scores.shape == ref.shape and rel(scores, ref) < 1e-3
+    assert torch.equal(scores.argmax(1).cpu(), ref.argmax(1))
+    # predict_clss_FALKON (:127-138) with a missing classifier
+    seq = torch.full((x.shape[0], 1), -2.0, device="cuda")
+    for c in (classifiers[0], None, classifiers[2]):
+        seq = torch.cat((seq, torch.full((x.shape[0], 1), -2.0, device="cuda") if c is None else c.predict(x)), 1)
+    ref = t("head_scores_seq")
+    assert torch.equal(seq[:, 2].cpu(), ref[:, 2]) and rel(seq, ref) < 1e-3
+
+
+@pytest.mark.gpu
 def test_product_region_refiner_matches_reference_trainer(odf, tmp_path):
     from region_refiner import RegionRefiner
     COXY = {"C": t("in_reg_C").cuda(), "O": None, "X": t("coxy_X_norm").cuda(), "Y": t("in_reg_Y").cuda()}
