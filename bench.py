@@ -334,9 +334,10 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         def e2e_step():
-            Xd.copy_(Xh, non_blocking=True)
-            Yd.copy_(Yh, non_blocking=True)
-            m = one_fit()
+            # the public call with HOST (pinned) buffers: fit() uploads X, Y on a side stream while it prepares the
+            # centres and builds the preconditioner, then reads them from HBM
+            m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=group)
+            m.fit(Xh, Yh, centres=centres, zscore=(mean, scale))
             return m.alpha_.cpu()                    # device -> host read of the result
         e2e_step()
         sync_all()

@@ -89,8 +89,9 @@ class FALKONWrapperBase(ca.ClassifierAbstract):
         src_device = X.device
         if not self.IN_CORE and not X.is_cuda:
             # out-of-core flavour: features are parked in host RAM, the iterations still run on
-            # the GPU (min_cuda_iter_size_* = 0 upstream) — stage them through HBM for the fit
-            self.model.fit(X.cuda(), y.cuda())
+            # the GPU (min_cuda_iter_size_* = 0 upstream) — fit() uploads them on a side stream while
+            # the centres are prepared and the preconditioner is built
+            self.model.fit(X, y)
             self.model.ny_points_ = self.model.ny_points_.to(src_device)
             self.model.alpha_ = self.model.alpha_.to(src_device)
         else:

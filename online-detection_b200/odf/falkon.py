@@ -221,15 +221,43 @@ class Falkon:
         """X (N x d) fp32 on the GPU [this rank's rows], Y (N,) or (N x T).  `centres` (M x d)
         overrides center_selection (rank 0's choice is broadcast in the row-sharded mode).
         `zscore=(mean, scale)` fuses OnlineRegionClassifier.zScores into the operand pre-pass:
-        X and the centres are taken as RAW features and (x - mean) * scale is applied on the fly."""
+        X and the centres are taken as RAW features and (x - mean) * scale is applied on the fly.
+
+        X / Y may also live in HOST memory (the reference's `--CPU` flavour parks the features there,
+        OnlineRegionClassifier.py:108-117): they are uploaded on a side stream while the main stream prepares the
+        centres and builds the preconditioner, which need only the centres — with pinned buffers the
+        host-to-device copy of a C2-sized shard (4.2 GB, ~75 ms) disappears behind the ~80 ms preconditioner."""
         be = self._be
         if Y.dim() == 1:
             Y = Y[:, None]
-        Y = Y.to(torch.float32)
         dist, world = _dist_info(self.process_group)
         group = None if self.process_group in (None, False) else self.process_group
-        dev = X.device
         opt = self.options
+        upload = None
+        if X.device.type == "cpu" and torch.cuda.is_available() and getattr(be, "__name__", "") == ops.__name__:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            if centres is None:
+                if self.center_selection is None:
+                    g = torch.Generator().manual_seed(0 if self.seed is None else int(self.seed))
+                    centres = X[torch.randperm(X.shape[0], generator=g)[:self.M]]
+                else:
+                    centres = self.center_selection.select(X, None)
+            centres = centres.to(dev)
+            main = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            Xd = torch.empty(X.shape, dtype=torch.float32, device=dev)
+            Yd = torch.empty(Y.shape, dtype=torch.float32, device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                Xd.copy_(X, non_blocking=True)
+                Yd.copy_(Y, non_blocking=True)
+                upload = torch.cuda.Event()
+                upload.record(side)
+            Xd.record_stream(side)
+            Yd.record_stream(side)
+            X, Y = Xd, Yd
+        Y = Y.to(torch.float32)
+        dev = X.device
         tm = _Timer(dev)
         tm.mark()
 
@@ -263,13 +291,18 @@ class Falkon:
         kind = opt.operand_kind
         zs = zs if zs else (None, 1.0)
         pc = be.Prepared(centres, zs[0], zs[1], kind=kind)
-        px = be.Prepared(X, zs[0], zs[1], kind=kind) if n_local > 0 else None
+        px = None
+        if upload is None:
+            px = be.Prepared(X, zs[0], zs[1], kind=kind) if n_local > 0 else None
         if zscore is not None:
             centres = be.zscore_(centres.clone(), zs[0], zs[1])     # ny_points_ live in normalised space
         tm.mark()
 
         # ---- preconditioner (built once per fit; the factors end up replicated on every rank) ----
         Tm, Am = self._build_preconditioner(be, pc, sigma, lam, dist if world > 1 else None, group, world)
+        if upload is not None:
+            torch.cuda.current_stream(dev).wait_event(upload)        # the rows have arrived by now
+            px = be.Prepared(X, zs[0], zs[1], kind=kind) if n_local > 0 else None
         tm.mark()
 
         alpha = torch.empty((M, T), dtype=torch.float32, device=dev)

@@ -247,6 +247,24 @@ def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
         assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), None), orc.dmmv(X, C, v, None, 15.0)) < 1e-4
 
 
+def test_fit_from_host_memory_matches_device_fit(odf):
+    """fit() with X / Y in (pinned or pageable) host memory uploads them on a side stream behind the preconditioner
+    build: same arithmetic, so alpha is bitwise the device fit's."""
+    X, c, Y = orc.make_synthetic(9000, 128, 3, seed=2)
+    C = X[orc.shared_centres(c, 300, seed=1)]
+    base = _gpu_fit(odf, X, Y, C, 15.0, 1e-4)
+    for Xh, Yh in ((X.pin_memory(), Y.pin_memory()), (X, Y)):
+        m = odf.InCoreFalkon(kernel=odf.GaussianKernel(15.0), penalty=1e-4, M=300)
+        m.fit(Xh, Yh, centres=C.cuda())
+        assert m.alpha_.is_cuda and torch.equal(m.alpha_, base.alpha_)
+    # centre selection on host rows (center_selection.select sees the host tensor)
+    from MyCenterSelector import MyCenterSelector
+    idx = orc.shared_centres(c, 300, seed=1).tolist()
+    m = odf.InCoreFalkon(kernel=odf.GaussianKernel(15.0), penalty=1e-4, M=300, center_selection=MyCenterSelector(idx))
+    m.fit(X, Y)
+    assert torch.equal(m.alpha_, base.alpha_) and m.ny_points_.is_cuda
+
+
 def test_recompute_and_trsm_options_agree_with_default(odf):
     X, c, Y = orc.make_synthetic(5000, 128, 3, seed=2)
     C = X[orc.shared_centres(c, 300, seed=1)]
