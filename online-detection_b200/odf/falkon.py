@@ -17,6 +17,7 @@ group, in which case each application of K_nm^T(K_nm .) ends in one all-reduce o
 partial (NCCL over NVLink on a B200 box, gloo in CPU tests of the host logic).
 """
 import math
+import os
 
 import torch
 
@@ -123,6 +124,25 @@ def _dist_info(group):
     if group is False:
         return None, 1
     return dist, dist.get_world_size(group)
+
+
+class _SegTimer:
+    """ODF_PRECOND_PROFILE=1: CUDA-event timing of the segments of the distributed preconditioner build (rank 0)."""
+
+    def __init__(self, dev):
+        self.dev, self.ev, self.names = dev, [torch.cuda.Event(enable_timing=True)], []
+        self.ev[0].record()
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.ev.append(e)
+        self.names.append(name)
+
+    def report(self):
+        torch.cuda.synchronize(self.dev)
+        print("precond segments (ms): " + "  ".join("%s %.2f" % (n, a.elapsed_time(b))
+                                                     for n, a, b in zip(self.names, self.ev[:-1], self.ev[1:])), flush=True)
 
 
 class _Timer:
@@ -330,45 +350,64 @@ class Falkon:
         serial fraction of the multi-GPU fit shrinks with the world size.  Every rank ends with bitwise
         identical factors (each block is computed once and broadcast by the gather)."""
         opt = self.options
+        prof0 = _SegTimer(pc.hi.device) if os.environ.get("ODF_PRECOND_PROFILE") and pc.hi.is_cuda else None
         Kmm = be.kmm(pc, sigma)
+        if prof0:
+            prof0.mark("kmm")
+            prof0.report()
         M = Kmm.shape[0]
         want = getattr(opt, "distributed_precond", None)
         want = (world >= 4) if want is None else bool(want)
         split = dist is not None and world > 1 and want and M >= 4 * world and hasattr(be, "potrf_upper_")
         if not split:
+            prof = _SegTimer(Kmm.device) if os.environ.get("ODF_PRECOND_PROFILE") and Kmm.is_cuda else None
+            if prof: prof.mark("kmm (since previous mark)")
             Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
+            if prof: prof.mark("precond_init")
             if opt.precond_apply == "inverse":
-                return _InvFactor(be, Tm), _InvFactor(be, Am)
+                fT = _InvFactor(be, Tm)
+                if prof: prof.mark("invert T")
+                fA = _InvFactor(be, Am)
+                if prof: prof.mark("invert A"); prof.report()
+                return fT, fA
             return _TriFactor(be, Tm), _TriFactor(be, Am)
         rank = dist.get_rank(group)
         dev, dt = Kmm.device, Kmm.dtype
         Mc = -(-M // world)
         Mc = -(-Mc // 4) * 4                                  # equal, 16-byte aligned blocks (the last may be short)
         c0, c1 = min(M, rank * Mc), min(M, (rank + 1) * Mc)
+        prof = _SegTimer(dev) if os.environ.get("ODF_PRECOND_PROFILE") and rank == 0 else None
 
-        def gather_columns(block):                            # block: (M x Mc), my columns first
+        def gather_columns(block, out=None):                  # block: (M x Mc), my columns first
             flat = torch.empty((world * M, Mc), dtype=dt, device=dev)
             dist.all_gather_into_tensor(flat, block.contiguous(), group=group)
             parts = flat.view(world, M, Mc)
-            full = torch.empty((M, M), dtype=dt, device=dev)
-            for r in range(world):
-                a, b = min(M, r * Mc), min(M, (r + 1) * Mc)
-                if b > a:
-                    full[:, a:b].copy_(parts[r, :, :b - a])
+            full = torch.empty((M, M), dtype=dt, device=dev) if out is None else out
+            if world * Mc == M:
+                full.view(M, world, Mc).copy_(parts.permute(1, 0, 2))          # one strided copy
+            else:
+                for r in range(world):
+                    a, b = min(M, r * Mc), min(M, (r + 1) * Mc)
+                    if b > a:
+                        full[:, a:b].copy_(parts[r, :, :b - a])
             return full
 
         be.add_diag_(Kmm, opt.pc_epsilon_32 * M)
         Tri_T = be.potrf_upper_(Kmm)                          # replicated
+        if prof: prof.mark("kmm+potrf(T)")
         # my columns of T T^T: (T T^T)[:, c0:c1] = T . (T[c0:c1, :])^T
         rows_t = torch.zeros((M, Mc), dtype=dt, device=dev)
         if c1 > c0:
             rows_t[:, :c1 - c0].copy_(Tri_T[c0:c1, :].t())
         G = torch.empty_like(rows_t)
         be.precond_apply(Tri_T, rows_t, G, False)
+        if prof: prof.mark("T T^T block")
         A0 = gather_columns(G)
         be.axpby(A0, 1.0 / M, A0)
         be.add_diag_(A0, lam)
+        if prof: prof.mark("gather A")
         Tri_A = be.potrf_upper_(A0)                           # replicated
+        if prof: prof.mark("potrf(A)")
         if opt.precond_apply != "inverse":
             return _TriFactor(be, Tri_T), _TriFactor(be, Tri_A)
         factors = []
@@ -377,9 +416,12 @@ class Falkon:
             if c1 > c0:
                 E[c0:c1, :c1 - c0].fill_diagonal_(1.0)
             be.precond_solve_(Tri, E, SOLVE_T)                # Tri^-1 I[:, c0:c1]
+            if prof: prof.mark("trsm block")
             Inv = gather_columns(E)
             be.zero_lower_(Inv)
+            if prof: prof.mark("gather inverse")
             factors.append(_InvFactor(be, Tri, Inv))
+        if prof: prof.report()
         return factors[0], factors[1]
 
     def _solve_block(self, px, pc, Yb, Tm, Am, N, sigma, lam, alpha_out, dist, group):
