@@ -186,6 +186,11 @@ int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t 
 int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream);
 int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T,
                       int64_t ldb, int transposed, void* stream);
+/* Rows [r0, r1) of the same product for an UPPER-triangular Inv (reads only its non-zero part): Bout_rows is
+ * (r1 - r0) x T with pitch ldo.  Used by the row-sharded fit: one row block per rank, then an all-gather.      */
+int odf_precond_apply_rows(const float* Inv, int64_t M, int64_t r0, int64_t r1, const float* Bin,
+                           float* Bout_rows, int64_t T, int64_t ldb, int64_t ldo, int transposed,
+                           void* stream);
 
 /* ---- conjugate-gradient vector kernels on M x T blocks (per-column scalars) ------------------ */
 /* FalkonConjugateGradient / ConjugateGradient.solve.  `state` is a device

@@ -531,6 +531,20 @@ int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream) {
   return zero_lower(Inv, M, st);      // exact zeros below the diagonal (scratch blocks and TRSM rounding dust)
 }
 
+// Rows [r0, r1) of op(Inv) Bin for an UPPER-triangular Inv: only the non-zero part of the operand is read
+// (plain: columns >= r0; transposed: rows < r1).  The row-sharded fit gives every rank one row block and all-gathers.
+int odf_precond_apply_rows(const float* Inv, int64_t M, int64_t r0, int64_t r1, const float* Bin, float* Bout_rows,
+                           int64_t T, int64_t ldb, int64_t ldo, int transposed, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = ensure_handles(st))) return rc;
+  if (r0 < 0 || r1 > M || r0 >= r1 || T <= 0 || ldb < T || ldo < T) return set_error(ODF_ERR_ARG, "precond_apply_rows: bad shape");
+  if (!transposed)        // Inv[r0:r1, r0:M] . Bin[r0:M, :]
+    return gemm_rm(false, false, r1 - r0, T, M - r0, 1.f, Inv + r0 * M + r0, M, Bin + r0 * ldb, ldb, 0.f, Bout_rows, ldo);
+  // Inv[0:r1, r0:r1]^T . Bin[0:r1, :]
+  return gemm_rm(true, false, r1 - r0, T, r1, 1.f, Inv + r0, M, Bin, ldb, 0.f, Bout_rows, ldo);
+}
+
 int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T, int64_t ldb,
                       int transposed, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -51,6 +51,8 @@ class FalkonOptions:
         # multi-GPU fits split T T^T and the explicit inverses over the ranks as column blocks (all-gathered); below
         # 4 ranks the replicated triangle-aware build is as fast and skips the M x M gathers.  None = by world size.
         self.distributed_precond = ignored.pop("distributed_precond", None)
+        # multi-GPU fits: every rank applies one row block of the explicit inverses per CG step and all-gathers
+        self.distributed_apply = ignored.pop("distributed_apply", True)
         self.ignored = dict(ignored)
 
 
@@ -184,12 +186,32 @@ class _TriFactor:
 class _InvFactor:
     """Upper-triangular factor applied through its explicit inverse (one GEMM per application)."""
 
-    def __init__(self, be, Tri, Inv=None):
+    def __init__(self, be, Tri, Inv=None, shard=None):
         self.be = be
         self.Inv = be.precond_invert(Tri) if Inv is None else Inv
+        # shard = (dist, group, world, rank): every rank applies one row block of the inverse (only its non-zero
+        # part is read) and the blocks are all-gathered -- the M^2 T product is no longer replicated per iteration.
+        # Each block is computed once and gathered, so the ranks still hold bitwise identical vectors.
+        self.shard = shard if (shard is not None and hasattr(be, "precond_apply_rows")) else None
+        self._bufs = {}
 
     def solve(self, b, out, transposed):
-        return self.be.precond_apply(self.Inv, b, out, transposed)
+        if self.shard is None:
+            return self.be.precond_apply(self.Inv, b, out, transposed)
+        dist, group, world, rank = self.shard
+        M, T = b.shape
+        Mc = -(-M // world)
+        key = (T, b.dtype, b.device)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.zeros((Mc, T), dtype=b.dtype, device=b.device),
+                               torch.empty((world * Mc, T), dtype=b.dtype, device=b.device))
+        mine, full = self._bufs[key]
+        r0, r1 = min(M, rank * Mc), min(M, (rank + 1) * Mc)
+        if r1 > r0:
+            self.be.precond_apply_rows(self.Inv, r0, r1, b, mine, transposed)
+        dist.all_gather_into_tensor(full, mine, group=group)
+        out.copy_(full[:M])
+        return out
 
 
 class Falkon:
@@ -356,6 +378,9 @@ class Falkon:
             prof0.mark("kmm")
             prof0.report()
         M = Kmm.shape[0]
+        shard = None
+        if dist is not None and world > 1 and getattr(opt, "distributed_apply", True) and M >= 4 * world:
+            shard = (dist, group, world, dist.get_rank(group))
         want = getattr(opt, "distributed_precond", None)
         want = (world >= 4) if want is None else bool(want)
         split = dist is not None and world > 1 and want and M >= 4 * world and hasattr(be, "potrf_upper_")
@@ -365,9 +390,9 @@ class Falkon:
             Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
             if prof: prof.mark("precond_init")
             if opt.precond_apply == "inverse":
-                fT = _InvFactor(be, Tm)
+                fT = _InvFactor(be, Tm, shard=shard)
                 if prof: prof.mark("invert T")
-                fA = _InvFactor(be, Am)
+                fA = _InvFactor(be, Am, shard=shard)
                 if prof: prof.mark("invert A"); prof.report()
                 return fT, fA
             return _TriFactor(be, Tm), _TriFactor(be, Am)
@@ -420,7 +445,7 @@ class Falkon:
             Inv = gather_columns(E)
             be.zero_lower_(Inv)
             if prof: prof.mark("gather inverse")
-            factors.append(_InvFactor(be, Tri, Inv))
+            factors.append(_InvFactor(be, Tri, Inv, shard=shard))
         if prof: prof.report()
         return factors[0], factors[1]
 

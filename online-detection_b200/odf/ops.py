@@ -371,6 +371,16 @@ def precond_apply(Inv, Bin, Bout, transposed):
     return Bout
 
 
+def precond_apply_rows(Inv, r0, r1, Bin, Bout_rows, transposed):
+    """Bout_rows = (op(Inv) @ Bin)[r0:r1] for an upper-triangular Inv (row block of the distributed application)."""
+    L = _lib.load()
+    assert Bin.stride(1) == 1 and Bout_rows.stride(1) == 1 and Bout_rows.shape[0] >= r1 - r0
+    check(L.odf_precond_apply_rows(ptr(Inv), Inv.shape[0], int(r0), int(r1), ptr(Bin), ptr(Bout_rows), Bin.shape[1],
+                                   Bin.stride(0), Bout_rows.stride(0), 1 if transposed else 0, _stream()),
+          "odf_precond_apply_rows")
+    return Bout_rows
+
+
 # ---- CG vector kernels ------------------------------------------------------------------------
 class CgState:
     def __init__(self, M, T, device):

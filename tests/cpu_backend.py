@@ -61,6 +61,12 @@ def precond_apply(Inv, Bin, Bout, transposed):
     return Bout
 
 
+def precond_apply_rows(Inv, r0, r1, Bin, Bout_rows, transposed):
+    full = (Inv.T if transposed else Inv) @ Bin.to(Inv.dtype)
+    Bout_rows[:r1 - r0].copy_(full[r0:r1].to(Bout_rows.dtype))
+    return Bout_rows
+
+
 class Sweeper:
     def __init__(self, rows, cols, sigma, T, mode="panel"):
         self.rows, self.cols, self.sigma, self.T = rows, cols, sigma, T
