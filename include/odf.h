@@ -186,6 +186,10 @@ int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t 
 int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream);
 int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T,
                       int64_t ldb, int transposed, void* stream);
+/* Row-major fp32 GEMM on sub-blocks, C (m x n) = alpha op(A) op(B) + beta C (cuBLAS sgemm, true fp32): used by the
+ * row-sharded fit for its column block of T T^T (only the non-zero ranges of the triangular factor are multiplied). */
+int odf_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, float alpha, const float* A,
+             int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* stream);
 /* Rows [r0, r1) of the same product for an UPPER-triangular Inv (reads only its non-zero part): Bout_rows is
  * (r1 - r0) x T with pitch ldo.  Used by the row-sharded fit: one row block per rank, then an all-gather.      */
 int odf_precond_apply_rows(const float* Inv, int64_t M, int64_t r0, int64_t r1, const float* Bin,

@@ -531,6 +531,16 @@ int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream) {
   return zero_lower(Inv, M, st);      // exact zeros below the diagonal (scratch blocks and TRSM rounding dust)
 }
 
+// Plain row-major fp32 GEMM C (m x n) = alpha op(A) op(B) + beta C on sub-blocks (pitches lda / ldb / ldc): the
+// building block of the distributed preconditioner (triangle-aware column blocks of T T^T).
+int odf_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
+             const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* stream) {
+  int rc;
+  if ((rc = ensure_handles(static_cast<cudaStream_t>(stream)))) return rc;
+  if (m <= 0 || n <= 0 || k <= 0) return set_error(ODF_ERR_ARG, "odf_gemm: empty product");
+  return gemm_rm(trans_a != 0, trans_b != 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
 // Rows [r0, r1) of op(Inv) Bin for an UPPER-triangular Inv: only the non-zero part of the operand is read
 // (plain: columns >= r0; transposed: rows < r1).  The row-sharded fit gives every rank one row block and all-gathers.
 int odf_precond_apply_rows(const float* Inv, int64_t M, int64_t r0, int64_t r1, const float* Bin, float* Bout_rows,

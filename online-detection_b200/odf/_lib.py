@@ -56,6 +56,7 @@ SIGNATURES = {
     "odf_precond_solve": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_fp]),
     "odf_precond_invert": (c_int, [c_fp, c_fp, c_i64, c_fp]),
     "odf_precond_apply": (c_int, [c_fp, c_i64, c_fp, c_fp, c_i64, c_i64, c_int, c_fp]),
+    "odf_gemm": (c_int, [c_int, c_int, c_i64, c_i64, c_i64, c_f, c_fp, c_i64, c_fp, c_i64, c_f, c_fp, c_i64, c_fp]),
     "odf_precond_apply_rows": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_i64, c_i64, c_i64, c_int, c_fp]),
     "odf_cg_init": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_sz, c_fp]),
     "odf_cg_alpha": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_sz, c_fp]),

@@ -403,11 +403,12 @@ class Falkon:
         c0, c1 = min(M, rank * Mc), min(M, (rank + 1) * Mc)
         prof = _SegTimer(dev) if os.environ.get("ODF_PRECOND_PROFILE") and rank == 0 else None
 
-        def gather_columns(block, out=None):                  # block: (M x Mc), my columns first
-            flat = torch.empty((world * M, Mc), dtype=dt, device=dev)
+        flat = torch.empty((world * M, Mc), dtype=dt, device=dev)       # one gather buffer for the three gathers
+
+        def gather_columns(block):                            # block: (M x Mc), my columns first
             dist.all_gather_into_tensor(flat, block.contiguous(), group=group)
             parts = flat.view(world, M, Mc)
-            full = torch.empty((M, M), dtype=dt, device=dev) if out is None else out
+            full = torch.empty((M, M), dtype=dt, device=dev)
             if world * Mc == M:
                 full.view(M, world, Mc).copy_(parts.permute(1, 0, 2))          # one strided copy
             else:
@@ -420,12 +421,16 @@ class Falkon:
         be.add_diag_(Kmm, opt.pc_epsilon_32 * M)
         Tri_T = be.potrf_upper_(Kmm)                          # replicated
         if prof: prof.mark("kmm+potrf(T)")
-        # my columns of T T^T: (T T^T)[:, c0:c1] = T . (T[c0:c1, :])^T
-        rows_t = torch.zeros((M, Mc), dtype=dt, device=dev)
+        # my columns of the UPPER triangle of T T^T: rows 0..c1 of (T T^T)[:, c0:c1] = T[0:c1, c0:] . (T[c0:c1, c0:])^T
+        # (T[c0:c1, k] = 0 for k < c0; rows below c1 belong to the lower triangle, which potrf never reads)
+        G = torch.zeros((M, Mc), dtype=dt, device=dev)
         if c1 > c0:
-            rows_t[:, :c1 - c0].copy_(Tri_T[c0:c1, :].t())
-        G = torch.empty_like(rows_t)
-        be.precond_apply(Tri_T, rows_t, G, False)
+            if hasattr(be, "gemm"):
+                be.gemm(Tri_T[0:c1, c0:], Tri_T[c0:c1, c0:], G[0:c1, :c1 - c0], trans_b=True)
+            else:
+                rows_t = torch.zeros((M, Mc), dtype=dt, device=dev)
+                rows_t[:, :c1 - c0].copy_(Tri_T[c0:c1, :].t())
+                be.precond_apply(Tri_T, rows_t, G, False)
         if prof: prof.mark("T T^T block")
         A0 = gather_columns(G)
         be.axpby(A0, 1.0 / M, A0)

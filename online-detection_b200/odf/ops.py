@@ -371,6 +371,19 @@ def precond_apply(Inv, Bin, Bout, transposed):
     return Bout
 
 
+def gemm(A, B, C, trans_a=False, trans_b=False, alpha=1.0, beta=0.0):
+    """C = alpha op(A) op(B) + beta C on (possibly strided-row) fp32 views; true-fp32 cuBLAS sgemm."""
+    L = _lib.load()
+    assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
+    m, n = C.shape
+    k = A.shape[0] if trans_a else A.shape[1]
+    assert (A.shape[1] if trans_a else A.shape[0]) == m and (B.shape[0] if trans_b else B.shape[1]) == n
+    assert (B.shape[1] if trans_b else B.shape[0]) == k
+    check(L.odf_gemm(1 if trans_a else 0, 1 if trans_b else 0, m, n, k, float(alpha), ptr(A), A.stride(0), ptr(B),
+                     B.stride(0), float(beta), ptr(C), C.stride(0), _stream()), "odf_gemm")
+    return C
+
+
 def precond_apply_rows(Inv, r0, r1, Bin, Bout_rows, transposed):
     """Bout_rows = (op(Inv) @ Bin)[r0:r1] for an upper-triangular Inv (row block of the distributed application)."""
     L = _lib.load()

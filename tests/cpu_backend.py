@@ -61,6 +61,12 @@ def precond_apply(Inv, Bin, Bout, transposed):
     return Bout
 
 
+def gemm(A, B, C, trans_a=False, trans_b=False, alpha=1.0, beta=0.0):
+    res = alpha * ((A.T if trans_a else A) @ (B.T if trans_b else B))
+    C.copy_(res + beta * C if beta != 0.0 else res)
+    return C
+
+
 def precond_apply_rows(Inv, r0, r1, Bin, Bout_rows, transposed):
     full = (Inv.T if transposed else Inv) @ Bin.to(Inv.dtype)
     Bout_rows[:r1 - r0].copy_(full[r0:r1].to(Bout_rows.dtype))

@@ -109,32 +109,34 @@ def test_region_classifier_surface(tmp_path):
 
 
 # ------------------------------------------------------------------ N > 1 host logic over gloo
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, dist_pc=None):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, os.path.join(ROOT, "online-detection_b200"))
     sys.path.insert(0, ROOT)
     import cpu_backend
-    from odf import Falkon, GaussianKernel
+    from odf import Falkon, FalkonOptions, GaussianKernel
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     X, c, Y = orc.make_synthetic(1100, 24, 3, seed=0)
     C = X[orc.shared_centres(c, 64, seed=1)]
     lo, hi = (1100 * rank) // world, (1100 * (rank + 1)) // world
-    m = Falkon(GaussianKernel(12.0), 1e-4, 64, process_group=None, _ops=cpu_backend)
+    m = Falkon(GaussianKernel(12.0), 1e-4, 64, process_group=None, _ops=cpu_backend,
+               options=FalkonOptions(distributed_precond=dist_pc))
     m.fit(X[lo:hi], Y[lo:hi], centres=C if rank == 0 else torch.zeros_like(C) + C)
     torch.save({"alpha": m.alpha_, "times": m.fit_times_}, os.path.join(out_dir, "r%d.pt" % rank))
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("dist_pc", [None, True])      # None: replicated build at world 2; True: column blocks + all-gather
 @pytest.mark.parametrize("world", [2])
-def test_row_sharded_fit_matches_single_rank(tmp_path, world):
+def test_row_sharded_fit_matches_single_rank(tmp_path, world, dist_pc):
     import socket
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), dist_pc), nprocs=world, join=True)
     outs = [torch.load(os.path.join(str(tmp_path), "r%d.pt" % r), weights_only=False) for r in range(world)]
     assert torch.equal(outs[0]["alpha"], outs[1]["alpha"])           # replicated CG state stays bitwise equal
     assert outs[0]["times"]["N"] == 1100 and outs[0]["times"]["sweeps"] == 23   # 1 RHS + 20 + 2 restarts
