@@ -260,6 +260,21 @@ def main():
         out["test_scores"] = preds[0].get_field("scores")
         out["zscored_pos0"] = pos[0]                                            # trainRegionClassifier z-scores in place
 
+        # the out-of-core ("--CPU") flavour: FALKONWrapper_with_centers_selection.py + OnlineRegionClassifier.py
+        # (features parked on the host, falkon.Falkon with three options, easy-negative pruning also after the last batch)
+        import FALKONWrapper_with_centers_selection as ref_falkon_ooc
+        import OnlineRegionClassifier as ref_ocr_ooc
+        pos2, neg2_ = clone_lists(inp["positives"], inp["negatives"])
+        n_calls = len(CALLS)
+        torch.manual_seed(12)
+        clf2 = ref_falkon_ooc.FALKONWrapper(cfg_path)
+        rc2 = ref_ocr_ooc.OnlineRegionClassifier(clf2, pos2, neg2_, stats, cfg_path=cfg_path)
+        models2 = rc2.trainRegionClassifier()
+        for i, m in enumerate(models2):
+            out["ooc_model%d_alpha" % i], out["ooc_model%d_centres" % i] = m.alpha_, m.ny_points_
+        ooc_calls = CALLS[n_calls:]
+        del CALLS[n_calls:]
+
         # a14: RLS refiners on the normalised COXY, train_region_refiner.py:25-119 (+ normalize_COXY, py_od_utils.py:105-111)
         COXY = {"C": inp["reg_C"].clone(), "O": None, "X": inp["reg_X"].clone(), "Y": inp["reg_Y"].clone()}
         COXY = UT.normalize_COXY(COXY, stats, cpu=True)
@@ -326,11 +341,13 @@ def main():
             arrays["in_neg%d_%d" % (t, j)] = b.numpy()
     np.savez_compressed(os.path.join(HERE, "reference_flow.npz"), **arrays)
     with open(os.path.join(HERE, "reference_flow.json"), "w") as f:
-        json.dump({"cfg": CFG, "third_party_calls": CALLS,
+        json.dump({"cfg": CFG, "third_party_calls": CALLS, "third_party_calls_out_of_core": ooc_calls,
                    "reference_files": ["src/py_od_utils.py",
                                        "src/modules/region-classifier/FALKONWrapper_with_centers_selection_incore.py",
                                        "src/modules/region-classifier/MyCenterSelector.py",
                                        "src/modules/region-classifier/OnlineRegionClassifier_incore.py",
+                                       "src/modules/region-classifier/FALKONWrapper_with_centers_selection.py",
+                                       "src/modules/region-classifier/OnlineRegionClassifier.py",
                                        "src/modules/region-refiner/region_refiner.py",
                                        "src/modules/region-refiner/region_refiner_trainer/train_region_refiner.py",
                                        "src/modules/feature-extractor/mrcnn_modified/modeling/roi_heads/box_head/roi_box_predictors.py"],

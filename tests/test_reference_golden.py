@@ -63,6 +63,20 @@ def test_reference_called_falkon_the_way_the_product_assumes():
         assert f["y_shape"] == [f["fit"][0]] and f["centres"] == c["M"]
 
 
+def test_reference_out_of_core_flavour_calls():
+    """The `--CPU` flavour (FALKONWrapper_with_centers_selection.py + OnlineRegionClassifier.py): falkon.Falkon, three
+    options, no explicit maxiter (falkon's default 20), and — same RNG stream, same arithmetic — the same models."""
+    calls = META["third_party_calls_out_of_core"]
+    ctors = [c for c in calls if "ctor" in c]
+    assert len(ctors) == T_CLS * N_BATCH
+    for c in ctors:
+        assert c["ctor"] == "Falkon" and c["maxiter"] == 20
+        assert c["options"] == {"min_cuda_iter_size_32": 0, "min_cuda_iter_size_64": 0, "keops_active": "no"}
+    for i in range(T_CLS):
+        assert np.array_equal(G["ooc_model%d_alpha" % i], G["model%d_alpha" % i])
+        assert np.array_equal(G["ooc_model%d_centres" % i], G["model%d_centres" % i])
+
+
 def test_oracle_centre_selection_matches_reference_rng():
     y = torch.cat((torch.ones(100), -torch.ones(400)))
     torch.manual_seed(SEEDS["sel_many_pos"])
@@ -195,6 +209,30 @@ def test_product_region_classifier_reproduces_reference_flow(odf, tmp_path):
     assert scores.shape == ref.shape and torch.equal(scores[:, 0].cpu(), ref[:, 0])   # background column = -1
     assert rel(scores, ref) < 1e-3
     assert torch.equal(scores[:, 1:].argmax(1).cpu(), ref[:, 1:].argmax(1))
+
+
+@pytest.mark.gpu
+def test_product_out_of_core_flavour_reproduces_reference_flow(odf, tmp_path):
+    """Drop-in OnlineRegionClassifier + FALKONWrapper_with_centers_selection (features and models parked in host RAM,
+    fits staged through HBM by fit()'s side-stream upload): same centres as the reference flow, host-resident models,
+    scores within the parity bar."""
+    import FALKONWrapper_with_centers_selection as falkon_cpu
+    import OnlineRegionClassifier as ocr_cpu
+    positives, negatives = inputs()
+    stats = {"mean": t("stats_mean"), "std": t("stats_std"), "mean_norm": t("stats_mean_norm")[0]}
+    cfg = cfg_file(tmp_path)
+    torch.manual_seed(SEEDS["minibootstrap"])
+    clf = falkon_cpu.FALKONWrapper(cfg)
+    rc = ocr_cpu.OnlineRegionClassifier(clf, positives, negatives, stats, cfg_path=cfg)
+    models = rc.trainRegionClassifier()
+    x = (t("in_test_feat") - stats["mean"]) * (20 / stats["mean_norm"])
+    for i, m in enumerate(models):
+        assert not m.ny_points_.is_cuda and not m.alpha_.is_cuda
+        assert torch.equal(m.ny_points_, t("ooc_model%d_centres" % i))
+        s = clf.predict(m, x)
+        assert not s.is_cuda
+        ref = orc.falkon_predict(x, t("ooc_model%d_centres" % i), t("ooc_model%d_alpha" % i).double(), 12.0)
+        assert rel(s, ref) < 1e-3
 
 
 @pytest.mark.gpu
