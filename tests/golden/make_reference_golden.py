@@ -286,6 +286,12 @@ def main():
             out["rls%d_W" % i] = torch.stack([m["Beta"][str(k)]["weights"] for k in range(4)], 1)
             out["rls%d_losses" % i] = torch.stack([m["Beta"][str(k)]["losses"] for k in range(4)], 1)
 
+        # f-2: region predictor (apply regressors per class, decode with np.spacing(1), clip), predict_regions.py:16-80
+        bl_pred = BoxList(inp["test_boxes"].clone(), (640, 480))
+        feats = [{"feat": inp["test_feat"].numpy(), "gt": np.zeros(len(inp["test_boxes"]))}]
+        refined = rr.predict([bl_pred], feats)
+        out["refined_boxes"] = refined[0].bbox
+
         # a10/a11 + RLS apply: the inference head that consumes the models, roi_box_predictors.py:32-160, loaded from its
         # file with a registry stub (mrcnn_modified/modeling/registry.py only wraps maskrcnn_benchmark's Registry)
         import importlib.util
@@ -350,6 +356,7 @@ def main():
                                        "src/modules/region-classifier/OnlineRegionClassifier.py",
                                        "src/modules/region-refiner/region_refiner.py",
                                        "src/modules/region-refiner/region_refiner_trainer/train_region_refiner.py",
+                                       "src/modules/region-refiner/region_predictor/predict_regions.py",
                                        "src/modules/feature-extractor/mrcnn_modified/modeling/roi_heads/box_head/roi_box_predictors.py"],
                    "seeds": {"stats": 11, "sel_many_pos": 5, "sel_few_pos": 6, "minibootstrap": 12, "shuffle": 21,
                              "positives_from_coxy": 22},

@@ -304,6 +304,27 @@ def test_product_region_refiner_matches_reference_trainer(odf, tmp_path):
 
 
 @pytest.mark.gpu
+def test_product_region_predictor_matches_reference(odf, tmp_path):
+    """RegionRefiner.predict (predict_regions.py:16-80) with the reference-trained regressors from the fixture: refined
+    boxes (n, classes, 4), example boxes in slot 0, np.spacing(1) widths, clipping."""
+    from region_refiner import RegionRefiner
+    from boxlist import BoxList
+    models = np.empty((0,))
+    for i in range(T_CLS):
+        W = t("rls%d_W" % i).cuda()
+        models = np.append(models, {"mu": t("rls%d_mu" % i).cuda(), "T": t("rls%d_T" % i).cuda(), "T_inv": t("rls%d_Tinv" % i).cuda(),
+                                    "Beta": {str(k): {"weights": W[:, k].contiguous()} for k in range(4)}})
+    rr = RegionRefiner(cfg_file(tmp_path))
+    bl = BoxList(t("in_test_boxes").clone(), (640, 480), mode="xyxy")
+    feats = [{"feat": G["in_test_feat"], "gt": np.zeros(len(G["in_test_boxes"]))}]
+    out = rr.predict([bl], feats, models=models)
+    ref = t("refined_boxes")
+    assert tuple(out[0].bbox.shape) == tuple(ref.shape)
+    assert torch.equal(out[0].bbox[:, 0].cpu(), ref[:, 0])                       # example boxes untouched
+    assert float((out[0].bbox.cpu() - ref).abs().max()) < 2e-3                    # fp32 GEMM order + expf, boxes up to 640
+
+
+@pytest.mark.gpu
 def test_product_box_decode_matches_reference(odf):
     import py_od_utils as UT
     from boxlist import BoxList
