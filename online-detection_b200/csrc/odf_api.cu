@@ -333,14 +333,14 @@ size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T) {
     case ODF_OP_MMV: {
       const int S = odf_tile_splits(n, M, d, kind);
       return prepared_bytes(n, d, kind) + prepared_bytes(M, d, kind) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
-             al(sizeof(float) * S * n * T_pad);
+             al(sizeof(float) * S * n * T_pad) + al(128);
     }
     case ODF_OP_DMMV: {
       const int S1 = odf_tile_splits(n, M, d, kind);
       const int S2 = odf_tile_splits(M, n, d, kind);
       return prepared_bytes(n, d, kind) + prepared_bytes(M, d, kind) + 2 * al(sizeof(float) * T_pad * round_up(M, 128)) +
              2 * al(sizeof(float) * T_pad * round_up(n, 128)) + al(sizeof(float) * S1 * n * T_pad) +
-             al(sizeof(float) * S2 * M * T_pad);
+             al(sizeof(float) * S2 * M * T_pad) + al(sizeof(float) * n * T_pad) + 2 * al(128);
     }
     case ODF_OP_KMM:
       return prepared_bytes(M, d, kind);
@@ -351,6 +351,24 @@ size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T) {
     default:
       return 0;
   }
+}
+
+// partial[s] = K(rows, cols restricted to split s) . V for a plain fp32 V (m x T): splits V into the operand format of
+// the tile that will run (fp16 pairs + per-column scales for the CTA-pair tile when the launch has >= 8192 rows, tf32
+// hi / lo otherwise) inside the two scratch arrays vbuf_a / vbuf_b (each T_pad x ldvt floats) and launches it.
+static int mmv_from_plain(int kind, const Prepared& rows, int64_t n_rows, const Prepared& cols, int64_t n_cols, int64_t d,
+                          const float* V, int64_t T, int64_t ldv, int T_pad, int64_t ldvt, float* vbuf_a, float* vbuf_b,
+                          uint32_t* absmax, int S, float sigma, float* partial, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (tile2_rows_eligible(n_rows)) {
+    if ((rc = split_rhs16(V, n_cols, T, ldv, 1.f, absmax, vbuf_a, vbuf_b, ldvt, T_pad, st))) return rc;
+    return odf_gauss_mmv_pair(kind, rows.hi, rows.lo, rows.sqn, rows.opscale, n_rows, cols.hi, cols.lo, cols.sqn,
+                              cols.opscale, n_cols, d, vbuf_a, vbuf_b, ldvt, absmax, T_pad, S, sigma, partial, nullptr, stream);
+  }
+  if ((rc = split_rhs(V, n_cols, T, ldv, 1.f, vbuf_a, vbuf_b, ldvt, T_pad, st))) return rc;
+  return odf_gauss_mmv_prepared(kind, rows.hi, rows.lo, rows.sqn, rows.opscale, n_rows, cols.hi, cols.lo, cols.sqn,
+                                cols.opscale, n_cols, d, vbuf_a, vbuf_b, ldvt, T_pad, S, sigma, partial, stream);
 }
 
 int odf_gauss_mmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_t M, int64_t ldc, int64_t d,
@@ -369,14 +387,12 @@ int odf_gauss_mmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_
   float* vtl = a.take<float>(T_pad * ldvt);
   const int S = odf_tile_splits(n, M, d, kind);
   float* partial = a.take<float>(static_cast<size_t>(S) * n * T_pad);
+  uint32_t* absmax = a.take<uint32_t>(32);
   if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_mmv: workspace too small");
   int rc;
   if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, kind, px.hi, px.lo, px.sqn, px.opscale, st))) return rc;
   if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, kind, pc.hi, pc.lo, pc.sqn, pc.opscale, st))) return rc;
-  if ((rc = split_rhs(V, M, T, ldv, 1.f, vth, vtl, ldvt, T_pad, st))) return rc;
-  if ((rc = odf_gauss_mmv_prepared(kind, px.hi, px.lo, px.sqn, px.opscale, n, pc.hi, pc.lo, pc.sqn, pc.opscale, M, d,
-                                   vth, vtl, ldvt, T_pad, S, sigma, partial, stream)))
-    return rc;
+  if ((rc = mmv_from_plain(kind, px, n, pc, M, d, V, T, ldv, T_pad, ldvt, vth, vtl, absmax, S, sigma, partial, stream))) return rc;
   return finish_rows(partial, S, n, T_pad, T, 1.f, nullptr, 0, out, ldo, st);
 }
 
@@ -401,22 +417,24 @@ int odf_gauss_dmmv(const float* X, int64_t n, int64_t ldx, const float* C, int64
   const int S2 = odf_tile_splits(M, n, d, kind);
   float* part1 = a.take<float>(static_cast<size_t>(S1) * n * T_pad);
   float* part2 = a.take<float>(static_cast<size_t>(S2) * M * T_pad);
+  float* Wf = a.take<float>(static_cast<size_t>(n) * T_pad);
+  uint32_t* absmax_v = a.take<uint32_t>(32);
+  uint32_t* absmax_w = a.take<uint32_t>(32);
   if (!a.ok()) return set_error(ODF_ERR_WORKSPACE, "odf_gauss_dmmv: workspace too small");
   int rc;
   if ((rc = prepare_points(X, n, d, ldx, nullptr, 1.f, kind, px.hi, px.lo, px.sqn, px.opscale, st))) return rc;
   if ((rc = prepare_points(C, M, d, ldc, nullptr, 1.f, kind, pc.hi, pc.lo, pc.sqn, pc.opscale, st))) return rc;
+  const float* Wsrc = W;
+  int64_t ldwsrc = ldw;
   if (V) {
-    if ((rc = split_rhs(V, M, T, ldv, 1.f, vth, vtl, ldvt, T_pad, st))) return rc;
-    if ((rc = odf_gauss_mmv_prepared(kind, px.hi, px.lo, px.sqn, px.opscale, n, pc.hi, pc.lo, pc.sqn, pc.opscale, M, d,
-                                     vth, vtl, ldvt, T_pad, S1, sigma, part1, stream)))
-      return rc;
-    if ((rc = finish_split(part1, S1, n, T_pad, T, 1.f, W, ldw, wth, wtl, ldwt, st))) return rc;
-  } else {
-    if ((rc = split_rhs(W, n, T, ldw, 1.f, wth, wtl, ldwt, T_pad, st))) return rc;
+    // first half: W' = K V + W  (n x T)
+    if ((rc = mmv_from_plain(kind, px, n, pc, M, d, V, T, ldv, T_pad, ldvt, vth, vtl, absmax_v, S1, sigma, part1, stream))) return rc;
+    if ((rc = finish_rows(part1, S1, n, T_pad, T, 1.f, W, ldw, Wf, T_pad, st))) return rc;
+    Wsrc = Wf;
+    ldwsrc = T_pad;
   }
-  if ((rc = odf_gauss_mmv_prepared(kind, pc.hi, pc.lo, pc.sqn, pc.opscale, M, px.hi, px.lo, px.sqn, px.opscale, n, d,
-                                   wth, wtl, ldwt, T_pad, S2, sigma, part2, stream)))
-    return rc;
+  // second half: K^T W'  (rows = centres, columns = data)
+  if ((rc = mmv_from_plain(kind, pc, M, px, n, d, Wsrc, T, ldwsrc, T_pad, ldwt, wth, wtl, absmax_w, S2, sigma, part2, stream))) return rc;
   return finish_rows(part2, S2, M, T_pad, T, 1.f, nullptr, 0, out, ldo, st);
 }
 

@@ -117,6 +117,34 @@ def test_pair_tile_mmv_matches_oracle(odf, n, M, d, T, kind):
     assert float(((out - ref).abs().max(0).values / ref.abs().max(0).values).max()) < 5e-5      # per column
 
 
+@pytest.mark.parametrize("n,M,d,T", [(9000, 500, 64, 7), (1000, 300, 48, 21), (8500, 8300, 32, 3)])
+def test_plain_c_abi_entries(odf, n, M, d, T):
+    """odf_gauss_mmv / odf_gauss_dmmv on raw fp32 buffers + one workspace (the binding INTEGRATION.md shows): they pick
+    the CTA-pair tile for launches with >= 8192 rows and the single-CTA tile below, like the Python path."""
+    from odf import _lib
+    L = _lib.load()
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
+    C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]].contiguous()
+    g = torch.Generator().manual_seed(8)
+    v, w = torch.randn(M, T, generator=g), torch.randn(n, T, generator=g)
+    Xg, Cg, vg, wg = X.cuda(), C.cuda(), v.cuda(), w.cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.empty(n, T, device="cuda")
+    wsb = int(L.odf_workspace_bytes(_lib.ODF_OP_MMV, n, M, d, T))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(L.odf_gauss_mmv(_lib.ptr(Xg), n, d, _lib.ptr(Cg), M, d, d, _lib.ptr(vg), T, T, 15.0, _lib.ptr(out), T,
+                               _lib.ptr(ws), wsb, st), "odf_gauss_mmv")
+    assert rel(out, orc.mmv(X, C, v, 15.0)) < 5e-5
+    out2 = torch.empty(M, T, device="cuda")
+    wsb = int(L.odf_workspace_bytes(_lib.ODF_OP_DMMV, n, M, d, T))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    for (vv, ww) in ((vg, wg), (vg, None), (None, wg)):
+        _lib.check(L.odf_gauss_dmmv(_lib.ptr(Xg), n, d, _lib.ptr(Cg), M, d, d, _lib.ptr(vv), T, _lib.ptr(ww), T, T, 15.0,
+                                    _lib.ptr(out2), T, _lib.ptr(ws), wsb, st), "odf_gauss_dmmv")
+        ref = orc.dmmv(X, C, None if vv is None else v, None if ww is None else w, 15.0)
+        assert rel(out2, ref) < 1e-4
+
+
 def test_recompute_sweep_with_pair_tile_in_both_passes(odf):
     """sweep_mode="recompute" with >= 8192 centres: the second pass (rows = centres) also runs on the pair tile and
     needs the fp16 form of W."""
