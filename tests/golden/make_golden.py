@@ -1,8 +1,10 @@
 """Regenerates the committed golden fixtures from the CPU oracle (fp64).
 
-The reference cannot be imported in this container (falkon / maskrcnn_benchmark are not
-installed), so these vectors pin the ORACLE against regressions and give the GPU
-tests fixed inputs; they are not outputs of the reference itself.
+The third-party `falkon` arithmetic of the reference cannot run in this container (falkon is not
+installed), so THESE vectors pin the ORACLE against regressions and give the GPU
+tests fixed inputs; they are not outputs of the reference itself.  (Everything around that
+arithmetic is pinned by tests/golden/make_reference_golden.py, which runs the reference's own
+first-party modules.)
 
     python tests/golden/make_golden.py
 """
