@@ -47,6 +47,11 @@ def parse():
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep-mode", default=None, choices=["auto", "resident", "panel16", "panel", "recompute"],
+                    help="how the CG sweeps evaluate K_nm (default: the library's, \"auto\" = K panels resident in HBM "
+                         "when they fit, else streamed per sweep)")
+    ap.add_argument("--no-streaming-compare", action="store_true",
+                    help="skip the extra short run in the streaming (\"panel16\") mode reported under \"streaming\"")
     return ap.parse_args()
 
 
@@ -238,8 +243,9 @@ def run_ours(args):
     if args.workload == "c5":
         return run_predict(args, odf, ops, dist, world, rank, dev, Xh, Xd, centres, mean, scale, N, d, M, T, sigma, n_local)
 
-    def one_fit():
-        m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=group)
+    def one_fit(mode=args.sweep_mode):
+        m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=group,
+                             options=odf.FalkonOptions(sweep_mode=mode))
         m.fit(Xd, Yd, centres=centres, zscore=(mean, scale))
         return m
 
@@ -282,53 +288,78 @@ def run_ours(args):
     F = fit_flops(N, M, d, T)
     value = F / (ms_dev * 1e-3) / 1e9
 
-    # dominant kernel: the fused Gaussian tile.  In the default "panel16" sweep K is evaluated ONCE per
-    # sweep: a tile launch over (r rows x c centres) does the 2 r c d distance product, the exp epilogue
-    # and the first contraction K.V (2 r c T); the second contraction K^T.W (2 r c T) is the panel kernel.
-    tile_ms = [a.elapsed_time(b) for (a, b, *_rest) in tile_events]
-    tile_alg = [2.0 * r * c_ * dd + 2.0 * r * c_ * tt for (_a, _b, r, c_, dd, tt) in tile_events]
-    tile_exec = [6.0 * r * c_ * ((dd + 63) // 64 * 64) + 6.0 * r * c_ * (16 if tt <= 16 else 32) for (_a, _b, r, c_, dd, tt) in tile_events]
-    avg_ms = sum(tile_ms) / max(len(tile_ms), 1)
-    achieved = sum(tile_alg) / max(sum(tile_ms), 1e-9) / 1e9          # TFLOP/s, algorithmic
-    executed = sum(tile_exec) / max(sum(tile_ms), 1e-9) / 1e9         # TFLOP/s, tensor-pipe work issued
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
-    peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else \
-        "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
-    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of the same launch shape
-    traffic, traffic_src = None, None
+    traffic_json = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v3_traffic.json")))
-        tk = tj["gauss_tile2_kernel"]
-        if any((r, c_, dd) == (tk["rows"], tk["cols"], tk["d"]) for (_a, _b, r, c_, dd, _t) in tile_events):
-            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
-            traffic_src = tj["source"]
+        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v3_traffic.json")))
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
-                "traffic_source": traffic_src, "peak_source": peak_src,
-                "avg_launch_ms": avg_ms, "launches_timed": len(tile_ms),
-                "tile_share_of_step": sum(tile_ms) / args.steps / ms_dev,
+    sweep_mode = model.fit_times_.get("sweep_mode")
+
+    def tile_roofline(tile_events, steps, step_ms):
+        """The fused Gaussian tile (tensor bound).  A launch over (r rows x c centres) does the 2 r c d distance
+        product, the exp epilogue and the first contraction K.V (2 r c T); K is evaluated once per launch."""
+        tile_ms = [a.elapsed_time(b) for (a, b, *_rest) in tile_events]
+        tile_alg = [2.0 * r * c_ * dd + 2.0 * r * c_ * tt for (_a, _b, r, c_, dd, tt) in tile_events]
+        tile_exec = [6.0 * r * c_ * ((dd + 63) // 64 * 64) + 6.0 * r * c_ * (16 if tt <= 16 else 32)
+                     for (_a, _b, r, c_, dd, tt) in tile_events]
+        achieved = sum(tile_alg) / max(sum(tile_ms), 1e-9) / 1e9          # TFLOP/s, algorithmic
+        executed = sum(tile_exec) / max(sum(tile_ms), 1e-9) / 1e9         # TFLOP/s, tensor-pipe work issued
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else \
+            "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
+        # DRAM traffic: from the committed ncu --set full capture of the same launch shape
+        traffic, traffic_src = None, None
+        tk = traffic_json.get("gauss_tile2_kernel")
+        if tk and any((r, c_, dd) == (tk["rows"], tk["cols"], tk["d"]) for (_a, _b, r, c_, dd, _t) in tile_events):
+            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+            traffic_src = traffic_json["source"]
+        return {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram read + write)", "traffic_source": traffic_src,
+                "peak_source": peak_src, "avg_launch_ms": sum(tile_ms) / max(len(tile_ms), 1), "launches_timed": len(tile_ms),
+                "share_of_step": sum(tile_ms) / steps / step_ms,
                 "executed_tensor_tflops": executed, "executed_frac_of_peak": executed / peak,
                 "note": "fp32-grade distances need 3 fp16 tensor passes per product (hi.hi + hi.lo + lo.hi, 2 x 11-bit "
                         "split): algorithmic flops count each product once, so frac is capped at 1/3; "
                         "executed_frac_of_peak is the tensor-pipe work actually issued over the same cuBLAS bf16 peak"}
-    hbm_peak = peaks.get("hbm_gbs") or 6650.0
-    if panel_events:
+
+    def panel_roofline(panel_events, steps, step_ms):
+        """The tensor-core panel contraction (HBM bound): streams one fp16-plane panel, 4 B per kernel value."""
         p_ms = [a.elapsed_time(b) for (a, b, *_r) in panel_events]
-        p_bytes = [4.0 * n_ * ((m_ + 127) // 128 * 128) for (_a, _b, n_, m_, _tp) in panel_events]
+        p_bytes = [4.0 * ((n_ + 127) // 128 * 128) * ((m_ + 127) // 128 * 128) for (_a, _b, n_, m_, _tp) in panel_events]
         p_gbs = sum(p_bytes) / max(sum(p_ms), 1e-9) / 1e6
-        roofline["panel_kernel"] = {"kernel": "panel16_kernel", "bound": "hbm", "achieved": p_gbs, "peak": hbm_peak,
-                                    "unit": "GB/s", "frac": p_gbs / hbm_peak, "avg_launch_ms": sum(p_ms) / len(p_ms),
-                                    "launches_timed": len(p_ms), "share_of_step": sum(p_ms) / args.steps / ms_dev,
-                                    "note": "streams the spilled fp16 hi/lo K planes (4 B per kernel value) once and "
-                                            "contracts them with tcgen05 kind::f16 MMAs; read-only stream, so it can "
-                                            "exceed the read+write copy figure used as peak"}
+        hbm_peak = peaks.get("hbm_gbs") or 6650.0
+        traffic, traffic_src = None, None
+        tk = traffic_json.get("panel16_kernel")
+        if tk and any({n_, m_} == {tk["rows"], tk["cols"]} for (_a, _b, n_, m_, _tp) in panel_events):
+            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+            traffic_src = traffic_json["source"]
+        return {"bound": "hbm", "kernel": "panel16_kernel", "achieved": p_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": p_gbs / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                "traffic_source": traffic_src,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read + write), of measured" if peaks else
+                               "fallback 6.65 TB/s (B200_PROFILING.md), of fallback",
+                "avg_launch_ms": sum(p_ms) / max(len(p_ms), 1), "launches_timed": len(p_ms),
+                "algorithmic_bytes_per_launch": sum(p_bytes) / max(len(p_bytes), 1),
+                "share_of_step": sum(p_ms) / steps / step_ms,
+                "note": "streams one fp16 hi/lo K panel (4 B per kernel value) and contracts it with tcgen05 kind::f16 "
+                        "MMAs; a read-only stream, so it can exceed the read+write copy figure used as peak"}
+
+    # dominant kernel = the one with the larger share of the step.  "resident" sweeps: the panel kernel (two passes
+    # over the resident K / K^T panels per sweep, HBM bound); streaming sweeps: the fused tile (tensor bound).
+    r_tile = tile_roofline(tile_events, args.steps, ms_dev) if tile_events else None
+    r_panel = panel_roofline(panel_events, args.steps, ms_dev) if panel_events else None
+    if r_panel is not None and (r_tile is None or r_panel["share_of_step"] > r_tile["share_of_step"]):
+        roofline = dict(r_panel)
+        roofline["other_kernel"] = r_tile
+    else:
+        roofline = dict(r_tile)
+        roofline["other_kernel"] = r_panel
 
     # ---- end-to-end: host buffers in, result out, every step --------------------------------------
     e2e = None
@@ -336,7 +367,8 @@ def run_ours(args):
         def e2e_step():
             # the public call with HOST (pinned) buffers: fit() uploads X, Y on a side stream while it prepares the
             # centres and builds the preconditioner, then reads them from HBM
-            m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=group)
+            m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=group,
+                                 options=odf.FalkonOptions(sweep_mode=args.sweep_mode))
             m.fit(Xh, Yh, centres=centres, zscore=(mean, scale))
             return m.alpha_.cpu()                    # device -> host read of the result
         e2e_step()
@@ -351,6 +383,26 @@ def run_ours(args):
         e2e = {"value": F / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": (Xh.numel() + Yh.numel()) * 4 * world if world == 1 else int(N) * (d + T) * 4,
                "d2h_bytes_per_step": alpha_host.numel() * 4 * world}
+
+    # ---- the same fit with K streamed (re-evaluated by the fused tile in every sweep), for comparison ---------------
+    streaming = None
+    if sweep_mode == "resident" and not args.no_streaming_compare:
+        one_fit("panel16")
+        sync_all()
+        ops.TILE_EVENTS, ops.PANEL_EVENTS = [], []
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(2):
+            one_fit("panel16")
+        s1.record()
+        sync_all()
+        ms_s = max_over_ranks(s0.elapsed_time(s1)) / 2
+        t_ev, ops.TILE_EVENTS = ops.TILE_EVENTS, None
+        p_ev, ops.PANEL_EVENTS = ops.PANEL_EVENTS, None
+        streaming = {"sweep_mode": "panel16", "steps": 2, "warmup": 1, "fit_s": ms_s * 1e-3, "value": F / (ms_s * 1e-3) / 1e9,
+                     "unit": "GFLOP/s", "tile_kernel": tile_roofline(t_ev, 2, ms_s), "panel_kernel": panel_roofline(p_ev, 2, ms_s),
+                     "note": "K_nm never materialised beyond one transient row-chunk panel: every sweep re-evaluates K on "
+                             "the tensor cores (the fused tile is the dominant kernel of this mode)"}
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
     cpu = None
@@ -372,8 +424,12 @@ def run_ours(args):
                        "rows_per_gpu": n_local, "l2_policy": "inputs (%.1f GB/GPU) far larger than L2; no flush needed"
                                                              % (n_local * d * 4 / 1e9),
                        "parallelism": "rows sharded over %d GPU(s), 1 all-reduce of M x T per sweep" % world},
-            "fit_s": ms_dev * 1e-3, "phases_ms": phase, "sweeps_per_fit": 23,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
+            "fit_s": ms_dev * 1e-3, "phases_ms": phase, "sweeps_per_fit": 23, "sweep_mode": sweep_mode,
+            "sweep_mode_note": ("K panels (fp16 hi/lo planes, both orientations, %.1f GB/GPU) filled by the first two sweeps of "
+                                "EVERY fit and kept in HBM for its remaining 21 sweeps; nothing is carried over between fits"
+                                % (ops.resident_bytes(n_local, M) / 1e9)) if sweep_mode == "resident" else None,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "streaming": streaming,
+            "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -46,8 +46,12 @@ class FalkonOptions:
         self.precond_apply = ignored.pop("precond_apply", "inverse")
         # "panel16": K is evaluated once per sweep, its tiles are spilled as fp16 hi/lo planes to a transient panel
         # and contracted by the tensor-core panel kernel; "panel": fp32 panel + fp32-FMA panel kernel;
-        # "recompute": evaluate K twice (no panel workspace)
-        self.sweep_mode = ignored.pop("sweep_mode", "panel16")
+        # "recompute": evaluate K twice (no panel workspace); "resident": the fp16-plane panels of every row chunk
+        # stay in HBM in both orientations -- they are filled by the first two sweeps of the fit and every later
+        # sweep is two passes of the panel kernel at HBM speed, no kernel value is evaluated again (2 x 4 B per
+        # value: 81 GB at N = 1 M, M = 10 k); "auto" (default): "resident" when that fits in the free device
+        # memory, else "panel16".  ODF_SWEEP_MODE overrides the default.
+        self.sweep_mode = ignored.pop("sweep_mode", None) or os.environ.get("ODF_SWEEP_MODE") or "auto"
         # multi-GPU fits split T T^T and the explicit inverses over the ranks as column blocks (all-gathered); below
         # 4 ranks the replicated triangle-aware build is as fast and skips the M x M gathers.  None = by world size.
         self.distributed_precond = ignored.pop("distributed_precond", None)
@@ -105,6 +109,8 @@ class GaussianKernel:
         cols = self._prep(X2, like=X1)
         rows = self._prep(X1, like=cols)
         mode = getattr(self.opt, "sweep_mode", "panel16") if self.opt is not None else "panel16"
+        if mode in ("auto", "resident"):
+            mode = "panel16"                 # a one-shot sweep has nothing to keep resident
         sw = ops.Sweeper(rows, cols, self.sigma, min(T, 32), mode=mode)
         for t0 in range(0, T, 32):
             t1 = min(T, t0 + 32)
@@ -361,7 +367,8 @@ class Falkon:
         if dev.type == "cuda":
             torch.cuda.synchronize(dev)
         self.fit_times_ = {"prepare_ms": tm.ms(0, 1), "precond_ms": tm.ms(1, 2), "cg_ms": tm.ms(2, 3),
-                           "cg_iters": iters, "sweeps": self._sweeps, "N": N, "M": M, "T": T}
+                           "cg_iters": iters, "sweeps": self._sweeps, "N": N, "M": M, "T": T,
+                           "sweep_mode": self._sweep_mode}
         return self
 
     def _build_preconditioner(self, be, pc, sigma, lam, dist, group, world):
@@ -461,6 +468,7 @@ class Falkon:
         M, T = pc.n, Yb.shape[1]
         eps, tol = opt.cg_epsilon_32, opt.cg_tolerance
         sw = be.Sweeper(px, pc, sigma, T, mode=opt.sweep_mode) if px is not None else None
+        self._sweep_mode = getattr(sw, "mode", opt.sweep_mode)
         new = lambda: torch.empty((M, T), dtype=torch.float32, device=dev)  # noqa: E731
         B, R, P, AP, beta, v, u, c, H, H2 = (new() for _ in range(10))
         self._sweeps = 0

@@ -470,16 +470,29 @@ class Sweeper:
     K_chunk^T (K_chunk V + W) streaming the panel once at HBM speed.  K is evaluated once per sweep.
     mode "panel": same with an fp32 panel and the fp32-FMA panel kernel.  mode "recompute": the second
     half re-evaluates K in the transposed orientation with the same fused tile (no panel workspace,
-    2x tensor work)."""
+    2x tensor work).
+
+    mode "resident": the fp16-plane panels of ALL row chunks stay in HBM for the life of the Sweeper, in both
+    orientations (K_chunk and K_chunk^T, 2 x 4 B per kernel value: 81 GB for 1 M x 10 k, inside the 180 GB of
+    a B200).  The first two sweeps of a fit fill them as a by-product (the right-hand side sweep K^T y runs the
+    tile in the transposed orientation, the first operator application in the forward one, both with the spill
+    on); every later sweep evaluates no kernel value at all: K v and K^T w are two passes of the tensor-core
+    panel kernel over the resident planes, at HBM speed.  mode "auto" = "resident" when both panel sets fit in
+    the free device memory (resident_fits), else "panel16"."""
 
     def __init__(self, rows, cols, sigma, T, mode="panel16"):
         L = _lib.load()
         dev = rows.hi.device
+        if mode == "auto":
+            mode = "resident" if resident_fits(rows.n, cols.n, dev) else "panel16"
         self.rows, self.cols, self.sigma, self.T, self.mode = rows, cols, sigma, int(T), mode
+        if mode not in ("panel16", "panel", "recompute", "resident"):
+            raise ValueError("unknown sweep mode %r" % (mode,))
         self.v_rhs = SplitRhs(cols.n, T, dev)       # V^T  (T_pad x M)
-        self.w_rhs = SplitRhs(rows.n, T, dev)       # W^T  (T_pad x n), used by "recompute" and by the v=None sweep
         Tp = self.v_rhs.T_pad
-        self.part2 = alloc_partial(cols, rows, Tp, dev)   # rows = centres
+        if mode != "resident":
+            self.w_rhs = SplitRhs(rows.n, T, dev)   # W^T  (T_pad x n), used by "recompute" and by the v=None sweep
+            self.part2 = alloc_partial(cols, rows, Tp, dev)   # rows = centres
         if mode == "panel16":
             self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
             self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
@@ -491,6 +504,30 @@ class Sweeper:
             self.absmax = torch.zeros((32,), dtype=torch.int32, device=dev)
             self.pslabs = [int(L.odf_panel16_splits(r1 - r0, cols.n)) for (r0, r1) in self.chunks]
             self.part3 = torch.empty((sum(self.pslabs), cols.n, Tp), dtype=torch.float32, device=dev)
+        elif mode == "resident":
+            M = cols.n
+            self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
+            self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
+            self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
+            sizes = sorted({r1 - r0 for (r0, r1) in self.chunks})
+            u8 = lambda nbytes: torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)  # noqa: E731
+            self.fwd = [u8(L.odf_panel16_bytes(r1 - r0, M)) for (r0, r1) in self.chunks]     # K_chunk
+            self.tr = [u8(L.odf_panel16_bytes(M, r1 - r0)) for (r0, r1) in self.chunks]      # K_chunk^T
+            self.have_fwd = self.have_tr = False
+            self.part1 = {n: alloc_partial(RowView(rows, 0, n), cols, Tp, dev) for n in sizes}
+            self.w_rhs_c = {n: SplitRhs(n, T, dev) for n in sizes}
+            self.kv_part = {n: torch.empty((int(L.odf_panel16_splits(M, n)), n, Tp), dtype=torch.float32, device=dev)
+                            for n in sizes}
+            self.Wf = torch.empty((self.chunk, Tp), dtype=torch.float32, device=dev)
+            self.W16 = torch.empty(((self.chunk + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
+            self.Wpad = torch.zeros((1, self.chunk, Tp), dtype=torch.float32, device=dev)   # padded columns stay 0
+            self.absmax = torch.zeros((32,), dtype=torch.int32, device=dev)
+            self.Vpad = torch.zeros((1, M, Tp), dtype=torch.float32, device=dev)
+            self.Vf = torch.empty((M, Tp), dtype=torch.float32, device=dev)
+            self.V16 = torch.empty(((M + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
+            self.absmax_v = torch.zeros((32,), dtype=torch.int32, device=dev)
+            self.pslabs = [int(L.odf_panel16_splits(r1 - r0, M)) for (r0, r1) in self.chunks]
+            self.part3 = torch.empty((sum(self.pslabs), M, Tp), dtype=torch.float32, device=dev)
         elif mode == "panel":
             self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
             self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
@@ -507,6 +544,8 @@ class Sweeper:
 
     def dmmv(self, v, w, out, scale=1.0, w_scale=1.0):
         """out = scale * K^T (K v + w_scale * w)   (local rows only; caller all-reduces)."""
+        if self.mode == "resident":
+            return self._dmmv_resident(v, w, out, scale, w_scale)
         if v is None:
             self.w_rhs.fill(w, w_scale)
             mmv_partial(self.cols, self.rows, self.w_rhs, self.sigma, self.part2)
@@ -541,6 +580,99 @@ class Sweeper:
             panel_tmm(self.panel, self.Wc[:n], n, self.cols.n, self.part3[slab:slab + S])
             slab += S
         return finish_rows(self.part3, self.T, out, scale)
+
+    # ---- mode "resident" ------------------------------------------------------------------------
+    def _fill_transposed(self, w=None, w_scale=1.0, out=None, scale=1.0):
+        """One pass of the fused tile in the transposed orientation (rows = centres, columns = one row chunk
+        of X) with the spill on: leaves K_chunk^T resident and, as a by-product, out = scale * K^T (w_scale w)."""
+        M, dev = self.cols.n, self.cols.hi.device
+        Tp = self.v_rhs.T_pad
+        S_c = [tile_splits(M, r1 - r0, self.cols.d, self.cols.kind) for (r0, r1) in self.chunks]
+        partT = torch.empty((sum(S_c), M, Tp), dtype=torch.float32, device=dev)
+        slab = 0
+        for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
+            rhs = self.w_rhs_c[r1 - r0]
+            if w is None:
+                rhs.fill(self.Wpad[0, :r1 - r0, :self.T])           # zeros: only the spill matters
+            else:
+                rhs.fill(w[r0:r1], w_scale)
+            mmv_partial(self.cols, view, rhs, self.sigma, partT[slab:slab + S_c[i]], panel16=self.tr[i])
+            slab += S_c[i]
+        self.have_tr = True
+        if out is not None:
+            finish_rows(partT, self.T, out, scale)
+        return out
+
+    def _dmmv_resident(self, v, w, out, scale, w_scale):
+        M = self.cols.n
+        if v is None:
+            if not self.have_fwd:
+                # right-hand side sweep of a fit: K^T (w_scale w) by the transposed tile, K_chunk^T stays resident
+                return self._fill_transposed(w, w_scale, out, scale)
+            slab = 0
+            for i, (r0, r1) in enumerate(self.chunks):
+                n = r1 - r0
+                self.Wpad[0, :n, :self.T].copy_(w[r0:r1])
+                if w_scale != 1.0:
+                    self.Wpad[0, :n, :self.T].mul_(w_scale)
+                finish_w16(self.Wpad[:, :n], self.T, self.Wf, self.absmax, self.W16)
+                S = self.pslabs[i]
+                panel16_tmm(self.fwd[i], self.W16, self.absmax, n, M, self.part3[slab:slab + S])
+                slab += S
+            return finish_rows(self.part3, self.T, out, scale)
+        if w is not None and w_scale != 1.0:
+            w = w * w_scale
+        if not self.have_fwd:
+            # first operator application: forward tile with the spill on (K v is its by-product), K_chunk stays resident
+            self.v_rhs.fill(v)
+            slab = 0
+            for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
+                n = r1 - r0
+                part1 = self.part1[n]
+                mmv_partial(view, self.cols, self.v_rhs, self.sigma, part1, panel16=self.fwd[i])
+                finish_w16(part1, self.T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
+                S = self.pslabs[i]
+                panel16_tmm(self.fwd[i], self.W16, self.absmax, n, M, self.part3[slab:slab + S])
+                slab += S
+            self.have_fwd = True
+            self.part1 = None                                       # only this pass needs the tile's slabs
+            return finish_rows(self.part3, self.T, out, scale)
+        if not self.have_tr:
+            self._fill_transposed()
+        # no kernel value is evaluated from here on: V -> fp16 split, then two panel passes per chunk
+        self.Vpad[0, :, :self.T].copy_(v)
+        finish_w16(self.Vpad, self.T, self.Vf, self.absmax_v, self.V16)
+        slab = 0
+        for i, (r0, r1) in enumerate(self.chunks):
+            n = r1 - r0
+            kv = self.kv_part[n]
+            panel16_tmm(self.tr[i], self.V16, self.absmax_v, M, n, kv)                      # K_chunk v
+            finish_w16(kv, self.T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
+            S = self.pslabs[i]
+            panel16_tmm(self.fwd[i], self.W16, self.absmax, n, M, self.part3[slab:slab + S])  # K_chunk^T (K_chunk v + w)
+            slab += S
+        return finish_rows(self.part3, self.T, out, scale)
+
+
+RESIDENT_FRACTION = 0.85   # share of the free device memory the resident panels may take in mode "auto"
+
+
+def resident_bytes(n_rows, M):
+    """Bytes of the two resident fp16-plane panel sets (K and K^T) of an n_rows x M kernel block."""
+    L = _lib.load()
+    chunk = min(int(PANEL_ROWS), (n_rows + 127) // 128 * 128)
+    total = 0
+    for r0 in range(0, n_rows, chunk):
+        n = min(n_rows, r0 + chunk) - r0
+        total += int(L.odf_panel16_bytes(n, M)) + int(L.odf_panel16_bytes(M, n))
+    return total
+
+
+def resident_fits(n_rows, M, device):
+    free, _total = torch.cuda.mem_get_info(device)
+    # blocks cached by torch's allocator are reusable too
+    free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return resident_bytes(n_rows, M) <= RESIDENT_FRACTION * free
 
 
 # ---- index side: selection / gather (minibootstrap), box decode, detection post-processing ----

@@ -1,5 +1,6 @@
 """Short profiling target for ncu (not a test): a few launches of the fused Gaussian tile at a
-BASELINE-config-2-shaped slice (rows 131072 x centres 10000 x d 1024, T=30), both orientations."""
+BASELINE-config-2-shaped slice (rows 131072 x centres 10000 x d 1024, T=30); ODF_MODE=resident runs the
+resident-panel sweeps (transposed + forward tile with spill once, then two panel16 passes per sweep)."""
 import os
 import sys
 
@@ -16,8 +17,12 @@ X *= 20.0 / X[:1024].norm(dim=1).mean()
 C = X[torch.randperm(n, device="cuda", generator=g)[:M]].contiguous()
 px, pc = ops.Prepared(X), ops.Prepared(C)
 v = torch.randn(M, T, device="cuda", generator=g)
-sw = ops.Sweeper(px, pc, 20.0, T)
+mode = os.environ.get("ODF_MODE", "panel16")
+sw = ops.Sweeper(px, pc, 20.0, T, mode=mode)
 out = torch.empty(M, T, device="cuda")
+if mode == "resident":
+    # launches: transposed tile (spill) | forward tile (spill), panel16 (K^T w) | then per rep panel16 (K v), panel16 (K^T w)
+    sw.dmmv(None, torch.randn(n, T, device="cuda", generator=g), out, 1.0, 1.0 / n)
 for _ in range(int(os.environ.get("ODF_REPS", 3))):
     sw.dmmv(v, None, out)
 torch.cuda.synchronize()

@@ -275,6 +275,67 @@ def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
         assert rel(k.dmmv(X.cuda(), C.cuda(), v.cuda(), None), orc.dmmv(X, C, v, None, 15.0)) < 1e-4
 
 
+@pytest.mark.parametrize("n,M,d,T,chunk", [(3333, 300, 64, 7, 1024), (20000, 8300, 96, 30, 8192), (9000, 1000, 1024, 21, 131072),
+                                            (100, 40, 33, 1, 131072)])
+def test_resident_sweeper_matches_oracle(odf, monkeypatch, n, M, d, T, chunk):
+    """sweep_mode="resident": the fp16-plane panels of every row chunk stay in HBM in both orientations.  The
+    right-hand side sweep fills K^T (transposed tile pass with the spill on; the pair tile when M >= 8192, the
+    single-CTA tile below), the first operator application fills K, every later sweep is two panel passes and
+    evaluates no kernel value.  Ragged chunks; every sweep against the fp64 oracle."""
+    from odf import ops
+    monkeypatch.setattr(ops, "PANEL_ROWS", chunk)
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
+    C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
+    g = torch.Generator().manual_seed(8)
+    k = odf.GaussianKernel(15.0)
+    cols = k._prep(C.cuda())
+    rows = k._prep(X.cuda(), like=cols)
+    sw = ops.Sweeper(rows, cols, 15.0, T, mode="resident")
+    assert len(sw.chunks) == -(-n // min(chunk, (n + 127) // 128 * 128))
+    out = torch.empty((M, T), device="cuda")
+    y = torch.randn(n, T, generator=g)
+    sw.dmmv(None, y.cuda(), out, 1.0, 1.0 / n)
+    assert rel(out, orc.dmmv(X, C, None, y / n, 15.0)) < 1e-4 and sw.have_tr and not sw.have_fwd
+    tile_launches = []
+    for i in range(4):
+        v = torch.randn(M, T, generator=g) * torch.logspace(-2, 2, T)[None, :]
+        w = None if i % 2 == 0 else torch.randn(n, T, generator=g)
+        ops.TILE_EVENTS = []
+        try:
+            sw.dmmv(v.cuda(), None if w is None else w.cuda(), out, 0.5)
+            tile_launches.append(len(ops.TILE_EVENTS))
+        finally:
+            ops.TILE_EVENTS = None
+        ref = 0.5 * orc.dmmv(X, C, v, w, 15.0)
+        err = (out.double().cpu() - ref).abs().max(0).values / ref.abs().max(0).values
+        assert float(err.max()) < 1e-4, (i, float(err.max()))
+    assert tile_launches == [len(sw.chunks), 0, 0, 0]             # K is evaluated in the first application only
+    sw.dmmv(None, y.cuda(), out, 2.0, 0.25)                        # K^T w from the resident forward panels
+    assert rel(out, 2.0 * orc.dmmv(X, C, None, 0.25 * y, 15.0)) < 1e-4
+
+
+def test_resident_fit_matches_streaming_fit_and_oracle(odf, monkeypatch):
+    """A whole fit in the resident mode against the streaming ("panel16") fit and the fp64 oracle."""
+    from odf import ops
+    monkeypatch.setattr(ops, "PANEL_ROWS", 4096)
+    d, T = 256, 21
+    X, c, Y = orc.make_synthetic(12000, d, T, seed=0)
+    C = X[orc.shared_centres(c, 600, seed=1)]
+    res = _gpu_fit(odf, X, Y, C, 15.0, 1e-3, options=odf.FalkonOptions(sweep_mode="resident"))
+    stream = _gpu_fit(odf, X, Y, C, 15.0, 1e-3, options=odf.FalkonOptions(sweep_mode="panel16"))
+    auto = _gpu_fit(odf, X, Y, C, 15.0, 1e-3)
+    assert res.fit_times_["sweep_mode"] == "resident" and stream.fit_times_["sweep_mode"] == "panel16"
+    assert auto.fit_times_["sweep_mode"] == "resident" and torch.equal(auto.alpha_, res.alpha_)
+    assert res.fit_times_["sweeps"] == 23
+    Xt, ct, _ = orc.make_synthetic(3000, d, T, seed=11)
+    s_res, s_str = res.predict(Xt.cuda()).cpu(), stream.predict(Xt.cuda()).cpu()
+    alpha = orc.falkon_fit(X, Y, C, 15.0, 1e-3, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+    s_ref = orc.falkon_predict(Xt, C, alpha, 15.0)
+    assert rel(s_res, s_ref) < SCORE_RTOL and rel(s_str, s_ref) < SCORE_RTOL
+    assert rel(s_res, s_str) < 5e-4
+    assert_same_argmax(s_res, s_ref)
+
+
 def test_fit_from_host_memory_matches_device_fit(odf):
     """fit() with X / Y in (pinned or pageable) host memory uploads them on a side stream behind the preconditioner
     build: same arithmetic, so alpha is bitwise the device fit's."""

@@ -1,0 +1,159 @@
+"""CPU test of the host orchestration of ops.Sweeper(mode="resident") (no GPU, no compute call into libodf).
+
+The device operators the Sweeper drives (fused tile with spill, W16 conversion, panel contraction, slab reduction)
+are replaced by TEST-ONLY torch emulations that keep the same calling convention — partial slabs per column split,
+"panels" identified by their buffer, W16 identified by its buffer — so the test pins the slab / chunk / orientation
+bookkeeping: which panel is filled when, which one every later sweep reads, ragged last chunks, w / w_scale / scale
+handling, and that all of it equals the oracle's dmmv.  The kernels themselves are checked on the GPU
+(tests/test_gpu_parity.py::test_resident_*)."""
+import pytest
+import torch
+
+from oracle import falkon_oracle as orc
+
+DT = torch.float64
+
+
+class _FakePrepared:
+    def __init__(self, X):
+        self.hi = X.to(DT).contiguous()
+        self.lo = self.hi
+        self.sqn = torch.zeros((X.shape[0] + 127) // 128 * 128, dtype=DT)
+        self.opscale = torch.ones(2)
+        self.n, self.d, self.kind, self.pitch = X.shape[0], X.shape[1], 1, X.shape[1]
+
+
+class _FakeRhs:
+    def __init__(self, m, T, device):
+        self.m, self.T, self.T_pad, self.V = int(m), int(T), (16 if T <= 16 else 32), None
+
+    def fill(self, V, scale=1.0):
+        assert V.shape == (self.m, self.T)
+        self.V = V.to(DT) * scale
+        return self
+
+
+@pytest.fixture()
+def emu(monkeypatch, lib):
+    from odf import ops
+    store = {"panel": {}, "w16": {}, "calls": []}
+
+    def tile_splits(n_rows, n_cols, d, kind):
+        return min(3, (n_cols + 127) // 128)
+
+    def alloc_partial(rows, cols, T_pad, device):
+        return torch.full((tile_splits(rows.n, cols.n, rows.d, rows.kind), rows.n, T_pad), float("nan"), dtype=torch.float32)
+
+    def mmv_partial(rows, cols, rhs, sigma, partial, panel=None, panel16=None):
+        assert rhs.m == cols.n and panel is None
+        K = orc.gaussian_kernel(rows.hi[:rows.n], cols.hi[:cols.n], sigma, DT)
+        S = partial.shape[0]
+        assert partial.shape[1] == rows.n
+        edges = [cols.n * s // S for s in range(S + 1)]
+        partial.zero_()
+        for s in range(S):
+            partial[s, :, :rhs.T] = (K[:, edges[s]:edges[s + 1]] @ rhs.V[edges[s]:edges[s + 1]]).to(torch.float32)
+        if panel16 is not None:
+            assert panel16.numel() >= ((rows.n + 127) // 128 * 128) * ((cols.n + 127) // 128 * 128) * 4
+            store["panel"][panel16.data_ptr()] = K
+        store["calls"].append(("tile", rows.n, cols.n, panel16 is not None))
+
+    def finish_w16(partial, T, Wf, absmax, W16, addend=None):
+        S, n, T_pad = partial.shape
+        W = partial.to(DT).sum(0)[:, :T]
+        if addend is not None:
+            W = W + addend.to(DT)
+        assert W16.shape[0] >= (n + 127) // 128 * 128 and Wf.shape[0] >= n
+        store["w16"][W16.data_ptr()] = W
+        return W16
+
+    def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial):
+        K = store["panel"][panel16.data_ptr()]
+        W = store["w16"][W16.data_ptr()]
+        assert K.shape == (n_rows, M) and W.shape[0] == n_rows, "panel read in the wrong orientation"
+        S = out_partial.shape[0]
+        assert out_partial.shape[1] == M
+        edges = [n_rows * s // S for s in range(S + 1)]
+        out_partial.zero_()
+        for s in range(S):
+            out_partial[s, :, :W.shape[1]] = (K[edges[s]:edges[s + 1]].T @ W[edges[s]:edges[s + 1]]).to(torch.float32)
+        store["calls"].append(("panel", n_rows, M))
+
+    def finish_rows(partial, T, out, scale=1.0, addend=None):
+        res = partial.to(DT).sum(0)[:, :T] * scale
+        if addend is not None:
+            res = res + addend.to(DT)
+        out.copy_(res.to(out.dtype))
+        return out
+
+    for name, fn in (("tile_splits", tile_splits), ("alloc_partial", alloc_partial), ("mmv_partial", mmv_partial),
+                     ("finish_w16", finish_w16), ("panel16_tmm", panel16_tmm), ("finish_rows", finish_rows),
+                     ("SplitRhs", _FakeRhs)):
+        monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(ops, "PANEL_ROWS", 256)
+    return ops, store
+
+
+@pytest.mark.parametrize("n,M,T", [(700, 150, 5), (256, 130, 21), (90, 40, 1)])
+def test_resident_sweeper_bookkeeping(emu, n, M, T):
+    ops, store = emu
+    g = torch.Generator().manual_seed(n + M)
+    X = torch.randn(n, 12, generator=g, dtype=DT)
+    C = X[torch.randperm(n, generator=g)[:M]]
+    sigma = 3.0
+    sw = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), sigma, T, mode="resident")
+    assert len(sw.chunks) == -(-n // 256) and sw.chunks[-1][1] == n
+
+    def check(v, w, scale=1.0, w_scale=1.0, tol=2e-5):
+        out = torch.empty((M, T), dtype=torch.float32)
+        sw.dmmv(v, w, out, scale, w_scale)
+        ref = orc.dmmv(X, C, None if v is None else v.to(DT), None if w is None else w.to(DT) * w_scale, sigma, DT) * scale
+        assert (out.to(DT) - ref).abs().max() <= tol * ref.abs().max()
+
+    y = torch.randn(n, T, generator=g)
+    # 1. right-hand side sweep: transposed tile pass, one per chunk, every one with the spill on; no panel pass yet
+    check(None, y, w_scale=1.0 / n)
+    assert store["calls"] == [("tile", M, r1 - r0, True) for (r0, r1) in sw.chunks]
+    assert sw.have_tr and not sw.have_fwd
+    # 2. first operator application: forward tile with spill + panel pass per chunk
+    store["calls"].clear()
+    check(torch.randn(M, T, generator=g), None)
+    assert [c[0] for c in store["calls"]] == ["tile", "panel"] * len(sw.chunks) and sw.have_fwd
+    # 3. later sweeps never evaluate a kernel value: two panel passes per chunk, K^T first read as (M x n)
+    for v, w, sc in ((torch.randn(M, T, generator=g), None, 1.0), (torch.randn(M, T, generator=g), y, 0.5)):
+        store["calls"].clear()
+        check(v, w, scale=sc, w_scale=0.25)
+        exp = []
+        for (r0, r1) in sw.chunks:
+            exp += [("panel", M, r1 - r0), ("panel", r1 - r0, M)]
+        assert store["calls"] == exp
+    # 4. K^T w alone once the forward panels are resident: one panel pass per chunk
+    store["calls"].clear()
+    check(None, y, scale=2.0, w_scale=0.125)
+    assert store["calls"] == [("panel", r1 - r0, M) for (r0, r1) in sw.chunks]
+
+
+def test_resident_sweeper_operator_first(emu):
+    """An operator application before any right-hand side sweep: the transposed panels are filled on demand."""
+    ops, store = emu
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(300, 8, generator=g, dtype=DT)
+    C = X[:64]
+    sw = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 2.0, 3, mode="resident")
+    for _ in range(2):
+        v = torch.randn(64, 3, generator=g)
+        out = torch.empty((64, 3), dtype=torch.float32)
+        sw.dmmv(v, None, out)
+        ref = orc.dmmv(X, C, v.to(DT), None, 2.0, DT)
+        assert (out.to(DT) - ref).abs().max() <= 2e-5 * ref.abs().max()
+    kinds = [c[0] for c in store["calls"]]
+    assert kinds == ["tile", "panel"] * 2 + ["tile"] * 2 + ["panel"] * 4
+
+
+def test_resident_bytes_and_mode_names(lib):
+    from odf import ops
+    # C2 on one GPU: 8 chunks x 2 orientations x 4 B x pad(rows) x pad(centres)
+    b = ops.resident_bytes(1_000_000, 10_000)
+    assert b == 2 * 4 * 10112 * (7 * 131072 + 82560)
+    with pytest.raises(ValueError):
+        ops.Sweeper(_FakePrepared(torch.zeros(4, 2)), _FakePrepared(torch.zeros(2, 2)), 1.0, 1, mode="nope")
