@@ -425,9 +425,11 @@ def run_ours(args):
                                                              % (n_local * d * 4 / 1e9),
                        "parallelism": "rows sharded over %d GPU(s), 1 all-reduce of M x T per sweep" % world},
             "fit_s": ms_dev * 1e-3, "phases_ms": phase, "sweeps_per_fit": 23, "sweep_mode": sweep_mode,
-            "sweep_mode_note": ("K panels (fp16 hi/lo planes, both orientations, %.1f GB/GPU) filled by the first two sweeps of "
-                                "EVERY fit and kept in HBM for its remaining 21 sweeps; nothing is carried over between fits"
-                                % (ops.resident_bytes(n_local, M) / 1e9)) if sweep_mode == "resident" else None,
+            "sweep_mode_note": ("K panels (fp16 hi/lo planes, 4 B per kernel value%s, %.1f GB/GPU) filled by the first sweep%s of "
+                                "EVERY fit and kept in HBM for its remaining sweeps (two panel-kernel passes each, no kernel "
+                                "value re-evaluated); nothing is carried over between fits"
+                                % ("" if ops.RESIDENT_SINGLE_COPY else ", both orientations", ops.resident_bytes(n_local, M) / 1e9,
+                                   "" if ops.RESIDENT_SINGLE_COPY else "s (one per orientation)")) if sweep_mode == "resident" else None,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "streaming": streaming,
             "cpu_baseline": cpu}))
     if world > 1:

@@ -136,6 +136,15 @@ int odf_finish_w16(const float* partial, int n_splits, int64_t n_rows, int T_pad
 int odf_panel16_splits(int64_t n_rows, int64_t M);
 int odf_panel16_tmm(const void* panel16, int64_t n_rows, int64_t M, const void* w16, const void* absmax,
                     int T_pad, int n_splits, float* out_partial, void* stream);
+/* The other contraction on the SAME panel, for sweeps over panels that stay resident in HBM (sweep mode
+ * "resident"): out_partial[s][r][0..T_pad) = sum_{c in column range s} K[r][c] V[c][.], i.e. the K_blk v half of
+ * falkon GaussianKernel.dmmv / mmv without evaluating a kernel value.  v16 [round_up(M,128) x 64] fp16 is the
+ * odf_finish_w16 split of V (hi | lo, per-column scales in absmax[32]).  A [8 rows x 8 centres] block of the panel
+ * is a K-major core matrix for this product (rows = the MMA's M dimension), so the planes stream through plain
+ * 16 KB bulk copies.  n_splits = odf_panel16_mmv_splits(n_rows, M).                                          */
+int odf_panel16_mmv_splits(int64_t n_rows, int64_t M);
+int odf_panel16_mmv(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax,
+                    int T_pad, int n_splits, float* out_partial, void* stream);
 /* out[r, t] = scale * sum_s partial[s][r][t] + addend[r, t]   (addend may be NULL) */
 int odf_finish_rows(const float* partial, int n_splits, int64_t n_rows, int T_pad, int64_t T,
                     float scale, const float* addend, int64_t ld_add, float* out, int64_t ldo,

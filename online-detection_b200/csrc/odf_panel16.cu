@@ -233,6 +233,204 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, QTM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K . V from the SAME panel (the first half of a sweep when the panels are resident in HBM): the centres are the K
+// dimension now and the rows the M dimension of the MMA.  A [8 rows x 8 centres] block of the panel layout is also a
+// K-major un-swizzled core matrix (8 rows of 16 bytes), and the 16 centre groups of one (column tile, row block) are
+// 32 KB of contiguous memory per plane, so a stage of 64 centres is two plain 16 KB bulk copies (hi, lo) that land in
+// shared memory exactly as the tensor core wants them: next 8 rows +128 B (SBO), next group of 8 centres +2048 B (LBO).
+//     out_partial[s][r][t] = sum_{c in column range s} K[r][c] * V[c][t]
+// B = V16 [centre][hi(s_t V) 0..31 | lo 32..63], the same MN-major SWIZZLE_128B operand as W16 above.  Same pipeline,
+// accumulators, chain length (512 centres) and epilogue (thread = TMEM lane = row) as panel16_kernel.
+constexpr int VA = 8 * 2048;              // [8 centre groups][128 rows][8 fp16] of one plane
+constexpr int VSTAGE = 2 * VA + QCHUNK;   // P_hi, P_lo, V16 (64 centres x 128 B)  = 40 KB
+static_assert(VSTAGE == QSTAGE, "both panel kernels use the same shared-memory budget");
+// A: K-major, no swizzle: core matrices [8 rows x 16 B]; next core matrix along K (centres) 2048 B (LBO), next 8 rows 128 B (SBO)
+constexpr uint64_t kSdescKPlainHi = (static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
+                                    (static_cast<uint64_t>(1) << 46);
+constexpr uint64_t kSdescKPlainHiSwapped = (static_cast<uint64_t>(128 >> 4) << 16) | (static_cast<uint64_t>(2048 >> 4) << 32) |
+                                           (static_cast<uint64_t>(1) << 46);
+// kind::f16, fp16 A/B, fp32 accumulate, A K-major, B MN-major (bit 16), N = 64, M = 128
+constexpr uint32_t kIdescV = (1u << 4) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+
+struct Panel16VParams {
+  int n_ct;               // column (centre) tiles of 128
+  int n_rb;               // row blocks of 128
+  int n_stages;           // 64-centre stages per row block (2 per column tile)
+  int stages_per_item;
+  int n_csplit;           // column ranges (= partial slabs)
+  int n_rows, T_pad;
+  int64_t plane_elems;    // fp16 elements between the hi and the lo plane
+  int swap_lbo_sbo;       // bring-up switch (env ODF_P16V_SWAP)
+  const __half* P;        // the panel
+  const uint32_t* absmax; // 32 words: bits of max|V[:, t]|
+  float* out;             // [n_csplit][n_rows][T_pad]
+};
+
+__global__ void __launch_bounds__(256, 1)
+panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QNS * VSTAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + QBARS);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int B_FULL = 0, B_EMPTY = QNS, B_AFULL = 2 * QNS, B_AEMPTY = 2 * QNS + 2;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmV);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < QNS; ++s) {
+      mbar_init(BAR(B_FULL + s), 1);
+      mbar_init(BAR(B_EMPTY + s), 1);
+    }
+    mbar_init(BAR(B_AFULL + 0), 1);
+    mbar_init(BAR(B_AFULL + 1), 1);
+    mbar_init(BAR(B_AEMPTY + 0), 128);
+    mbar_init(BAR(B_AEMPTY + 1), 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), QTM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = p.n_rb * p.n_csplit;
+  // item -> (column range s, row block rb), rb fastest: CTAs running side by side share the V16 rows in L2
+
+  if (warp == 0) {
+    // ======================= producer =======================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int s = it / p.n_rb, rb = it - s * p.n_rb;
+        const int st0 = s * p.stages_per_item;
+        const int st1 = min(st0 + p.stages_per_item, p.n_stages);
+        for (int st = st0; st < st1; ++st) {
+          mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
+          const uint32_t full = BAR(B_FULL + stage);
+          const uint32_t dst = smem_u32(smem) + stage * VSTAGE;
+          // 8 centre groups of column tile j = st / 2, half st % 2: 16 KB of contiguous panel per plane
+          const __half* src = p.P + ((static_cast<int64_t>(st >> 1) * p.n_rb + rb) * 16 + (st & 1) * 8) * 1024;
+          mbar_arrive_expect_tx(full, VSTAGE);
+          bulk_g2s_hint(dst, src, VA, full, kEvictFirst);
+          bulk_g2s_hint(dst + VA, src + p.plane_elems, VA, full, kEvictFirst);
+          tma_load_2d_hint(dst + 2 * VA, &tmV, full, 0, st * QR, kEvictLast);
+          if (++stage == QNS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (elect_one()) {
+      const uint32_t sdesc0 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      const uint64_t a_const = p.swap_lbo_sbo ? kSdescKPlainHiSwapped : kSdescKPlainHi;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t g = 0;                       // accumulation chains started so far
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int s = it / p.n_rb;
+        const int st0 = s * p.stages_per_item;
+        const int st1 = min(st0 + p.stages_per_item, p.n_stages);
+        for (int st = st0; st < st1; ++st) {
+          const int local = st - st0;
+          const bool first = (local % QFLUSH) == 0;
+          const uint32_t t_acc = tmem_base + (g & 1) * 128;
+          if (first) mbar_wait(BAR(B_AEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
+          mbar_wait(BAR(B_FULL + stage), phase);
+          tc_fence_after();
+          const uint32_t sd = sdesc0 + stage * (VSTAGE >> 4);
+#pragma unroll
+          for (int kk = 0; kk < QR / 16; ++kk) {          // K = 16 centres per MMA: two centre groups of A, two 8-row groups of B
+            const uint64_t a_hi = a_const | static_cast<uint64_t>(sd + ((kk * 4096) >> 4));
+            const uint64_t a_lo = a_const | static_cast<uint64_t>(sd + ((VA + kk * 4096) >> 4));
+            const uint64_t b_v = kSdescMnHi | static_cast<uint64_t>(sd + ((2 * VA + kk * 2048) >> 4));
+            const uint32_t accum = (first && kk == 0) ? 0u : 1u;
+            mma_f16_ss(t_acc, a_hi, b_v, kIdescV, accum);
+            mma_f16_ss(t_acc + 64, a_lo, b_v, kIdescV, accum);
+          }
+          tc_commit(BAR(B_EMPTY + stage));
+          if (((local + 1) % QFLUSH) == 0 || st == st1 - 1) {
+            tc_commit(BAR(B_AFULL + (g & 1)));
+            ++g;
+          }
+          if (++stage == QNS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ======================= epilogue =======================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                        // row inside the row block (= TMEM lane)
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t g = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int s = it / p.n_rb, rb = it - s * p.n_rb;
+      const int st0 = s * p.stages_per_item;
+      const int st1 = min(st0 + p.stages_per_item, p.n_stages);
+      const int n_chains = (st1 - st0 + QFLUSH - 1) / QFLUSH;
+      float acc[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) acc[t] = 0.f;
+      for (int c = 0; c < n_chains; ++c, ++g) {
+        const uint32_t b = g & 1;
+        mbar_wait_warp(BAR(B_AFULL + b), (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + lane_off + b * 128;
+        uint32_t r[32];
+        float tmp[32];
+        __syncwarp();
+        tmem_ld32(t_acc + 64, r);                         // lo.hi  (x 2^-12)
+        tc_wait_ld();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * (1.f / 4096.f);
+        tmem_ld32(t_acc + 32, r);                         // hi.lo  (x 2^-11)
+        tc_wait_ld();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) tmp[t] = fmaf(__uint_as_float(r[t]), 1.f / 2048.f, tmp[t]);
+        tmem_ld32(t_acc, r);                              // hi.hi
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(BAR(B_AEMPTY + b));
+#pragma unroll
+        for (int t = 0; t < 32; ++t) acc[t] += __uint_as_float(r[t]) + tmp[t];
+      }
+      const int m = rb * 128 + row;
+      if (m < p.n_rows) {
+        float* orow = p.out + (static_cast<int64_t>(s) * p.n_rows + m) * p.T_pad;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          if (4 * v < p.T_pad) {
+            const uint4 mx = __ldg(reinterpret_cast<const uint4*>(p.absmax) + v);     // per-column scales of V16
+            float4 t4;
+            t4.x = acc[4 * v + 0] * w16_scale_from_bits(mx.x, true); t4.y = acc[4 * v + 1] * w16_scale_from_bits(mx.y, true);
+            t4.z = acc[4 * v + 2] * w16_scale_from_bits(mx.z, true); t4.w = acc[4 * v + 3] * w16_scale_from_bits(mx.w, true);
+            *reinterpret_cast<float4*>(orow + 4 * v) = t4;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, QTM_COLS);
+}
+
 int q_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -307,6 +505,50 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
   panel16_kernel<<<grid, 256, QSMEM, st>>>(tmP, tmW, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "panel16_kernel launch");
+  return ODF_OK;
+}
+
+// Column ranges per row block for panel16_mmv: the same cost model with the roles of rows and centres swapped
+// (items = row blocks, stages = 64-centre halves of the column tiles).
+int panel16_mmv_splits(int64_t n_rows, int64_t M) { return panel16_splits(round_up(M, 128), n_rows); }
+
+int launch_panel16_mmv(const void* P16, int64_t n_rows, int64_t M, const void* V16, const uint32_t* absmax, int T_pad,
+                       int n_splits, float* out_partial, cudaStream_t st) {
+  if (n_rows <= 0 || M <= 0 || (T_pad != 16 && T_pad != 32) || (reinterpret_cast<uintptr_t>(P16) & 127) != 0 ||
+      (reinterpret_cast<uintptr_t>(V16) & 127) != 0 || (reinterpret_cast<uintptr_t>(out_partial) & 15) != 0 || !absmax || (reinterpret_cast<uintptr_t>(absmax) & 15) != 0)
+    return set_error(ODF_ERR_ARG, "panel16_mmv: bad shape or alignment (P16, V16 128-byte aligned; T_pad 16 or 32)");
+  if (n_splits != panel16_mmv_splits(n_rows, M)) return set_error(ODF_ERR_ARG, "panel16_mmv: n_splits must come from odf_panel16_mmv_splits");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(panel16_mmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(panel16_mmv_kernel)");
+    attr_set = true;
+  }
+  Panel16VParams p;
+  p.n_ct = static_cast<int>((M + 127) / 128);
+  p.n_rb = static_cast<int>((n_rows + 127) / 128);
+  p.n_stages = 2 * p.n_ct;
+  p.stages_per_item = (p.n_stages + n_splits - 1) / n_splits;
+  p.n_csplit = n_splits;
+  p.n_rows = static_cast<int>(n_rows);
+  p.T_pad = T_pad;
+  p.plane_elems = static_cast<int64_t>(p.n_ct) * p.n_rb * 16384;
+  {
+    const char* e = getenv("ODF_P16V_SWAP");
+    p.swap_lbo_sbo = e ? atoi(e) : 0;
+  }
+  p.P = static_cast<const __half*>(P16);
+  p.absmax = absmax;
+  p.out = out_partial;
+  CUtensorMap tmV;
+  int rc;
+  if ((rc = make_map_sw128(&tmV, V16, static_cast<int64_t>(p.n_ct) * 128, 64, 64, QR, 2))) return rc;
+  const int n_items = p.n_rb * p.n_csplit;
+  const int sms = q_num_sms();
+  const int grid = n_items < sms ? n_items : sms;
+  panel16_mmv_kernel<<<grid, 256, QSMEM, st>>>(tmV, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "panel16_mmv_kernel launch");
   return ODF_OK;
 }
 

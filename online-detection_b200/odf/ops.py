@@ -2,6 +2,7 @@
 streams; every arithmetic step is a libodf call.  All functions require CUDA fp32 tensors and
 raise (OdfError / ValueError) otherwise — no fallback path exists."""
 import ctypes
+import os
 
 import torch
 
@@ -260,6 +261,24 @@ def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial):
     _count(1)
 
 
+def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial):
+    """out_partial[s] = K[:, column range s] @ V from the SAME fp16-plane panel (rows are the MMA's M dimension, the
+    blocked planes stream through plain bulk copies) -- K v without evaluating a kernel value."""
+    L = _lib.load()
+    S, n_, T_pad = out_partial.shape
+    assert n_ == n_rows and S == int(L.odf_panel16_mmv_splits(n_rows, M)) and out_partial.is_contiguous()
+    ev = None
+    if PANEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(L.odf_panel16_mmv(ptr(panel16), n_rows, M, ptr(V16), ptr(absmax), T_pad, S, ptr(out_partial), _stream()),
+          "odf_panel16_mmv")
+    if ev is not None:
+        ev[1].record()
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad))
+    _count(1)
+
+
 def finish_rows(partial, T, out, scale=1.0, addend=None):
     L = _lib.load()
     S, n, T_pad = partial.shape
@@ -478,7 +497,10 @@ class Sweeper:
     tile in the transposed orientation, the first operator application in the forward one, both with the spill
     on); every later sweep evaluates no kernel value at all: K v and K^T w are two passes of the tensor-core
     panel kernel over the resident planes, at HBM speed.  mode "auto" = "resident" when both panel sets fit in
-    the free device memory (resident_fits), else "panel16"."""
+    the free device memory (resident_fits), else "panel16".
+    With RESIDENT_SINGLE_COPY only K_chunk is kept (half the memory): K v comes from the same panel through
+    odf_panel16_mmv (rows as the MMA's M dimension), and the right-hand side sweep fills the panels with a
+    forward tile pass."""
 
     def __init__(self, rows, cols, sigma, T, mode="panel16"):
         L = _lib.load()
@@ -511,13 +533,17 @@ class Sweeper:
             self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
             sizes = sorted({r1 - r0 for (r0, r1) in self.chunks})
             u8 = lambda nbytes: torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)  # noqa: E731
+            self.single = bool(RESIDENT_SINGLE_COPY)
             self.fwd = [u8(L.odf_panel16_bytes(r1 - r0, M)) for (r0, r1) in self.chunks]     # K_chunk
-            self.tr = [u8(L.odf_panel16_bytes(M, r1 - r0)) for (r0, r1) in self.chunks]      # K_chunk^T
             self.have_fwd = self.have_tr = False
             self.part1 = {n: alloc_partial(RowView(rows, 0, n), cols, Tp, dev) for n in sizes}
-            self.w_rhs_c = {n: SplitRhs(n, T, dev) for n in sizes}
-            self.kv_part = {n: torch.empty((int(L.odf_panel16_splits(M, n)), n, Tp), dtype=torch.float32, device=dev)
-                            for n in sizes}
+            if self.single:
+                kv_splits = {n: int(L.odf_panel16_mmv_splits(n, M)) for n in sizes}
+            else:
+                self.tr = [u8(L.odf_panel16_bytes(M, r1 - r0)) for (r0, r1) in self.chunks]  # K_chunk^T
+                self.w_rhs_c = {n: SplitRhs(n, T, dev) for n in sizes}
+                kv_splits = {n: int(L.odf_panel16_splits(M, n)) for n in sizes}
+            self.kv_part = {n: torch.empty((kv_splits[n], n, Tp), dtype=torch.float32, device=dev) for n in sizes}
             self.Wf = torch.empty((self.chunk, Tp), dtype=torch.float32, device=dev)
             self.W16 = torch.empty(((self.chunk + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
             self.Wpad = torch.zeros((1, self.chunk, Tp), dtype=torch.float32, device=dev)   # padded columns stay 0
@@ -606,12 +632,19 @@ class Sweeper:
     def _dmmv_resident(self, v, w, out, scale, w_scale):
         M = self.cols.n
         if v is None:
-            if not self.have_fwd:
+            if not self.have_fwd and not self.single:
                 # right-hand side sweep of a fit: K^T (w_scale w) by the transposed tile, K_chunk^T stays resident
                 return self._fill_transposed(w, w_scale, out, scale)
+            fill = not self.have_fwd
+            if fill:
+                # single copy: a forward tile pass (its K.0 by-product is dropped) leaves K_chunk resident
+                self.Vpad.zero_()
+                self.v_rhs.fill(self.Vpad[0, :, :self.T])
             slab = 0
-            for i, (r0, r1) in enumerate(self.chunks):
+            for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
                 n = r1 - r0
+                if fill:
+                    mmv_partial(view, self.cols, self.v_rhs, self.sigma, self.part1[n], panel16=self.fwd[i])
                 self.Wpad[0, :n, :self.T].copy_(w[r0:r1])
                 if w_scale != 1.0:
                     self.Wpad[0, :n, :self.T].mul_(w_scale)
@@ -619,6 +652,9 @@ class Sweeper:
                 S = self.pslabs[i]
                 panel16_tmm(self.fwd[i], self.W16, self.absmax, n, M, self.part3[slab:slab + S])
                 slab += S
+            if fill:
+                self.have_fwd = True
+                self.part1 = None
             return finish_rows(self.part3, self.T, out, scale)
         if w is not None and w_scale != 1.0:
             w = w * w_scale
@@ -637,7 +673,7 @@ class Sweeper:
             self.have_fwd = True
             self.part1 = None                                       # only this pass needs the tile's slabs
             return finish_rows(self.part3, self.T, out, scale)
-        if not self.have_tr:
+        if not self.have_tr and not self.single:
             self._fill_transposed()
         # no kernel value is evaluated from here on: V -> fp16 split, then two panel passes per chunk
         self.Vpad[0, :, :self.T].copy_(v)
@@ -646,7 +682,10 @@ class Sweeper:
         for i, (r0, r1) in enumerate(self.chunks):
             n = r1 - r0
             kv = self.kv_part[n]
-            panel16_tmm(self.tr[i], self.V16, self.absmax_v, M, n, kv)                      # K_chunk v
+            if self.single:
+                panel16_mmv(self.fwd[i], self.V16, self.absmax_v, n, M, kv)                 # K_chunk v, same panel
+            else:
+                panel16_tmm(self.tr[i], self.V16, self.absmax_v, M, n, kv)                  # K_chunk v
             finish_w16(kv, self.T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
             S = self.pslabs[i]
             panel16_tmm(self.fwd[i], self.W16, self.absmax, n, M, self.part3[slab:slab + S])  # K_chunk^T (K_chunk v + w)
@@ -655,16 +694,19 @@ class Sweeper:
 
 
 RESIDENT_FRACTION = 0.85   # share of the free device memory the resident panels may take in mode "auto"
+# keep only K_chunk (default) instead of K_chunk and K_chunk^T: K v then comes from the same panel through
+# odf_panel16_mmv, half the memory and no transposed tile pass.  ODF_RESIDENT_SINGLE=0 selects the two-copy variant.
+RESIDENT_SINGLE_COPY = os.environ.get("ODF_RESIDENT_SINGLE", "1") not in ("0", "")
 
 
 def resident_bytes(n_rows, M):
-    """Bytes of the two resident fp16-plane panel sets (K and K^T) of an n_rows x M kernel block."""
+    """Bytes of the resident fp16-plane panel sets (K and, unless RESIDENT_SINGLE_COPY, K^T) of an n_rows x M block."""
     L = _lib.load()
     chunk = min(int(PANEL_ROWS), (n_rows + 127) // 128 * 128)
     total = 0
     for r0 in range(0, n_rows, chunk):
         n = min(n_rows, r0 + chunk) - r0
-        total += int(L.odf_panel16_bytes(n, M)) + int(L.odf_panel16_bytes(M, n))
+        total += int(L.odf_panel16_bytes(n, M)) * (1 if RESIDENT_SINGLE_COPY else 2)
     return total
 
 

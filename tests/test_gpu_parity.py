@@ -261,6 +261,43 @@ def test_panel16_kernel_matches_fp64_product(odf):
     assert float((out - ref).abs().max() / ref.abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize("n,M,d,T", [(9000, 333, 64, 21), (131, 2900, 40, 16), (20000, 1300, 96, 30), (3000, 2900, 32, 5)])
+def test_panel16_mmv_kernel_matches_fp64_product(odf, n, M, d, T):
+    """The other contraction on the same fp16-plane panel (odf_panel16_mmv, K-major A operand): spill K(X, C) with the
+    fused tile, contract with a wide-range V and compare with the fp64 product K V and with the tile's own K.V (the
+    same packed kernel values, so they agree to fp32 summation order).  Ragged rows / centres, one and several
+    column ranges."""
+    from odf import ops
+    P, _, _ = orc.make_synthetic(max(n, M), d, 3, seed=6)
+    X = P[:n].contiguous()
+    C = P[torch.randperm(max(n, M), generator=torch.Generator().manual_seed(7))[:M]].contiguous()
+    V = torch.randn(M, T, generator=torch.Generator().manual_seed(8)) * torch.logspace(-2, 2, T)[None, :]
+    k = odf.GaussianKernel(15.0)
+    cols = k._prep(C.cuda())
+    rows = k._prep(X.cuda(), like=cols)
+    dev = torch.device("cuda")
+    rhs = ops.SplitRhs(M, T, dev).fill(V.cuda())
+    part1 = ops.alloc_partial(rows, cols, rhs.T_pad, dev)
+    L = ops._lib.load()
+    p16 = torch.empty((int(L.odf_panel16_bytes(n, M)),), dtype=torch.uint8, device=dev)
+    ops.mmv_partial(rows, cols, rhs, 15.0, part1, panel16=p16)
+    Vpad = torch.zeros((1, M, rhs.T_pad), device=dev)
+    Vpad[0, :, :T] = V.cuda()
+    Vf = torch.empty((M, rhs.T_pad), device=dev)
+    V16 = torch.empty(((M + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
+    absmax = torch.zeros(32, dtype=torch.int32, device=dev)
+    ops.finish_w16(Vpad, T, Vf, absmax, V16)
+    S = int(L.odf_panel16_mmv_splits(n, M))
+    out_p = torch.full((S, n, rhs.T_pad), float("nan"), device=dev)
+    ops.panel16_mmv(p16, V16, absmax, n, M, out_p)
+    out = out_p.sum(0)[:, :T].double().cpu()
+    K = orc.gaussian_kernel(X, C, 15.0)
+    ref = K @ V.double()
+    assert float(((out - ref).abs() / (K @ V.double().abs())).max()) < 2e-5
+    tile_kv = part1.sum(0)[:, :T].double().cpu()
+    assert float(((out - tile_kv).abs() / tile_kv.abs().max(0).values).max()) < 2e-5
+
+
 def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
     """The spilled-panel sweep walks the rows in chunks; force several (ragged) chunks."""
     from odf import ops
@@ -277,13 +314,15 @@ def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
 
 @pytest.mark.parametrize("n,M,d,T,chunk", [(3333, 300, 64, 7, 1024), (20000, 8300, 96, 30, 8192), (9000, 1000, 1024, 21, 131072),
                                             (100, 40, 33, 1, 131072)])
-def test_resident_sweeper_matches_oracle(odf, monkeypatch, n, M, d, T, chunk):
+@pytest.mark.parametrize("single", [False, True])
+def test_resident_sweeper_matches_oracle(odf, monkeypatch, n, M, d, T, chunk, single):
     """sweep_mode="resident": the fp16-plane panels of every row chunk stay in HBM in both orientations.  The
     right-hand side sweep fills K^T (transposed tile pass with the spill on; the pair tile when M >= 8192, the
     single-CTA tile below), the first operator application fills K, every later sweep is two panel passes and
     evaluates no kernel value.  Ragged chunks; every sweep against the fp64 oracle."""
     from odf import ops
     monkeypatch.setattr(ops, "PANEL_ROWS", chunk)
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", single)      # True: only K is kept, K v through odf_panel16_mmv
     X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
     C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
     g = torch.Generator().manual_seed(8)
@@ -295,7 +334,8 @@ def test_resident_sweeper_matches_oracle(odf, monkeypatch, n, M, d, T, chunk):
     out = torch.empty((M, T), device="cuda")
     y = torch.randn(n, T, generator=g)
     sw.dmmv(None, y.cuda(), out, 1.0, 1.0 / n)
-    assert rel(out, orc.dmmv(X, C, None, y / n, 15.0)) < 1e-4 and sw.have_tr and not sw.have_fwd
+    assert rel(out, orc.dmmv(X, C, None, y / n, 15.0)) < 1e-4
+    assert (sw.have_fwd and not sw.have_tr) if single else (sw.have_tr and not sw.have_fwd)
     tile_launches = []
     for i in range(4):
         v = torch.randn(M, T, generator=g) * torch.logspace(-2, 2, T)[None, :]
@@ -309,15 +349,19 @@ def test_resident_sweeper_matches_oracle(odf, monkeypatch, n, M, d, T, chunk):
         ref = 0.5 * orc.dmmv(X, C, v, w, 15.0)
         err = (out.double().cpu() - ref).abs().max(0).values / ref.abs().max(0).values
         assert float(err.max()) < 1e-4, (i, float(err.max()))
-    assert tile_launches == [len(sw.chunks), 0, 0, 0]             # K is evaluated in the first application only
+    # K is evaluated once per orientation kept: in the right-hand side sweep (and, with both orientations, in the
+    # first operator application), never afterwards
+    assert tile_launches == [0 if single else len(sw.chunks), 0, 0, 0]
     sw.dmmv(None, y.cuda(), out, 2.0, 0.25)                        # K^T w from the resident forward panels
     assert rel(out, 2.0 * orc.dmmv(X, C, None, 0.25 * y, 15.0)) < 1e-4
 
 
-def test_resident_fit_matches_streaming_fit_and_oracle(odf, monkeypatch):
+@pytest.mark.parametrize("single", [False, True])
+def test_resident_fit_matches_streaming_fit_and_oracle(odf, monkeypatch, single):
     """A whole fit in the resident mode against the streaming ("panel16") fit and the fp64 oracle."""
     from odf import ops
     monkeypatch.setattr(ops, "PANEL_ROWS", 4096)
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", single)
     d, T = 256, 21
     X, c, Y = orc.make_synthetic(12000, d, T, seed=0)
     C = X[orc.shared_centres(c, 600, seed=1)]

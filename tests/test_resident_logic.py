@@ -79,6 +79,18 @@ def emu(monkeypatch, lib):
             out_partial[s, :, :W.shape[1]] = (K[edges[s]:edges[s + 1]].T @ W[edges[s]:edges[s + 1]]).to(torch.float32)
         store["calls"].append(("panel", n_rows, M))
 
+    def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial):
+        K = store["panel"][panel16.data_ptr()]
+        V = store["w16"][V16.data_ptr()]
+        assert K.shape == (n_rows, M) and V.shape[0] == M, "panel read in the wrong orientation"
+        S = out_partial.shape[0]
+        assert out_partial.shape[1] == n_rows
+        edges = [M * s // S for s in range(S + 1)]
+        out_partial.zero_()
+        for s in range(S):
+            out_partial[s, :, :V.shape[1]] = (K[:, edges[s]:edges[s + 1]] @ V[edges[s]:edges[s + 1]]).to(torch.float32)
+        store["calls"].append(("mmv", n_rows, M))
+
     def finish_rows(partial, T, out, scale=1.0, addend=None):
         res = partial.to(DT).sum(0)[:, :T] * scale
         if addend is not None:
@@ -87,10 +99,12 @@ def emu(monkeypatch, lib):
         return out
 
     for name, fn in (("tile_splits", tile_splits), ("alloc_partial", alloc_partial), ("mmv_partial", mmv_partial),
-                     ("finish_w16", finish_w16), ("panel16_tmm", panel16_tmm), ("finish_rows", finish_rows),
+                     ("finish_w16", finish_w16), ("panel16_tmm", panel16_tmm), ("panel16_mmv", panel16_mmv),
+                     ("finish_rows", finish_rows),
                      ("SplitRhs", _FakeRhs)):
         monkeypatch.setattr(ops, name, fn)
     monkeypatch.setattr(ops, "PANEL_ROWS", 256)
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", False)
     return ops, store
 
 
@@ -152,8 +166,47 @@ def test_resident_sweeper_operator_first(emu):
 
 def test_resident_bytes_and_mode_names(lib):
     from odf import ops
-    # C2 on one GPU: 8 chunks x 2 orientations x 4 B x pad(rows) x pad(centres)
+    # C2 on one GPU: 8 chunks x 4 B x pad(rows) x pad(centres) (x 2 orientations in the two-copy variant)
     b = ops.resident_bytes(1_000_000, 10_000)
-    assert b == 2 * 4 * 10112 * (7 * 131072 + 82560)
+    assert b == (1 if ops.RESIDENT_SINGLE_COPY else 2) * 4 * 10112 * (7 * 131072 + 82560)
     with pytest.raises(ValueError):
         ops.Sweeper(_FakePrepared(torch.zeros(4, 2)), _FakePrepared(torch.zeros(2, 2)), 1.0, 1, mode="nope")
+
+
+@pytest.mark.parametrize("n,M,T", [(700, 150, 5), (90, 40, 1)])
+def test_resident_single_copy_bookkeeping(emu, monkeypatch, n, M, T):
+    """RESIDENT_SINGLE_COPY: only K_chunk is kept; the right-hand side sweep fills it with a forward tile pass and
+    K v comes from the same panel (odf_panel16_mmv)."""
+    ops, store = emu
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    assert ops.resident_bytes(n, M) * 2 == sum(2 * 4 * ((r + 127) // 128 * 128) * ((M + 127) // 128 * 128)
+                                               for r in [min(256, n - r0) for r0 in range(0, n, 256)])
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(n, 12, generator=g, dtype=DT)
+    C = X[torch.randperm(n, generator=g)[:M]]
+    sw = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 3.0, T, mode="resident")
+    assert sw.single and not hasattr(sw, "tr")
+
+    def check(v, w, scale=1.0, w_scale=1.0):
+        out = torch.empty((M, T), dtype=torch.float32)
+        sw.dmmv(v, w, out, scale, w_scale)
+        ref = orc.dmmv(X, C, None if v is None else v.to(DT), None if w is None else w.to(DT) * w_scale, 3.0, DT) * scale
+        assert (out.to(DT) - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+    y = torch.randn(n, T, generator=g)
+    check(None, y, w_scale=1.0 / n)
+    assert [c[0] for c in store["calls"]] == ["tile", "panel"] * len(sw.chunks) and sw.have_fwd
+    for v, w in ((torch.randn(M, T, generator=g), None), (torch.randn(M, T, generator=g), y)):
+        store["calls"].clear()
+        check(v, w, scale=0.5, w_scale=2.0)
+        exp = []
+        for (r0, r1) in sw.chunks:
+            exp += [("mmv", r1 - r0, M), ("panel", r1 - r0, M)]
+        assert store["calls"] == exp
+    # operator first on a fresh Sweeper: forward tile pass with spill, then resident
+    sw2 = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 3.0, T, mode="resident")
+    store["calls"].clear()
+    sw, = (sw2,)
+    check(torch.randn(M, T, generator=g), y)
+    check(torch.randn(M, T, generator=g), None)
+    assert [c[0] for c in store["calls"]] == ["tile", "panel"] * len(sw2.chunks) + ["mmv", "panel"] * len(sw2.chunks)
