@@ -295,7 +295,7 @@ def run_ours(args):
         pass
     traffic_json = {}
     try:
-        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v3_traffic.json")))
+        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v9_traffic.json")))
     except Exception:  # noqa: BLE001
         pass
     sweep_mode = model.fit_times_.get("sweep_mode")
@@ -329,26 +329,35 @@ def run_ours(args):
                         "executed_frac_of_peak is the tensor-pipe work actually issued over the same cuBLAS bf16 peak"}
 
     def panel_roofline(panel_events, steps, step_ms):
-        """The tensor-core panel contraction (HBM bound): streams one fp16-plane panel, 4 B per kernel value."""
-        p_ms = [a.elapsed_time(b) for (a, b, *_r) in panel_events]
-        p_bytes = [4.0 * ((n_ + 127) // 128 * 128) * ((m_ + 127) // 128 * 128) for (_a, _b, n_, m_, _tp) in panel_events]
-        p_gbs = sum(p_bytes) / max(sum(p_ms), 1e-9) / 1e6
+        """The tensor-core panel contractions (HBM bound): each launch streams one fp16-plane panel, 4 B per kernel
+        value: panel16_kernel (K^T w) and, in the resident sweeps, panel16_mmv_kernel (K v from the same panel)."""
         hbm_peak = peaks.get("hbm_gbs") or 6650.0
+        per = {}
+        for (a, b, n_, m_, _tp, *name) in panel_events:
+            k = name[0] if name else "panel16_kernel"
+            e = per.setdefault(k, [0.0, 0.0, 0])
+            e[0] += a.elapsed_time(b)
+            e[1] += 4.0 * ((n_ + 127) // 128 * 128) * ((m_ + 127) // 128 * 128)
+            e[2] += 1
+        t_ms, t_bytes, t_n = (sum(e[i] for e in per.values()) for i in range(3))
+        p_gbs = t_bytes / max(t_ms, 1e-9) / 1e6
         traffic, traffic_src = None, None
-        tk = traffic_json.get("panel16_kernel")
-        if tk and any({n_, m_} == {tk["rows"], tk["cols"]} for (_a, _b, n_, m_, _tp) in panel_events):
-            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
-            traffic_src = traffic_json["source"]
-        return {"bound": "hbm", "kernel": "panel16_kernel", "achieved": p_gbs, "peak": hbm_peak, "unit": "GB/s",
+        for k in per:
+            tk = traffic_json.get(k)
+            if tk and any({n_, m_} == {tk["rows"], tk["cols"]} for (_a, _b, n_, m_, *_r) in panel_events):
+                traffic = max(traffic or 0, tk["dram_bytes_read"] + tk["dram_bytes_write"])
+                traffic_src = traffic_json["source"]
+        return {"bound": "hbm", "kernel": " + ".join(sorted(per)), "achieved": p_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": p_gbs / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
                 "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read + write), of measured" if peaks else
                                "fallback 6.65 TB/s (B200_PROFILING.md), of fallback",
-                "avg_launch_ms": sum(p_ms) / max(len(p_ms), 1), "launches_timed": len(p_ms),
-                "algorithmic_bytes_per_launch": sum(p_bytes) / max(len(p_bytes), 1),
-                "share_of_step": sum(p_ms) / steps / step_ms,
-                "note": "streams one fp16 hi/lo K panel (4 B per kernel value) and contracts it with tcgen05 kind::f16 "
-                        "MMAs; a read-only stream, so it can exceed the read+write copy figure used as peak"}
+                "avg_launch_ms": t_ms / max(t_n, 1), "launches_timed": t_n,
+                "algorithmic_bytes_per_launch": t_bytes / max(t_n, 1),
+                "share_of_step": t_ms / steps / step_ms,
+                "per_kernel": {k: {"launches": e[2], "avg_launch_ms": e[0] / e[2], "GB/s": e[1] / e[0] / 1e6} for k, e in per.items()},
+                "note": "each launch streams one fp16 hi/lo K panel (4 B per kernel value) and contracts it with tcgen05 "
+                        "kind::f16 MMAs; a read-only stream, so it can exceed the read+write copy figure used as peak"}
 
     # dominant kernel = the one with the larger share of the step.  "resident" sweeps: the panel kernel (two passes
     # over the resident K / K^T panels per sweep, HBM bound); streaming sweeps: the fused tile (tensor bound).
@@ -386,7 +395,7 @@ def run_ours(args):
 
     # ---- the same fit with K streamed (re-evaluated by the fused tile in every sweep), for comparison ---------------
     streaming = None
-    if sweep_mode == "resident" and not args.no_streaming_compare:
+    if str(sweep_mode).startswith("resident") and not args.no_streaming_compare:
         one_fit("panel16")
         sync_all()
         ops.TILE_EVENTS, ops.PANEL_EVENTS = [], []

@@ -468,7 +468,7 @@ class Falkon:
         M, T = pc.n, Yb.shape[1]
         eps, tol = opt.cg_epsilon_32, opt.cg_tolerance
         sw = be.Sweeper(px, pc, sigma, T, mode=opt.sweep_mode) if px is not None else None
-        self._sweep_mode = getattr(sw, "mode", opt.sweep_mode)
+        self._sweep_mode = sw.describe() if hasattr(sw, "describe") else getattr(sw, "mode", opt.sweep_mode)
         new = lambda: torch.empty((M, T), dtype=torch.float32, device=dev)  # noqa: E731
         B, R, P, AP, beta, v, u, c, H, H2 = (new() for _ in range(10))
         self._sweeps = 0

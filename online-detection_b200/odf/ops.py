@@ -225,7 +225,7 @@ def panel_tmm(panel, W, n_rows, M, out_partial):
           "odf_panel_tmm")
     if ev is not None:
         ev[1].record()
-        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad))
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel_tmm_kernel"))
     _count(1)
 
 
@@ -257,7 +257,7 @@ def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial):
           "odf_panel16_tmm")
     if ev is not None:
         ev[1].record()
-        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad))
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_kernel"))
     _count(1)
 
 
@@ -275,7 +275,7 @@ def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial):
           "odf_panel16_mmv")
     if ev is not None:
         ev[1].record()
-        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad))
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_mmv_kernel"))
     _count(1)
 
 
@@ -502,11 +502,13 @@ class Sweeper:
     odf_panel16_mmv (rows as the MMA's M dimension), and the right-hand side sweep fills the panels with a
     forward tile pass."""
 
-    def __init__(self, rows, cols, sigma, T, mode="panel16"):
+    def __init__(self, rows, cols, sigma, T, mode="panel16", resident_chunks=None):
         L = _lib.load()
         dev = rows.hi.device
         if mode == "auto":
-            mode = "resident" if resident_fits(rows.n, cols.n, dev) else "panel16"
+            # as many row chunks resident as fit (single-copy variant: the rest is streamed through a transient panel)
+            resident_chunks = resident_plan(rows.n, cols.n, dev)
+            mode = "resident" if resident_chunks > 0 else "panel16"
         self.rows, self.cols, self.sigma, self.T, self.mode = rows, cols, sigma, int(T), mode
         if mode not in ("panel16", "panel", "recompute", "resident"):
             raise ValueError("unknown sweep mode %r" % (mode,))
@@ -534,7 +536,12 @@ class Sweeper:
             sizes = sorted({r1 - r0 for (r0, r1) in self.chunks})
             u8 = lambda nbytes: torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)  # noqa: E731
             self.single = bool(RESIDENT_SINGLE_COPY)
-            self.fwd = [u8(L.odf_panel16_bytes(r1 - r0, M)) for (r0, r1) in self.chunks]     # K_chunk
+            # the first n_res chunks stay resident; the others (single-copy variant only) go through a transient
+            # panel and re-evaluate K in every sweep, as in mode "panel16"
+            self.n_res = len(self.chunks) if (resident_chunks is None or not self.single) else \
+                max(0, min(int(resident_chunks), len(self.chunks)))
+            self.fwd = [u8(L.odf_panel16_bytes(r1 - r0, M)) for (r0, r1) in self.chunks[:self.n_res]]     # K_chunk
+            self.transient = u8(L.odf_panel16_bytes(self.chunk, M)) if self.n_res < len(self.chunks) else None
             self.have_fwd = self.have_tr = False
             self.part1 = {n: alloc_partial(RowView(rows, 0, n), cols, Tp, dev) for n in sizes}
             if self.single:
@@ -629,22 +636,72 @@ class Sweeper:
             finish_rows(partT, self.T, out, scale)
         return out
 
+    def _dmmv_single(self, v, w, out, scale, w_scale):
+        """Single-copy resident sweep.  Per row chunk: a RESIDENT chunk evaluates K once (the first sweep runs the
+        fused tile with the spill into the chunk's own panel; K v is its by-product) and afterwards costs two panel
+        passes, odf_panel16_mmv (K v) and odf_panel16_tmm (K^T (K v + w)); a STREAMED chunk (beyond n_res) runs the
+        tile with the spill into the transient panel in every sweep."""
+        M, T = self.cols.n, self.T
+        fill = not self.have_fwd
+        need_tile = fill or self.n_res < len(self.chunks)
+        if v is None:
+            if need_tile:
+                self.Vpad.zero_()
+                self.v_rhs.fill(self.Vpad[0, :, :T])                # the tile's K.0 by-product is dropped
+        else:
+            if w is not None and w_scale != 1.0:
+                w = w * w_scale
+            if need_tile:
+                self.v_rhs.fill(v)
+            if not fill and self.n_res > 0:
+                self.Vpad[0, :, :T].copy_(v)
+                finish_w16(self.Vpad, T, self.Vf, self.absmax_v, self.V16)
+        slab = 0
+        for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
+            n = r1 - r0
+            resident = i < self.n_res
+            panel = self.fwd[i] if resident else self.transient
+            tile = fill or not resident
+            if tile:
+                mmv_partial(view, self.cols, self.v_rhs, self.sigma, self.part1[n], panel16=panel)
+            if v is None:
+                self.Wpad[0, :n, :T].copy_(w[r0:r1])
+                if w_scale != 1.0:
+                    self.Wpad[0, :n, :T].mul_(w_scale)
+                finish_w16(self.Wpad[:, :n], T, self.Wf, self.absmax, self.W16)
+            elif tile:
+                finish_w16(self.part1[n], T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
+            else:
+                kv = self.kv_part[n]
+                panel16_mmv(panel, self.V16, self.absmax_v, n, M, kv)                       # K_chunk v, same panel
+                finish_w16(kv, T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
+            S = self.pslabs[i]
+            panel16_tmm(panel, self.W16, self.absmax, n, M, self.part3[slab:slab + S])      # K_chunk^T (K_chunk v + w)
+            slab += S
+        self.have_fwd = True
+        if self.n_res == len(self.chunks):
+            self.part1 = None                                       # only the filling pass needs the tile's slabs
+        return finish_rows(self.part3, T, out, scale)
+
+    def describe(self):
+        if self.mode != "resident":
+            return self.mode
+        if self.n_res == len(self.chunks):
+            return "resident"
+        return "resident(%d of %d row chunks, the rest streamed)" % (self.n_res, len(self.chunks))
+
     def _dmmv_resident(self, v, w, out, scale, w_scale):
+        if self.single:
+            return self._dmmv_single(v, w, out, scale, w_scale)
+        # two-copy variant (ODF_RESIDENT_SINGLE=0): K_chunk and K_chunk^T both resident, only odf_panel16_tmm is used
         M = self.cols.n
         if v is None:
-            if not self.have_fwd and not self.single:
+            if not self.have_fwd:
                 # right-hand side sweep of a fit: K^T (w_scale w) by the transposed tile, K_chunk^T stays resident
                 return self._fill_transposed(w, w_scale, out, scale)
-            fill = not self.have_fwd
-            if fill:
-                # single copy: a forward tile pass (its K.0 by-product is dropped) leaves K_chunk resident
-                self.Vpad.zero_()
-                self.v_rhs.fill(self.Vpad[0, :, :self.T])
             slab = 0
-            for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
+            for i, (r0, r1) in enumerate(self.chunks):
                 n = r1 - r0
-                if fill:
-                    mmv_partial(view, self.cols, self.v_rhs, self.sigma, self.part1[n], panel16=self.fwd[i])
                 self.Wpad[0, :n, :self.T].copy_(w[r0:r1])
                 if w_scale != 1.0:
                     self.Wpad[0, :n, :self.T].mul_(w_scale)
@@ -652,9 +709,6 @@ class Sweeper:
                 S = self.pslabs[i]
                 panel16_tmm(self.fwd[i], self.W16, self.absmax, n, M, self.part3[slab:slab + S])
                 slab += S
-            if fill:
-                self.have_fwd = True
-                self.part1 = None
             return finish_rows(self.part3, self.T, out, scale)
         if w is not None and w_scale != 1.0:
             w = w * w_scale
@@ -673,7 +727,7 @@ class Sweeper:
             self.have_fwd = True
             self.part1 = None                                       # only this pass needs the tile's slabs
             return finish_rows(self.part3, self.T, out, scale)
-        if not self.have_tr and not self.single:
+        if not self.have_tr:
             self._fill_transposed()
         # no kernel value is evaluated from here on: V -> fp16 split, then two panel passes per chunk
         self.Vpad[0, :, :self.T].copy_(v)
@@ -682,10 +736,7 @@ class Sweeper:
         for i, (r0, r1) in enumerate(self.chunks):
             n = r1 - r0
             kv = self.kv_part[n]
-            if self.single:
-                panel16_mmv(self.fwd[i], self.V16, self.absmax_v, n, M, kv)                 # K_chunk v, same panel
-            else:
-                panel16_tmm(self.tr[i], self.V16, self.absmax_v, M, n, kv)                  # K_chunk v
+            panel16_tmm(self.tr[i], self.V16, self.absmax_v, M, n, kv)                      # K_chunk v from K_chunk^T
             finish_w16(kv, self.T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
             S = self.pslabs[i]
             panel16_tmm(self.fwd[i], self.W16, self.absmax, n, M, self.part3[slab:slab + S])  # K_chunk^T (K_chunk v + w)
@@ -710,11 +761,30 @@ def resident_bytes(n_rows, M):
     return total
 
 
-def resident_fits(n_rows, M, device):
+def _free_bytes(device):
     free, _total = torch.cuda.mem_get_info(device)
     # blocks cached by torch's allocator are reusable too
-    free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
-    return resident_bytes(n_rows, M) <= RESIDENT_FRACTION * free
+    return free + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+
+
+def resident_fits(n_rows, M, device):
+    return resident_bytes(n_rows, M) <= RESIDENT_FRACTION * _free_bytes(device)
+
+
+def resident_plan(n_rows, M, device, budget=None):
+    """How many row chunks of an n_rows x M block can stay resident (mode "auto").  All of them when the panels fit
+    into RESIDENT_FRACTION of the free device memory; otherwise (single-copy variant) as many as fit beside the
+    transient panel the streamed chunks share; 0 = stream everything (mode "panel16")."""
+    L = _lib.load()
+    budget = RESIDENT_FRACTION * _free_bytes(device) if budget is None else budget
+    if resident_bytes(n_rows, M) <= budget:
+        return -(-n_rows // min(int(PANEL_ROWS), (n_rows + 127) // 128 * 128))
+    if not RESIDENT_SINGLE_COPY:
+        return 0
+    chunk = min(int(PANEL_ROWS), (n_rows + 127) // 128 * 128)
+    per_chunk = int(L.odf_panel16_bytes(chunk, M))
+    k = int((budget - per_chunk) // per_chunk)                      # one transient panel + k resident ones
+    return max(0, min(k, n_rows // chunk))
 
 
 # ---- index side: selection / gather (minibootstrap), box decode, detection post-processing ----

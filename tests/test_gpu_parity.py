@@ -356,6 +356,48 @@ def test_resident_sweeper_matches_oracle(odf, monkeypatch, n, M, d, T, chunk, si
     assert rel(out, 2.0 * orc.dmmv(X, C, None, 0.25 * y, 15.0)) < 1e-4
 
 
+def test_resident_partial_matches_oracle_and_fit(odf, monkeypatch):
+    """Hybrid residency: what does not fit in the memory budget is streamed.  2 of 4 row chunks resident at the
+    sweep level, 1 of 3 in a whole fit (plan forced through ops.resident_plan)."""
+    from odf import ops
+    monkeypatch.setattr(ops, "PANEL_ROWS", 1024)
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    n, M, d, T = 3333, 300, 64, 7
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
+    C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
+    g = torch.Generator().manual_seed(8)
+    k = odf.GaussianKernel(15.0)
+    cols = k._prep(C.cuda())
+    rows = k._prep(X.cuda(), like=cols)
+    sw = ops.Sweeper(rows, cols, 15.0, T, mode="resident", resident_chunks=2)
+    assert sw.describe() == "resident(2 of 4 row chunks, the rest streamed)"
+    out = torch.empty((M, T), device="cuda")
+    y = torch.randn(n, T, generator=g)
+    sw.dmmv(None, y.cuda(), out, 1.0, 1.0 / n)
+    assert rel(out, orc.dmmv(X, C, None, y / n, 15.0)) < 1e-4
+    for i in range(3):
+        v = torch.randn(M, T, generator=g)
+        w = None if i % 2 == 0 else torch.randn(n, T, generator=g)
+        ops.TILE_EVENTS = []
+        try:
+            sw.dmmv(v.cuda(), None if w is None else w.cuda(), out)
+            assert len(ops.TILE_EVENTS) == 2                       # only the two streamed chunks evaluate K
+        finally:
+            ops.TILE_EVENTS = None
+        assert rel(out, orc.dmmv(X, C, v, w, 15.0)) < 1e-4
+    # whole fit, 1 of 3 chunks resident
+    monkeypatch.setattr(ops, "PANEL_ROWS", 4096)
+    monkeypatch.setattr(ops, "resident_plan", lambda n_rows, M_, dev, budget=None: 1)
+    Xf, c, Y = orc.make_synthetic(12000, 256, 21, seed=0)
+    Cf = Xf[orc.shared_centres(c, 600, seed=1)]
+    part = _gpu_fit(odf, Xf, Y, Cf, 15.0, 1e-3)
+    assert part.fit_times_["sweep_mode"] == "resident(1 of 3 row chunks, the rest streamed)"
+    full = _gpu_fit(odf, Xf, Y, Cf, 15.0, 1e-3, options=odf.FalkonOptions(sweep_mode="resident"))
+    assert full.fit_times_["sweep_mode"] == "resident"
+    Xt = Xf[:3000].cuda()
+    assert rel(part.predict(Xt), full.predict(Xt)) < 5e-4
+
+
 @pytest.mark.parametrize("single", [False, True])
 def test_resident_fit_matches_streaming_fit_and_oracle(odf, monkeypatch, single):
     """A whole fit in the resident mode against the streaming ("panel16") fit and the fp64 oracle."""

@@ -210,3 +210,45 @@ def test_resident_single_copy_bookkeeping(emu, monkeypatch, n, M, T):
     check(torch.randn(M, T, generator=g), y)
     check(torch.randn(M, T, generator=g), None)
     assert [c[0] for c in store["calls"]] == ["tile", "panel"] * len(sw2.chunks) + ["mmv", "panel"] * len(sw2.chunks)
+
+
+@pytest.mark.parametrize("n_res", [0, 1, 2])
+def test_resident_partial_bookkeeping(emu, monkeypatch, n_res):
+    """Hybrid: the first n_res row chunks stay resident, the others are streamed through the transient panel and
+    re-evaluate K in every sweep."""
+    ops, store = emu
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    n, M, T = 700, 150, 5                                          # 3 chunks: 256, 256, 188
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(n, 12, generator=g, dtype=DT)
+    C = X[torch.randperm(n, generator=g)[:M]]
+    sw = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 3.0, T, mode="resident", resident_chunks=n_res)
+    assert sw.n_res == n_res and len(sw.fwd) == n_res and sw.transient is not None
+    assert sw.describe() == "resident(%d of 3 row chunks, the rest streamed)" % n_res
+
+    def check(v, w, scale=1.0, w_scale=1.0):
+        out = torch.empty((M, T), dtype=torch.float32)
+        sw.dmmv(v, w, out, scale, w_scale)
+        ref = orc.dmmv(X, C, None if v is None else v.to(DT), None if w is None else w.to(DT) * w_scale, 3.0, DT) * scale
+        assert (out.to(DT) - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+    y = torch.randn(n, T, generator=g)
+    check(None, y, w_scale=1.0 / n)
+    assert [c[0] for c in store["calls"]] == ["tile", "panel"] * 3
+    for v, w in ((torch.randn(M, T, generator=g), None), (torch.randn(M, T, generator=g), y), (None, y)):
+        store["calls"].clear()
+        check(v, w, scale=0.5, w_scale=2.0)
+        first = ["panel"] if v is None else ["mmv", "panel"]
+        assert [c[0] for c in store["calls"]] == first * n_res + ["tile", "panel"] * (3 - n_res)
+
+
+def test_resident_plan(lib, monkeypatch):
+    from odf import ops
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    per = 4 * 131072 * 10112
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) == 8                  # everything fits
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=4.5 * per) == 3             # transient + 3 resident
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=1.5 * per) == 0             # stream everything
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", False)
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) == 0                  # two copies: 81 GB
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=90e9) == 8
