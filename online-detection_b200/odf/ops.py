@@ -16,6 +16,15 @@ LAUNCHES = 0
 TILE_EVENTS = None      # set to a list to record (start, stop, flops) per tile launch
 PANEL_EVENTS = None     # same for the panel contraction kernel
 PANEL_ROWS = 131072     # rows per spilled K panel (x pad_rows(M) x 4 B of transient workspace)
+# rows per RESIDENT panel when every chunk is resident = RESIDENT_MULT x PANEL_ROWS: resident panels are not
+# workspace, so a chunk may be larger -- fewer, longer launches of the panel kernels (C2 fit 0.460 -> 0.450 s at 4 x;
+# profiles/r1_resident_rows_v11.log).  Partially resident fits keep PANEL_ROWS (finer residency granularity).
+RESIDENT_MULT = int(os.environ.get("ODF_RESIDENT_MULT", "4"))
+
+
+def _resident_chunk(n_rows, all_resident=True):
+    rows = int(PANEL_ROWS) * (max(1, int(RESIDENT_MULT)) if all_resident else 1)
+    return min(rows // 128 * 128, (n_rows + 127) // 128 * 128)
 
 
 def _count(n):
@@ -508,7 +517,7 @@ class Sweeper:
         if mode == "auto":
             # as many row chunks resident as fit (single-copy variant: the rest is streamed through a transient panel)
             resident_chunks = resident_plan(rows.n, cols.n, dev)
-            mode = "resident" if resident_chunks > 0 else "panel16"
+            mode = "resident" if (resident_chunks is None or resident_chunks > 0) else "panel16"
         self.rows, self.cols, self.sigma, self.T, self.mode = rows, cols, sigma, int(T), mode
         if mode not in ("panel16", "panel", "recompute", "resident"):
             raise ValueError("unknown sweep mode %r" % (mode,))
@@ -530,7 +539,7 @@ class Sweeper:
             self.part3 = torch.empty((sum(self.pslabs), cols.n, Tp), dtype=torch.float32, device=dev)
         elif mode == "resident":
             M = cols.n
-            self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
+            self.chunk = _resident_chunk(rows.n, resident_chunks is None or not RESIDENT_SINGLE_COPY)
             self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
             self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
             sizes = sorted({r1 - r0 for (r0, r1) in self.chunks})
@@ -753,7 +762,7 @@ RESIDENT_SINGLE_COPY = os.environ.get("ODF_RESIDENT_SINGLE", "1") not in ("0", "
 def resident_bytes(n_rows, M):
     """Bytes of the resident fp16-plane panel sets (K and, unless RESIDENT_SINGLE_COPY, K^T) of an n_rows x M block."""
     L = _lib.load()
-    chunk = min(int(PANEL_ROWS), (n_rows + 127) // 128 * 128)
+    chunk = _resident_chunk(n_rows)
     total = 0
     for r0 in range(0, n_rows, chunk):
         n = min(n_rows, r0 + chunk) - r0
@@ -772,16 +781,16 @@ def resident_fits(n_rows, M, device):
 
 
 def resident_plan(n_rows, M, device, budget=None):
-    """How many row chunks of an n_rows x M block can stay resident (mode "auto").  All of them when the panels fit
+    """How many row chunks of an n_rows x M block can stay resident (mode "auto").  None = all of them: the panels fit
     into RESIDENT_FRACTION of the free device memory; otherwise (single-copy variant) as many as fit beside the
     transient panel the streamed chunks share; 0 = stream everything (mode "panel16")."""
     L = _lib.load()
     budget = RESIDENT_FRACTION * _free_bytes(device) if budget is None else budget
     if resident_bytes(n_rows, M) <= budget:
-        return -(-n_rows // min(int(PANEL_ROWS), (n_rows + 127) // 128 * 128))
+        return None                                                 # everything (chunks of _resident_chunk rows)
     if not RESIDENT_SINGLE_COPY:
         return 0
-    chunk = min(int(PANEL_ROWS), (n_rows + 127) // 128 * 128)
+    chunk = _resident_chunk(n_rows, all_resident=False)
     per_chunk = int(L.odf_panel16_bytes(chunk, M))
     k = int((budget - per_chunk) // per_chunk)                      # one transient panel + k resident ones
     return max(0, min(k, n_rows // chunk))

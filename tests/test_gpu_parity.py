@@ -322,6 +322,7 @@ def test_resident_sweeper_matches_oracle(odf, monkeypatch, n, M, d, T, chunk, si
     evaluates no kernel value.  Ragged chunks; every sweep against the fp64 oracle."""
     from odf import ops
     monkeypatch.setattr(ops, "PANEL_ROWS", chunk)
+    monkeypatch.setattr(ops, "RESIDENT_MULT", 1)
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", single)      # True: only K is kept, K v through odf_panel16_mmv
     X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
     C = X[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:M]]
@@ -361,6 +362,7 @@ def test_resident_partial_matches_oracle_and_fit(odf, monkeypatch):
     sweep level, 1 of 3 in a whole fit (plan forced through ops.resident_plan)."""
     from odf import ops
     monkeypatch.setattr(ops, "PANEL_ROWS", 1024)
+    monkeypatch.setattr(ops, "RESIDENT_MULT", 4)                   # partially resident fits keep PANEL_ROWS chunks
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
     n, M, d, T = 3333, 300, 64, 7
     X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
@@ -403,6 +405,7 @@ def test_resident_fit_matches_streaming_fit_and_oracle(odf, monkeypatch, single)
     """A whole fit in the resident mode against the streaming ("panel16") fit and the fp64 oracle."""
     from odf import ops
     monkeypatch.setattr(ops, "PANEL_ROWS", 4096)
+    monkeypatch.setattr(ops, "RESIDENT_MULT", 2 if single else 1)   # 12000 rows: 2 chunks of 8192 / 3 of 4096
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", single)
     d, T = 256, 21
     X, c, Y = orc.make_synthetic(12000, d, T, seed=0)

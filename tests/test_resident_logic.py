@@ -104,6 +104,7 @@ def emu(monkeypatch, lib):
                      ("SplitRhs", _FakeRhs)):
         monkeypatch.setattr(ops, name, fn)
     monkeypatch.setattr(ops, "PANEL_ROWS", 256)
+    monkeypatch.setattr(ops, "RESIDENT_MULT", 1)
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", False)
     return ops, store
 
@@ -166,9 +167,10 @@ def test_resident_sweeper_operator_first(emu):
 
 def test_resident_bytes_and_mode_names(lib):
     from odf import ops
-    # C2 on one GPU: 8 chunks x 4 B x pad(rows) x pad(centres) (x 2 orientations in the two-copy variant)
+    # C2 on one GPU: 4 B x pad(rows) x pad(centres) (x 2 orientations in the two-copy variant); 1 000 000 rows pad to
+    # 1 000 064 whatever the chunking (chunks are multiples of 128 rows)
     b = ops.resident_bytes(1_000_000, 10_000)
-    assert b == (1 if ops.RESIDENT_SINGLE_COPY else 2) * 4 * 10112 * (7 * 131072 + 82560)
+    assert b == (1 if ops.RESIDENT_SINGLE_COPY else 2) * 4 * 10112 * 1_000_064
     with pytest.raises(ValueError):
         ops.Sweeper(_FakePrepared(torch.zeros(4, 2)), _FakePrepared(torch.zeros(2, 2)), 1.0, 1, mode="nope")
 
@@ -245,10 +247,12 @@ def test_resident_partial_bookkeeping(emu, monkeypatch, n_res):
 def test_resident_plan(lib, monkeypatch):
     from odf import ops
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    assert ops._resident_chunk(1_000_000) == 4 * 131072 and ops._resident_chunk(1_000_000, all_resident=False) == 131072
+    assert ops._resident_chunk(1000) == 1024
     per = 4 * 131072 * 10112
-    assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) == 8                  # everything fits
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) is None               # everything fits
     assert ops.resident_plan(1_000_000, 10_000, None, budget=4.5 * per) == 3             # transient + 3 resident
     assert ops.resident_plan(1_000_000, 10_000, None, budget=1.5 * per) == 0             # stream everything
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", False)
     assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) == 0                  # two copies: 81 GB
-    assert ops.resident_plan(1_000_000, 10_000, None, budget=90e9) == 8
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=90e9) is None
