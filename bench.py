@@ -295,7 +295,7 @@ def run_ours(args):
         pass
     traffic_json = {}
     try:
-        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v9_traffic.json")))
+        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v12_traffic.json")))
     except Exception:  # noqa: BLE001
         pass
     sweep_mode = model.fit_times_.get("sweep_mode")
@@ -313,11 +313,15 @@ def run_ours(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else \
             "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
         # DRAM traffic: from the committed ncu --set full capture of the same launch shape
-        traffic, traffic_src = None, None
-        tk = traffic_json.get("gauss_tile2_kernel")
-        if tk and any((r, c_, dd) == (tk["rows"], tk["cols"], tk["d"]) for (_a, _b, r, c_, dd, _t) in tile_events):
-            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
-            traffic_src = traffic_json["source"]
+        traffic, traffic_src, best_n = None, None, 0
+        shapes = {}
+        for (_a, _b, r, c_, dd, _t) in tile_events:
+            shapes[(r, c_, dd)] = shapes.get((r, c_, dd), 0) + 1
+        for tk in traffic_json.get("gauss_tile2_kernel", []):      # the captured shape launched most often
+            if (tk["rows"], tk["cols"], tk["d"]) in shapes and (traffic is None or shapes[(tk["rows"], tk["cols"], tk["d"])] > best_n):
+                best_n = shapes[(tk["rows"], tk["cols"], tk["d"])]
+                traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+                traffic_src = traffic_json["source"] + " [%d x %d x %d launch]" % (tk["rows"], tk["cols"], tk["d"])
         return {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_unit": "bytes per launch (dram read + write)", "traffic_source": traffic_src,
@@ -342,11 +346,17 @@ def run_ours(args):
         t_ms, t_bytes, t_n = (sum(e[i] for e in per.values()) for i in range(3))
         p_gbs = t_bytes / max(t_ms, 1e-9) / 1e6
         traffic, traffic_src = None, None
-        for k in per:
-            tk = traffic_json.get(k)
-            if tk and any({n_, m_} == {tk["rows"], tk["cols"]} for (_a, _b, n_, m_, *_r) in panel_events):
-                traffic = max(traffic or 0, tk["dram_bytes_read"] + tk["dram_bytes_write"])
-                traffic_src = traffic_json["source"]
+        shapes = {}
+        for (_a, _b, n_, m_, *_r) in panel_events:
+            shapes[(n_, m_)] = shapes.get((n_, m_), 0) + 1
+        best_n = 0
+        for k in per:                                               # the captured shape launched most often
+            for tk in traffic_json.get(k, []):
+                cnt = shapes.get((tk["rows"], tk["cols"]), 0)
+                if cnt > best_n:
+                    best_n = cnt
+                    traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+                    traffic_src = traffic_json["source"] + " [%s, %d x %d panel]" % (k, tk["rows"], tk["cols"])
         return {"bound": "hbm", "kernel": " + ".join(sorted(per)), "achieved": p_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": p_gbs / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
                 "traffic_source": traffic_src,
