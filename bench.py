@@ -33,7 +33,9 @@ WORKLOADS = {
     "c3": (20_000_000, 256, 30_000, 21, 10.0, 1e-6),     # per-pixel mask head; needs --gpus 8 (or --n for one GPU's share)
     "c5": (1_000_000, 1024, 10_000, 30, 20.0, 1e-3),     # batched predict K(X, C) alpha (--workload c5 times predict, not fit)
 }
-CPU_SAMPLE = (20_000, 1_000)        # rows / centres of the CPU-baseline sample
+CPU_SAMPLE = (20_000, 1_000)        # rows / centres of the CPU-baseline sample (ODF_CPU_SAMPLE="rows,centres" overrides)
+if os.environ.get("ODF_CPU_SAMPLE"):
+    CPU_SAMPLE = tuple(int(v) for v in os.environ["ODF_CPU_SAMPLE"].split(","))
 
 
 def parse():
@@ -189,6 +191,77 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+# ------------------------------------------------------------------------------ roofline entries
+def tile_roofline(tile_events, steps, step_ms, peaks, traffic_json):
+    """The fused Gaussian tile (tensor bound).  A launch over (r rows x c centres) does the 2 r c d distance
+    product, the exp epilogue and the first contraction K.V (2 r c T); K is evaluated once per launch."""
+    tile_ms = [a.elapsed_time(b) for (a, b, *_rest) in tile_events]
+    tile_alg = [2.0 * r * c_ * dd + 2.0 * r * c_ * tt for (_a, _b, r, c_, dd, tt) in tile_events]
+    tile_exec = [6.0 * r * c_ * ((dd + 63) // 64 * 64) + 6.0 * r * c_ * (16 if tt <= 16 else 32)
+                 for (_a, _b, r, c_, dd, tt) in tile_events]
+    achieved = sum(tile_alg) / max(sum(tile_ms), 1e-9) / 1e9          # TFLOP/s, algorithmic
+    executed = sum(tile_exec) / max(sum(tile_ms), 1e-9) / 1e9         # TFLOP/s, tensor-pipe work issued
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else \
+        "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
+    # DRAM traffic: from the committed ncu --set full capture of the same launch shape
+    traffic, traffic_src, best_n = None, None, 0
+    shapes = {}
+    for (_a, _b, r, c_, dd, _t) in tile_events:
+        shapes[(r, c_, dd)] = shapes.get((r, c_, dd), 0) + 1
+    for tk in traffic_json.get("gauss_tile2_kernel", []):      # the captured shape launched most often
+        if (tk["rows"], tk["cols"], tk["d"]) in shapes and (traffic is None or shapes[(tk["rows"], tk["cols"], tk["d"])] > best_n):
+            best_n = shapes[(tk["rows"], tk["cols"], tk["d"])]
+            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+            traffic_src = traffic_json["source"] + " [%d x %d x %d launch]" % (tk["rows"], tk["cols"], tk["d"])
+    return {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_unit": "bytes per launch (dram read + write)", "traffic_source": traffic_src,
+            "peak_source": peak_src, "avg_launch_ms": sum(tile_ms) / max(len(tile_ms), 1), "launches_timed": len(tile_ms),
+            "share_of_step": sum(tile_ms) / steps / step_ms,
+            "executed_tensor_tflops": executed, "executed_frac_of_peak": executed / peak,
+            "note": "fp32-grade distances need 3 fp16 tensor passes per product (hi.hi + hi.lo + lo.hi, 2 x 11-bit "
+                    "split): algorithmic flops count each product once, so frac is capped at 1/3; "
+                    "executed_frac_of_peak is the tensor-pipe work actually issued over the same cuBLAS bf16 peak"}
+
+def panel_roofline(panel_events, steps, step_ms, peaks, traffic_json):
+    """The tensor-core panel contractions (HBM bound): each launch streams one fp16-plane panel, 4 B per kernel
+    value: panel16_kernel (K^T w) and, in the resident sweeps, panel16_mmv_kernel (K v from the same panel)."""
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
+    per = {}
+    for (a, b, n_, m_, _tp, *name) in panel_events:
+        k = name[0] if name else "panel16_kernel"
+        e = per.setdefault(k, [0.0, 0.0, 0])
+        e[0] += a.elapsed_time(b)
+        e[1] += 4.0 * ((n_ + 127) // 128 * 128) * ((m_ + 127) // 128 * 128)
+        e[2] += 1
+    t_ms, t_bytes, t_n = (sum(e[i] for e in per.values()) for i in range(3))
+    p_gbs = t_bytes / max(t_ms, 1e-9) / 1e6
+    traffic, traffic_src = None, None
+    shapes = {}
+    for (_a, _b, n_, m_, *_r) in panel_events:
+        shapes[(n_, m_)] = shapes.get((n_, m_), 0) + 1
+    best_n = 0
+    for k in per:                                               # the captured shape launched most often
+        for tk in traffic_json.get(k, []):
+            cnt = shapes.get((tk["rows"], tk["cols"]), 0)
+            if cnt > best_n:
+                best_n = cnt
+                traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+                traffic_src = traffic_json["source"] + " [%s, %d x %d panel]" % (k, tk["rows"], tk["cols"])
+    return {"bound": "hbm", "kernel": " + ".join(sorted(per)), "achieved": p_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": p_gbs / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+            "traffic_source": traffic_src,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read + write), of measured" if peaks else
+                           "fallback 6.65 TB/s (B200_PROFILING.md), of fallback",
+            "avg_launch_ms": t_ms / max(t_n, 1), "launches_timed": t_n,
+            "algorithmic_bytes_per_launch": t_bytes / max(t_n, 1),
+            "share_of_step": t_ms / steps / step_ms,
+            "per_kernel": {k: {"launches": e[2], "avg_launch_ms": e[0] / e[2], "GB/s": e[1] / e[0] / 1e6} for k, e in per.items()},
+            "note": "each launch streams one fp16 hi/lo K panel (4 B per kernel value) and contracts it with tcgen05 "
+                    "kind::f16 MMAs; a read-only stream, so it can exceed the read+write copy figure used as peak"}
+
+
 # ------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -300,79 +373,10 @@ def run_ours(args):
         pass
     sweep_mode = model.fit_times_.get("sweep_mode")
 
-    def tile_roofline(tile_events, steps, step_ms):
-        """The fused Gaussian tile (tensor bound).  A launch over (r rows x c centres) does the 2 r c d distance
-        product, the exp epilogue and the first contraction K.V (2 r c T); K is evaluated once per launch."""
-        tile_ms = [a.elapsed_time(b) for (a, b, *_rest) in tile_events]
-        tile_alg = [2.0 * r * c_ * dd + 2.0 * r * c_ * tt for (_a, _b, r, c_, dd, tt) in tile_events]
-        tile_exec = [6.0 * r * c_ * ((dd + 63) // 64 * 64) + 6.0 * r * c_ * (16 if tt <= 16 else 32)
-                     for (_a, _b, r, c_, dd, tt) in tile_events]
-        achieved = sum(tile_alg) / max(sum(tile_ms), 1e-9) / 1e9          # TFLOP/s, algorithmic
-        executed = sum(tile_exec) / max(sum(tile_ms), 1e-9) / 1e9         # TFLOP/s, tensor-pipe work issued
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else \
-            "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
-        # DRAM traffic: from the committed ncu --set full capture of the same launch shape
-        traffic, traffic_src, best_n = None, None, 0
-        shapes = {}
-        for (_a, _b, r, c_, dd, _t) in tile_events:
-            shapes[(r, c_, dd)] = shapes.get((r, c_, dd), 0) + 1
-        for tk in traffic_json.get("gauss_tile2_kernel", []):      # the captured shape launched most often
-            if (tk["rows"], tk["cols"], tk["d"]) in shapes and (traffic is None or shapes[(tk["rows"], tk["cols"], tk["d"])] > best_n):
-                best_n = shapes[(tk["rows"], tk["cols"], tk["d"])]
-                traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
-                traffic_src = traffic_json["source"] + " [%d x %d x %d launch]" % (tk["rows"], tk["cols"], tk["d"])
-        return {"bound": "tensor", "kernel": "gauss_tile2_kernel<f16 split operands, CTA pair>", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_unit": "bytes per launch (dram read + write)", "traffic_source": traffic_src,
-                "peak_source": peak_src, "avg_launch_ms": sum(tile_ms) / max(len(tile_ms), 1), "launches_timed": len(tile_ms),
-                "share_of_step": sum(tile_ms) / steps / step_ms,
-                "executed_tensor_tflops": executed, "executed_frac_of_peak": executed / peak,
-                "note": "fp32-grade distances need 3 fp16 tensor passes per product (hi.hi + hi.lo + lo.hi, 2 x 11-bit "
-                        "split): algorithmic flops count each product once, so frac is capped at 1/3; "
-                        "executed_frac_of_peak is the tensor-pipe work actually issued over the same cuBLAS bf16 peak"}
-
-    def panel_roofline(panel_events, steps, step_ms):
-        """The tensor-core panel contractions (HBM bound): each launch streams one fp16-plane panel, 4 B per kernel
-        value: panel16_kernel (K^T w) and, in the resident sweeps, panel16_mmv_kernel (K v from the same panel)."""
-        hbm_peak = peaks.get("hbm_gbs") or 6650.0
-        per = {}
-        for (a, b, n_, m_, _tp, *name) in panel_events:
-            k = name[0] if name else "panel16_kernel"
-            e = per.setdefault(k, [0.0, 0.0, 0])
-            e[0] += a.elapsed_time(b)
-            e[1] += 4.0 * ((n_ + 127) // 128 * 128) * ((m_ + 127) // 128 * 128)
-            e[2] += 1
-        t_ms, t_bytes, t_n = (sum(e[i] for e in per.values()) for i in range(3))
-        p_gbs = t_bytes / max(t_ms, 1e-9) / 1e6
-        traffic, traffic_src = None, None
-        shapes = {}
-        for (_a, _b, n_, m_, *_r) in panel_events:
-            shapes[(n_, m_)] = shapes.get((n_, m_), 0) + 1
-        best_n = 0
-        for k in per:                                               # the captured shape launched most often
-            for tk in traffic_json.get(k, []):
-                cnt = shapes.get((tk["rows"], tk["cols"]), 0)
-                if cnt > best_n:
-                    best_n = cnt
-                    traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
-                    traffic_src = traffic_json["source"] + " [%s, %d x %d panel]" % (k, tk["rows"], tk["cols"])
-        return {"bound": "hbm", "kernel": " + ".join(sorted(per)), "achieved": p_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": p_gbs / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
-                "traffic_source": traffic_src,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read + write), of measured" if peaks else
-                               "fallback 6.65 TB/s (B200_PROFILING.md), of fallback",
-                "avg_launch_ms": t_ms / max(t_n, 1), "launches_timed": t_n,
-                "algorithmic_bytes_per_launch": t_bytes / max(t_n, 1),
-                "share_of_step": t_ms / steps / step_ms,
-                "per_kernel": {k: {"launches": e[2], "avg_launch_ms": e[0] / e[2], "GB/s": e[1] / e[0] / 1e6} for k, e in per.items()},
-                "note": "each launch streams one fp16 hi/lo K panel (4 B per kernel value) and contracts it with tcgen05 "
-                        "kind::f16 MMAs; a read-only stream, so it can exceed the read+write copy figure used as peak"}
-
     # dominant kernel = the one with the larger share of the step.  "resident" sweeps: the panel kernel (two passes
     # over the resident K / K^T panels per sweep, HBM bound); streaming sweeps: the fused tile (tensor bound).
-    r_tile = tile_roofline(tile_events, args.steps, ms_dev) if tile_events else None
-    r_panel = panel_roofline(panel_events, args.steps, ms_dev) if panel_events else None
+    r_tile = tile_roofline(tile_events, args.steps, ms_dev, peaks, traffic_json) if tile_events else None
+    r_panel = panel_roofline(panel_events, args.steps, ms_dev, peaks, traffic_json) if panel_events else None
     if r_panel is not None and (r_tile is None or r_panel["share_of_step"] > r_tile["share_of_step"]):
         roofline = dict(r_panel)
         roofline["other_kernel"] = r_tile
@@ -419,7 +423,7 @@ def run_ours(args):
         t_ev, ops.TILE_EVENTS = ops.TILE_EVENTS, None
         p_ev, ops.PANEL_EVENTS = ops.PANEL_EVENTS, None
         streaming = {"sweep_mode": "panel16", "steps": 2, "warmup": 1, "fit_s": ms_s * 1e-3, "value": F / (ms_s * 1e-3) / 1e9,
-                     "unit": "GFLOP/s", "tile_kernel": tile_roofline(t_ev, 2, ms_s), "panel_kernel": panel_roofline(p_ev, 2, ms_s),
+                     "unit": "GFLOP/s", "tile_kernel": tile_roofline(t_ev, 2, ms_s, peaks, traffic_json), "panel_kernel": panel_roofline(p_ev, 2, ms_s, peaks, traffic_json),
                      "note": "K_nm never materialised beyond one transient row-chunk panel: every sweep re-evaluates K on "
                              "the tensor cores (the fused tile is the dominant kernel of this mode)"}
 

@@ -512,12 +512,26 @@ class Sweeper:
     forward tile pass."""
 
     def __init__(self, rows, cols, sigma, T, mode="panel16", resident_chunks=None):
+        auto = mode == "auto"
+        if auto:
+            # as many row chunks resident as fit (single-copy variant: the rest is streamed through a transient panel)
+            resident_chunks = resident_plan(rows.n, cols.n, rows.hi.device)
+            mode = "resident" if (resident_chunks is None or resident_chunks > 0) else "panel16"
+        try:
+            self._setup(rows, cols, sigma, T, mode, resident_chunks)
+        except torch.OutOfMemoryError:
+            if not (auto and mode == "resident"):
+                raise
+            # the plan was too optimistic (fragmentation, another allocation in between): stream instead
+            for k in list(self.__dict__):
+                delattr(self, k)
+            if rows.hi.is_cuda:
+                torch.cuda.empty_cache()
+            self._setup(rows, cols, sigma, T, "panel16", None)
+
+    def _setup(self, rows, cols, sigma, T, mode, resident_chunks):
         L = _lib.load()
         dev = rows.hi.device
-        if mode == "auto":
-            # as many row chunks resident as fit (single-copy variant: the rest is streamed through a transient panel)
-            resident_chunks = resident_plan(rows.n, cols.n, dev)
-            mode = "resident" if (resident_chunks is None or resident_chunks > 0) else "panel16"
         self.rows, self.cols, self.sigma, self.T, self.mode = rows, cols, sigma, int(T), mode
         if mode not in ("panel16", "panel", "recompute", "resident"):
             raise ValueError("unknown sweep mode %r" % (mode,))

@@ -256,3 +256,33 @@ def test_resident_plan(lib, monkeypatch):
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", False)
     assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) == 0                  # two copies: 81 GB
     assert ops.resident_plan(1_000_000, 10_000, None, budget=90e9) is None
+
+
+def test_auto_mode_falls_back_to_streaming_when_the_panels_do_not_fit_after_all(emu, monkeypatch):
+    """mode "auto": an out-of-memory error while allocating the resident panels (plan too optimistic) is not fatal."""
+    ops, store = emu
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    monkeypatch.setattr(ops, "resident_plan", lambda n_rows, M, dev, budget=None: None)
+    real_alloc, calls = ops.alloc_partial, {"n": 0}
+
+    def flaky_alloc(rows, cols, T_pad, device):
+        calls["n"] += 1
+        if calls["n"] == 1:
+            raise torch.OutOfMemoryError("simulated")
+        return real_alloc(rows, cols, T_pad, device)
+
+    monkeypatch.setattr(ops, "alloc_partial", flaky_alloc)
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(300, 8, generator=g, dtype=DT)
+    C = X[:64]
+    sw = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 2.0, 3, mode="auto")
+    assert sw.mode == "panel16" and sw.describe() == "panel16" and not hasattr(sw, "fwd")
+    v = torch.randn(64, 3, generator=g)
+    out = torch.empty((64, 3), dtype=torch.float32)
+    sw.dmmv(v, None, out)
+    ref = orc.dmmv(X, C, v.to(DT), None, 2.0, DT)
+    assert (out.to(DT) - ref).abs().max() <= 2e-5 * ref.abs().max()
+    # an explicit "resident" request does not hide the error
+    calls["n"] = 0
+    with pytest.raises(torch.OutOfMemoryError):
+        ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 2.0, 3, mode="resident")
