@@ -52,6 +52,11 @@ class FalkonOptions:
         # value: 81 GB at N = 1 M, M = 10 k); "auto" (default): "resident" when that fits in the free device
         # memory, else "panel16".  ODF_SWEEP_MODE overrides the default.
         self.sweep_mode = ignored.pop("sweep_mode", None) or os.environ.get("ODF_SWEEP_MODE") or "auto"
+        # run the right-hand side sweep K_nm^T y (which also fills the resident K panels: tensor pipe + HBM) on a side
+        # stream while the main stream builds the preconditioner (SIMT GEMMs and latency-bound Cholesky panels); the
+        # two only meet at B = A^-T T^-T K_nm^T y.  ODF_OVERLAP_RHS=1/0 overrides the default.
+        ov = ignored.pop("overlap_rhs", None)
+        self.overlap_rhs = (os.environ.get("ODF_OVERLAP_RHS", "0") not in ("0", "")) if ov is None else bool(ov)
         # multi-GPU fits split T T^T and the explicit inverses over the ranks as column blocks (all-gathered); below
         # 4 ranks the replicated triangle-aware build is as fast and skips the M x M gathers.  None = by world size.
         self.distributed_precond = ignored.pop("distributed_precond", None)
@@ -346,9 +351,38 @@ class Falkon:
             centres = be.zscore_(centres.clone(), zs[0], zs[1])     # ny_points_ live in normalised space
         tm.mark()
 
+        # ---- right-hand side sweep of the first column block on a side stream (optional), preconditioner on the main one
+        pre = None
+        overlap = bool(getattr(opt, "overlap_rhs", False)) and dev.type == "cuda" and getattr(be, "__name__", "") == ops.__name__ \
+            and n_local > 0
+        if overlap:
+            main = torch.cuda.current_stream(dev)
+            side2 = torch.cuda.Stream(dev)
+            Tb = min(T, 32)
+            side2.wait_stream(main)
+            if upload is not None:
+                side2.wait_event(upload)                             # rows / labels arrive on their own stream
+            with torch.cuda.stream(side2):
+                if upload is not None:
+                    px = be.Prepared(X, zs[0], zs[1], kind=kind)     # prepared behind the copy, off the main stream
+                Yb0 = Y[:, :Tb].contiguous()
+            for t_ in (px.hi, px.lo, px.sqn, px.opscale, Yb0, X, Y):
+                t_.record_stream(main)                               # allocated on one stream, used on both
+                t_.record_stream(side2)
+            sw0 = be.Sweeper(px, pc, sigma, Tb, mode=opt.sweep_mode)  # allocations (and zero fills) on the main stream
+            c0 = torch.empty((M, Tb), dtype=torch.float32, device=dev)
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):
+                sw0.dmmv(None, Yb0, c0, 1.0, 1.0 / N)                # local rows; reduced over the ranks after the build
+            pre = (sw0, c0, Yb0)
+
         # ---- preconditioner (built once per fit; the factors end up replicated on every rank) ----
         Tm, Am = self._build_preconditioner(be, pc, sigma, lam, dist if world > 1 else None, group, world)
-        if upload is not None:
+        if overlap:
+            torch.cuda.current_stream(dev).wait_stream(side2)
+            if world > 1:
+                dist.all_reduce(pre[1], group=group)
+        elif upload is not None:
             torch.cuda.current_stream(dev).wait_event(upload)        # the rows have arrived by now
             px = be.Prepared(X, zs[0], zs[1], kind=kind) if n_local > 0 else None
         tm.mark()
@@ -357,8 +391,8 @@ class Falkon:
         iters = 0
         for t0 in range(0, T, 32):
             t1 = min(T, t0 + 32)
-            it = self._solve_block(px, pc, Y[:, t0:t1].contiguous(), Tm, Am, N, sigma, lam, alpha[:, t0:t1],
-                                   dist if world > 1 else None, group)
+            it = self._solve_block(px, pc, Y[:, t0:t1].contiguous() if (pre is None or t0 > 0) else pre[2], Tm, Am, N, sigma,
+                                   lam, alpha[:, t0:t1], dist if world > 1 else None, group, pre=pre if t0 == 0 else None)
             iters = max(iters, it)
         tm.mark()
         self.ny_points_ = centres
@@ -461,13 +495,18 @@ class Falkon:
         if prof: prof.report()
         return factors[0], factors[1]
 
-    def _solve_block(self, px, pc, Yb, Tm, Am, N, sigma, lam, alpha_out, dist, group):
+    def _solve_block(self, px, pc, Yb, Tm, Am, N, sigma, lam, alpha_out, dist, group, pre=None):
+        """`pre` = (sweeper, K_nm^T y / N already reduced over the ranks, y block): the right-hand side sweep was run
+        ahead of the preconditioner on a side stream (fit, overlap_rhs)."""
         be = self._be
         opt = self.options
         dev = pc.hi.device
         M, T = pc.n, Yb.shape[1]
         eps, tol = opt.cg_epsilon_32, opt.cg_tolerance
-        sw = be.Sweeper(px, pc, sigma, T, mode=opt.sweep_mode) if px is not None else None
+        if pre is not None:
+            sw = pre[0]
+        else:
+            sw = be.Sweeper(px, pc, sigma, T, mode=opt.sweep_mode) if px is not None else None
         self._sweep_mode = sw.describe() if hasattr(sw, "describe") else getattr(sw, "mode", opt.sweep_mode)
         new = lambda: torch.empty((M, T), dtype=torch.float32, device=dev)  # noqa: E731
         B, R, P, AP, beta, v, u, c, H, H2 = (new() for _ in range(10))
@@ -485,7 +524,11 @@ class Falkon:
             return out
 
         # B = apply_t(K_nm^T (Y / N)) = A^-T T^-T K_nm^T (Y / N)
-        sweep(None, Yb, c, 1.0 / N)
+        if pre is not None:
+            c.copy_(pre[1])
+            self._sweeps += 1
+        else:
+            sweep(None, Yb, c, 1.0 / N)
         Am.solve(Tm.solve(c, u, True), B, True)
 
         def op(s, out):

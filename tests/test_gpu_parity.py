@@ -443,6 +443,32 @@ def test_fit_from_host_memory_matches_device_fit(odf):
     assert torch.equal(m.alpha_, base.alpha_) and m.ny_points_.is_cuda
 
 
+def test_overlapped_rhs_sweep_is_bitwise_the_default_fit(odf, monkeypatch):
+    """overlap_rhs: the right-hand side sweep (which fills the resident panels) runs on a side stream while the main
+    stream builds the preconditioner.  Same kernels in the same order per stream, so alpha is bitwise the default
+    fit's: device-resident and host-resident inputs, one and several row chunks, and > 32 classes (only the first
+    column block is run ahead)."""
+    from odf import ops
+    monkeypatch.setattr(ops, "PANEL_ROWS", 4096)
+    monkeypatch.setattr(ops, "RESIDENT_MULT", 1)
+    X, c, Y = orc.make_synthetic(9000, 128, 3, seed=2)
+    C = X[orc.shared_centres(c, 300, seed=1)]
+    base = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(overlap_rhs=False))
+    for Xi, Yi in ((X.cuda(), Y.cuda()), (X.pin_memory(), Y.pin_memory()), (X, Y)):
+        for _ in range(2):
+            m = odf.InCoreFalkon(kernel=odf.GaussianKernel(15.0), penalty=1e-4, M=300, options=odf.FalkonOptions(overlap_rhs=True))
+            m.fit(Xi, Yi, centres=C.cuda())
+            assert m.fit_times_["sweeps"] == 23 and torch.equal(m.alpha_, base.alpha_)
+    Y40 = torch.sign(torch.randn(9000, 40, generator=torch.Generator().manual_seed(3)))
+    a = _gpu_fit(odf, X, Y40, C, 15.0, 1e-4, options=odf.FalkonOptions(overlap_rhs=False))
+    b = _gpu_fit(odf, X, Y40, C, 15.0, 1e-4, options=odf.FalkonOptions(overlap_rhs=True))
+    assert torch.equal(a.alpha_, b.alpha_)
+    for mode in ("panel16", "recompute"):
+        a = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(overlap_rhs=False, sweep_mode=mode))
+        b = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(overlap_rhs=True, sweep_mode=mode))
+        assert torch.equal(a.alpha_, b.alpha_)
+
+
 def test_recompute_and_trsm_options_agree_with_default(odf):
     X, c, Y = orc.make_synthetic(5000, 128, 3, seed=2)
     C = X[orc.shared_centres(c, 300, seed=1)]
