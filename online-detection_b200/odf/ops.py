@@ -706,6 +706,26 @@ class Sweeper:
             self.part1 = None                                       # only the filling pass needs the tile's slabs
         return finish_rows(self.part3, T, out, scale)
 
+    def record_stream(self, stream):
+        """Mark every buffer of the Sweeper as in use on `stream` (torch.Tensor.record_stream): needed when a sweep is
+        launched on a stream other than the one the Sweeper was built on, because buffers the sweep drops (the tile's
+        slab buffer after the panel-filling pass) would otherwise be handed out again while that sweep still runs."""
+        def walk(v):
+            if isinstance(v, torch.Tensor):
+                if v.is_cuda:
+                    v.record_stream(stream)
+            elif isinstance(v, dict):
+                for x in v.values():
+                    walk(x)
+            elif isinstance(v, (list, tuple)):
+                for x in v:
+                    walk(x)
+            elif isinstance(v, SplitRhs):
+                for name in SplitRhs.__slots__:
+                    walk(getattr(v, name, None))
+        for v in self.__dict__.values():
+            walk(v)
+
     def describe(self):
         if self.mode != "resident":
             return self.mode

@@ -277,6 +277,7 @@ def test_auto_mode_falls_back_to_streaming_when_the_panels_do_not_fit_after_all(
     C = X[:64]
     sw = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 2.0, 3, mode="auto")
     assert sw.mode == "panel16" and sw.describe() == "panel16" and not hasattr(sw, "fwd")
+    sw.record_stream(None)                                         # walks every buffer; host tensors are skipped
     v = torch.randn(64, 3, generator=g)
     out = torch.empty((64, 3), dtype=torch.float32)
     sw.dmmv(v, None, out)
