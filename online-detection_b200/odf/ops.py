@@ -721,7 +721,7 @@ class Sweeper:
                 for x in v:
                     walk(x)
             elif isinstance(v, SplitRhs):
-                for name in SplitRhs.__slots__:
+                for name in (getattr(type(v), "__slots__", None) or list(getattr(v, "__dict__", {}))):
                     walk(getattr(v, name, None))
         for v in self.__dict__.values():
             walk(v)
