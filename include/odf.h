@@ -102,12 +102,12 @@ int odf_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, i
                   int n_splits, float* out_partial, void* stream);
 /* Tensor-core variant of the spill + panel pair (the default sweep): the tile writes its K tiles as two fp16
  * planes, hi = rn16(K) and lo = rn16((K - hi) 2^12), tile-blocked
- * [plane][column tile][row block][half][128 rows][64 centres] (odf_panel16_bytes(n_rows, n_cols) bytes,
+ * [plane][column tile][row block][16 groups of 8 centres][128 rows][8] (odf_panel16_bytes(n_rows, n_cols) bytes,
  * 128-byte aligned); odf_finish_w16 reduces the partial slabs of the first contraction into W = K v (+ addend)
  * [n_rows x T_pad] and splits it into W16 [round_up(n_rows,128) x 64] fp16 (hi | lo, per-column power-of-two
  * scales derived from max|W[:, t]|, left in absmax[32]); odf_panel16_tmm streams the planes once from HBM and contracts
  * out_partial[s][c][0..T_pad) = sum_r K[r][c] W[r][.] with tcgen05 kind::f16 MMAs on MN-major operands
- * (three split products, fp32 accumulation chains of 2048 rows).  n_splits = odf_panel16_splits(n_rows, M).
+ * (three split products, fp32 accumulation chains of 512 rows).  n_splits = odf_panel16_splits(n_rows, M).
  * Replaces the K_blk^T w half of falkon GaussianKernel.dmmv (...incore.py:68).                               */
 size_t odf_panel16_bytes(int64_t n_rows, int64_t n_cols);
 /* CTA-pair variant of the fused tile (cta_group::2, M = 256 per MMA: each CTA of a 2-CTA cluster loads half of every
