@@ -300,6 +300,16 @@ int odf_panel16_tmm(const void* panel16, int64_t n_rows, int64_t M, const void* 
   return launch_panel16_tmm(panel16, n_rows, M, w16, static_cast<const uint32_t*>(absmax), T_pad, n_splits, out_partial,
                             static_cast<cudaStream_t>(stream));
 }
+int odf_panel16_tmm_hi(const void* panel16, int64_t n_rows, int64_t M, const void* w16, const void* absmax, int T_pad,
+                       int n_splits, float* out_partial, void* stream) {
+  return launch_panel16_tmm(panel16, n_rows, M, w16, static_cast<const uint32_t*>(absmax), T_pad, n_splits, out_partial,
+                            static_cast<cudaStream_t>(stream), 1);
+}
+int odf_panel16_mmv_hi(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax, int T_pad,
+                       int n_splits, float* out_partial, void* stream) {
+  return launch_panel16_mmv(panel16, n_rows, M, v16, static_cast<const uint32_t*>(absmax), T_pad, n_splits, out_partial,
+                            static_cast<cudaStream_t>(stream), 1);
+}
 int odf_panel16_mmv_splits(int64_t n_rows, int64_t M) { return panel16_mmv_splits(n_rows, M); }
 int odf_panel16_mmv(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax, int T_pad,
                     int n_splits, float* out_partial, void* stream) {

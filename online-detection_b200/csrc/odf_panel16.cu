@@ -66,6 +66,9 @@ struct Panel16Params {
   float* out;             // [n_rsplit][M][T_pad]
 };
 
+// HI_ONLY = 1 (experimental precision tier): only the hi plane is streamed (2 B per kernel value, 11 bits of
+// K): the lo loads, the acc2 MMAs and the lo.hi term of the read-out are dropped.
+template <int HI_ONLY>
 __global__ void __launch_bounds__(256, 1)
 panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmW, const Panel16Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -122,12 +125,14 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
           // [total x 1024] fp16 view, one row per (plane, j, rb, g) holding [128 rows][8]; a box is 16 g x 32 rows
           const int y = (j * p.n_rb + (st >> 1)) * 16;
           const int x = (st & 1) * 512;
-          mbar_arrive_expect_tx(full, QSTAGE);
+          mbar_arrive_expect_tx(full, HI_ONLY ? QSTAGE - 2 * QBOX : QSTAGE);
           // the planes are read exactly once (evict first); W16 is shared by every column tile (evict last)
           tma_load_2d_hint(dst + 0 * QBOX, &tmP, full, x, y, kEvictFirst);
           tma_load_2d_hint(dst + 1 * QBOX, &tmP, full, x + 256, y, kEvictFirst);
-          tma_load_2d_hint(dst + 2 * QBOX, &tmP, full, x, p.plane_rows + y, kEvictFirst);
-          tma_load_2d_hint(dst + 3 * QBOX, &tmP, full, x + 256, p.plane_rows + y, kEvictFirst);
+          if (!HI_ONLY) {
+            tma_load_2d_hint(dst + 2 * QBOX, &tmP, full, x, p.plane_rows + y, kEvictFirst);
+            tma_load_2d_hint(dst + 3 * QBOX, &tmP, full, x + 256, p.plane_rows + y, kEvictFirst);
+          }
           tma_load_2d_hint(dst + 4 * QBOX, &tmW, full, 0, st * QR, kEvictLast);
           if (++stage == QNS) { stage = 0; phase ^= 1; }
         }
@@ -162,7 +167,7 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             const uint64_t b_w = kSdescMnHi | static_cast<uint64_t>(sd + ((4 * QBOX + kk * 2048) >> 4));
             const uint32_t accum = (first && kk == 0) ? 0u : 1u;
             mma_f16_ss(t_acc, a_hi, b_w, kIdesc, accum);
-            mma_f16_ss(t_acc + 64, a_lo, b_w, kIdesc, accum);
+            if (!HI_ONLY) mma_f16_ss(t_acc + 64, a_lo, b_w, kIdesc, accum);
           }
           tc_commit(BAR(B_EMPTY + stage));
           if (((local + 1) % QFLUSH) == 0 || st == st1 - 1) {
@@ -196,10 +201,15 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         uint32_t r[32];
         float tmp[32];
         __syncwarp();
-        tmem_ld32(t_acc + 64, r);                         // lo.hi  (x 2^-12)
-        tc_wait_ld();
+        if (!HI_ONLY) {
+          tmem_ld32(t_acc + 64, r);                       // lo.hi  (x 2^-12)
+          tc_wait_ld();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * (1.f / 4096.f);
+          for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * (1.f / 4096.f);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) tmp[t] = 0.f;
+        }
         tmem_ld32(t_acc + 32, r);                         // hi.lo  (x 2^-11)
         tc_wait_ld();
 #pragma unroll
@@ -272,6 +282,7 @@ struct Panel16VParams {
   float* out;             // [n_csplit][n_rows][T_pad]
 };
 
+template <int HI_ONLY>
 __global__ void __launch_bounds__(256, 1)
 panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -324,9 +335,9 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
           const uint32_t dst = smem_u32(smem) + stage * VSTAGE;
           // 8 centre groups of column tile j = st / 2, half st % 2: 16 KB of contiguous panel per plane
           const __half* src = p.P + ((static_cast<int64_t>(st >> 1) * p.n_rb + rb) * 16 + (st & 1) * 8) * 1024;
-          mbar_arrive_expect_tx(full, VSTAGE);
+          mbar_arrive_expect_tx(full, HI_ONLY ? VSTAGE - VA : VSTAGE);
           bulk_g2s_hint(dst, src, VA, full, kEvictFirst);
-          bulk_g2s_hint(dst + VA, src + p.plane_elems, VA, full, kEvictFirst);
+          if (!HI_ONLY) bulk_g2s_hint(dst + VA, src + p.plane_elems, VA, full, kEvictFirst);
           tma_load_2d_hint(dst + 2 * VA, &tmV, full, 0, st * QR, kEvictLast);
           if (++stage == QNS) { stage = 0; phase ^= 1; }
         }
@@ -360,7 +371,7 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
             const uint64_t b_v = kSdescMnHi | static_cast<uint64_t>(sd + ((2 * VA + kk * 2048) >> 4));
             const uint32_t accum = (first && kk == 0) ? 0u : 1u;
             mma_f16_ss(t_acc, a_hi, b_v, kIdescV, accum);
-            mma_f16_ss(t_acc + 64, a_lo, b_v, kIdescV, accum);
+            if (!HI_ONLY) mma_f16_ss(t_acc + 64, a_lo, b_v, kIdescV, accum);
           }
           tc_commit(BAR(B_EMPTY + stage));
           if (((local + 1) % QFLUSH) == 0 || st == st1 - 1) {
@@ -394,10 +405,15 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
         uint32_t r[32];
         float tmp[32];
         __syncwarp();
-        tmem_ld32(t_acc + 64, r);                         // lo.hi  (x 2^-12)
-        tc_wait_ld();
+        if (!HI_ONLY) {
+          tmem_ld32(t_acc + 64, r);                       // lo.hi  (x 2^-12)
+          tc_wait_ld();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * (1.f / 4096.f);
+          for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * (1.f / 4096.f);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) tmp[t] = 0.f;
+        }
         tmem_ld32(t_acc + 32, r);                         // hi.lo  (x 2^-11)
         tc_wait_ld();
 #pragma unroll
@@ -467,14 +483,15 @@ int panel16_splits(int64_t n_rows, int64_t M) {
 }
 
 int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W16, const uint32_t* absmax, int T_pad,
-                       int n_splits, float* out_partial, cudaStream_t st) {
+                       int n_splits, float* out_partial, cudaStream_t st, int hi_only) {
   if (n_rows <= 0 || M <= 0 || (T_pad != 16 && T_pad != 32) || (reinterpret_cast<uintptr_t>(P16) & 127) != 0 ||
       (reinterpret_cast<uintptr_t>(W16) & 127) != 0 || (reinterpret_cast<uintptr_t>(out_partial) & 15) != 0 || !absmax || (reinterpret_cast<uintptr_t>(absmax) & 15) != 0)
     return set_error(ODF_ERR_ARG, "panel16_tmm: bad shape or alignment (P16, W16 128-byte aligned; T_pad 16 or 32)");
   if (n_splits != panel16_splits(n_rows, M)) return set_error(ODF_ERR_ARG, "panel16_tmm: n_splits must come from odf_panel16_splits");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(panel16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
+    cudaError_t e = cudaFuncSetAttribute(panel16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(panel16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(panel16_kernel)");
     attr_set = true;
   }
@@ -502,7 +519,8 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
   const int n_items = p.n_ct * p.n_rsplit;
   const int sms = q_num_sms();
   const int grid = n_items < sms ? n_items : sms;
-  panel16_kernel<<<grid, 256, QSMEM, st>>>(tmP, tmW, p);
+  if (hi_only) panel16_kernel<1><<<grid, 256, QSMEM, st>>>(tmP, tmW, p);
+  else panel16_kernel<0><<<grid, 256, QSMEM, st>>>(tmP, tmW, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "panel16_kernel launch");
   return ODF_OK;
@@ -513,14 +531,15 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
 int panel16_mmv_splits(int64_t n_rows, int64_t M) { return panel16_splits(round_up(M, 128), n_rows); }
 
 int launch_panel16_mmv(const void* P16, int64_t n_rows, int64_t M, const void* V16, const uint32_t* absmax, int T_pad,
-                       int n_splits, float* out_partial, cudaStream_t st) {
+                       int n_splits, float* out_partial, cudaStream_t st, int hi_only) {
   if (n_rows <= 0 || M <= 0 || (T_pad != 16 && T_pad != 32) || (reinterpret_cast<uintptr_t>(P16) & 127) != 0 ||
       (reinterpret_cast<uintptr_t>(V16) & 127) != 0 || (reinterpret_cast<uintptr_t>(out_partial) & 15) != 0 || !absmax || (reinterpret_cast<uintptr_t>(absmax) & 15) != 0)
     return set_error(ODF_ERR_ARG, "panel16_mmv: bad shape or alignment (P16, V16 128-byte aligned; T_pad 16 or 32)");
   if (n_splits != panel16_mmv_splits(n_rows, M)) return set_error(ODF_ERR_ARG, "panel16_mmv: n_splits must come from odf_panel16_mmv_splits");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(panel16_mmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
+    cudaError_t e = cudaFuncSetAttribute(panel16_mmv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(panel16_mmv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(panel16_mmv_kernel)");
     attr_set = true;
   }
@@ -546,7 +565,8 @@ int launch_panel16_mmv(const void* P16, int64_t n_rows, int64_t M, const void* V
   const int n_items = p.n_rb * p.n_csplit;
   const int sms = q_num_sms();
   const int grid = n_items < sms ? n_items : sms;
-  panel16_mmv_kernel<<<grid, 256, QSMEM, st>>>(tmV, p);
+  if (hi_only) panel16_mmv_kernel<1><<<grid, 256, QSMEM, st>>>(tmV, p);
+  else panel16_mmv_kernel<0><<<grid, 256, QSMEM, st>>>(tmV, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "panel16_mmv_kernel launch");
   return ODF_OK;

@@ -44,6 +44,8 @@ SIGNATURES = {
     "odf_panel16_tmm": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),
     "odf_panel16_mmv_splits": (c_int, [c_i64, c_i64]),
     "odf_panel16_mmv": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),
+    "odf_panel16_tmm_hi": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),
+    "odf_panel16_mmv_hi": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),
     "odf_finish_rows": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_i64, c_fp]),
     "odf_finish_split": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_f, c_fp, c_i64, c_fp, c_fp,
                                  c_i64, c_fp]),

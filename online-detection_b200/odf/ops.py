@@ -253,8 +253,9 @@ def finish_w16(partial, T, Wf, absmax, W16, addend=None):
     return W16
 
 
-def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial):
-    """out_partial[s] = K[rows of range s]^T @ W from the fp16-plane panel (tcgen05 kind::f16, HBM-streaming)."""
+def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial, hi_only=False):
+    """out_partial[s] = K[rows of range s]^T @ W from the fp16-plane panel (tcgen05 kind::f16, HBM-streaming).
+    hi_only (experimental): stream the hi plane only (K to 11 bits, half the bytes)."""
     L = _lib.load()
     S, M_, T_pad = out_partial.shape
     assert M_ == M and S == int(L.odf_panel16_splits(n_rows, M)) and out_partial.is_contiguous()
@@ -262,15 +263,15 @@ def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial):
     if PANEL_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    check(L.odf_panel16_tmm(ptr(panel16), n_rows, M, ptr(W16), ptr(absmax), T_pad, S, ptr(out_partial), _stream()),
-          "odf_panel16_tmm")
+    fn = L.odf_panel16_tmm_hi if hi_only else L.odf_panel16_tmm
+    check(fn(ptr(panel16), n_rows, M, ptr(W16), ptr(absmax), T_pad, S, ptr(out_partial), _stream()), "odf_panel16_tmm")
     if ev is not None:
         ev[1].record()
-        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_kernel"))
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_kernel<hi>" if hi_only else "panel16_kernel"))
     _count(1)
 
 
-def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial):
+def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial, hi_only=False):
     """out_partial[s] = K[:, column range s] @ V from the SAME fp16-plane panel (rows are the MMA's M dimension, the
     blocked planes stream through plain bulk copies) -- K v without evaluating a kernel value."""
     L = _lib.load()
@@ -280,11 +281,11 @@ def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial):
     if PANEL_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    check(L.odf_panel16_mmv(ptr(panel16), n_rows, M, ptr(V16), ptr(absmax), T_pad, S, ptr(out_partial), _stream()),
-          "odf_panel16_mmv")
+    fn = L.odf_panel16_mmv_hi if hi_only else L.odf_panel16_mmv
+    check(fn(ptr(panel16), n_rows, M, ptr(V16), ptr(absmax), T_pad, S, ptr(out_partial), _stream()), "odf_panel16_mmv")
     if ev is not None:
         ev[1].record()
-        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_mmv_kernel"))
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_mmv_kernel<hi>" if hi_only else "panel16_mmv_kernel"))
     _count(1)
 
 
@@ -666,6 +667,7 @@ class Sweeper:
         tile with the spill into the transient panel in every sweep."""
         M, T = self.cols.n, self.T
         fill = not self.have_fwd
+        hi = bool(PANEL_HI_ONLY)            # experimental: passes over filled resident panels read the hi plane only
         need_tile = fill or self.n_res < len(self.chunks)
         if v is None:
             if need_tile:
@@ -696,10 +698,10 @@ class Sweeper:
                 finish_w16(self.part1[n], T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
             else:
                 kv = self.kv_part[n]
-                panel16_mmv(panel, self.V16, self.absmax_v, n, M, kv)                       # K_chunk v, same panel
+                panel16_mmv(panel, self.V16, self.absmax_v, n, M, kv, hi_only=hi)           # K_chunk v, same panel
                 finish_w16(kv, T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
             S = self.pslabs[i]
-            panel16_tmm(panel, self.W16, self.absmax, n, M, self.part3[slab:slab + S])      # K_chunk^T (K_chunk v + w)
+            panel16_tmm(panel, self.W16, self.absmax, n, M, self.part3[slab:slab + S], hi_only=hi and not tile)  # K_chunk^T (K_chunk v + w)
             slab += S
         self.have_fwd = True
         if self.n_res == len(self.chunks):
@@ -787,6 +789,9 @@ class Sweeper:
         return finish_rows(self.part3, self.T, out, scale)
 
 
+# EXPERIMENTAL precision tier: resident sweeps stream the hi plane only (K to 11 bits, 2 B per value) once the panels
+# are filled.  ODF_PANEL_HI_ONLY=1.  Off by default: emulated on the CPU only so far (tools/precision_study.py).
+PANEL_HI_ONLY = os.environ.get("ODF_PANEL_HI_ONLY", "0") not in ("0", "")
 RESIDENT_FRACTION = 0.85   # share of the free device memory the resident panels may take in mode "auto"
 # keep only K_chunk (default) instead of K_chunk and K_chunk^T: K v then comes from the same panel through
 # odf_panel16_mmv, half the memory and no transposed tile pass.  ODF_RESIDENT_SINGLE=0 selects the two-copy variant.

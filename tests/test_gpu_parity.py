@@ -443,9 +443,80 @@ def test_fit_from_host_memory_matches_device_fit(odf):
     assert torch.equal(m.alpha_, base.alpha_) and m.ny_points_.is_cuda
 
 
-@pytest.mark.skipif(os.environ.get("ODF_EXPERIMENTAL", "0") in ("0", ""),
-                    reason="overlap_rhs is experimental and off by default (passed on the box before the record_stream fix of the "
-                           "C2-size race, profiles/r1_pytest_gpu_v15.log; the fixed version is to be re-validated: ODF_EXPERIMENTAL=1)")
+# Code paths that exist but are OFF by default because they have not been (re-)validated on the GPU box yet; run them
+# with ODF_EXPERIMENTAL=1.
+EXPERIMENTAL = pytest.mark.skipif(os.environ.get("ODF_EXPERIMENTAL", "0") in ("0", ""),
+                                  reason="experimental path, off by default: set ODF_EXPERIMENTAL=1 to run (DESIGN.md §7)")
+
+
+@EXPERIMENTAL
+def test_hi_only_panel_kernels(odf):
+    """Precision tier "hi plane only" of the two panel kernels: the result must be the product with rn16(K) to fp32
+    accuracy, i.e. within 2^-11 of the exact-K product."""
+    from odf import ops
+    n, M, d, T = 9000, 333, 64, 21
+    X, _, _ = orc.make_synthetic(n, d, 3, seed=6)
+    C = X[::27][:M].contiguous()
+    g = torch.Generator().manual_seed(8)
+    W = torch.randn(n, T, generator=g) * torch.logspace(-2, 2, T)[None, :]
+    V = torch.randn(M, T, generator=g) * torch.logspace(-2, 2, T)[None, :]
+    k = odf.GaussianKernel(15.0)
+    cols = k._prep(C.cuda())
+    rows = k._prep(X.cuda(), like=cols)
+    dev = torch.device("cuda")
+    rhs = ops.SplitRhs(M, T, dev).fill(torch.zeros(M, T, device=dev))
+    part1 = ops.alloc_partial(rows, cols, rhs.T_pad, dev)
+    L = ops._lib.load()
+    p16 = torch.empty((int(L.odf_panel16_bytes(n, M)),), dtype=torch.uint8, device=dev)
+    ops.mmv_partial(rows, cols, rhs, 15.0, part1, panel16=p16)
+    K = orc.gaussian_kernel(X, C, 15.0)
+    K16 = K.to(torch.float16).double()
+    Wf = torch.empty((n, rhs.T_pad), device=dev)
+    W16 = torch.empty(((n + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
+    absmax = torch.zeros(32, dtype=torch.int32, device=dev)
+    ops.finish_w16(part1, T, Wf, absmax, W16, addend=W.cuda())
+    out_p = torch.empty((int(L.odf_panel16_splits(n, M)), M, rhs.T_pad), device=dev)
+    ops.panel16_tmm(p16, W16, absmax, n, M, out_p, hi_only=True)
+    out = out_p.sum(0)[:, :T].double().cpu()
+    scale = K.T @ W.double().abs()
+    assert float(((out - K16.T @ W.double()).abs() / scale).max()) < 2e-5
+    assert float(((out - K.T @ W.double()).abs() / scale).max()) < 2.0 ** -11
+    Vpad = torch.zeros((1, M, rhs.T_pad), device=dev)
+    Vpad[0, :, :T] = V.cuda()
+    Vf = torch.empty((M, rhs.T_pad), device=dev)
+    V16 = torch.empty(((M + 127) // 128 * 128, 64), dtype=torch.float16, device=dev)
+    ops.finish_w16(Vpad, T, Vf, absmax, V16)
+    kv_p = torch.empty((int(L.odf_panel16_mmv_splits(n, M)), n, rhs.T_pad), device=dev)
+    ops.panel16_mmv(p16, V16, absmax, n, M, kv_p, hi_only=True)
+    kv = kv_p.sum(0)[:, :T].double().cpu()
+    scale = K @ V.double().abs()
+    assert float(((kv - K16 @ V.double()).abs() / scale).max()) < 2e-5
+    assert float(((kv - K @ V.double()).abs() / scale).max()) < 2.0 ** -11
+
+
+@EXPERIMENTAL
+def test_hi_only_fit_stays_inside_the_parity_bar(odf, monkeypatch):
+    """A whole fit whose resident sweeps read 11-bit K: scores within the 1e-3 bar of the fp64 oracle and within a
+    few 1e-5 of the default (22-bit) fit, as the CPU emulation predicts (profiles/r1_precision_study_cpu.log)."""
+    from odf import ops
+    d, T = 256, 21
+    for sigma, lam in ((15.0, 1e-3), (10.0, 1e-6)):
+        X, c, Y = orc.make_synthetic(12000, d, T, seed=0)
+        C = X[orc.shared_centres(c, 600, seed=1)]
+        monkeypatch.setattr(ops, "PANEL_HI_ONLY", False)
+        full = _gpu_fit(odf, X, Y, C, sigma, lam, options=odf.FalkonOptions(sweep_mode="resident"))
+        monkeypatch.setattr(ops, "PANEL_HI_ONLY", True)
+        hi = _gpu_fit(odf, X, Y, C, sigma, lam, options=odf.FalkonOptions(sweep_mode="resident"))
+        Xt, _, _ = orc.make_synthetic(3000, d, T, seed=11)
+        alpha = orc.falkon_fit(X, Y, C, sigma, lam, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+        s_ref = orc.falkon_predict(Xt, C, alpha, sigma)
+        s_hi, s_full = hi.predict(Xt.cuda()).cpu(), full.predict(Xt.cuda()).cpu()
+        assert rel(s_hi, s_ref) < SCORE_RTOL
+        assert rel(s_hi, s_full) < 2e-4
+        assert_same_argmax(s_hi, s_ref)
+
+
+@EXPERIMENTAL
 def test_overlapped_rhs_sweep_is_bitwise_the_default_fit(odf, monkeypatch):
     """overlap_rhs: the right-hand side sweep (which fills the resident panels) runs on a side stream while the main
     stream builds the preconditioner.  Same kernels in the same order per stream, so alpha is bitwise the default

@@ -36,7 +36,7 @@ class _FakeRhs:
 @pytest.fixture()
 def emu(monkeypatch, lib):
     from odf import ops
-    store = {"panel": {}, "w16": {}, "calls": []}
+    store = {"panel": {}, "w16": {}, "calls": [], "hi": []}
 
     def tile_splits(n_rows, n_cols, d, kind):
         return min(3, (n_cols + 127) // 128)
@@ -67,7 +67,8 @@ def emu(monkeypatch, lib):
         store["w16"][W16.data_ptr()] = W
         return W16
 
-    def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial):
+    def panel16_tmm(panel16, W16, absmax, n_rows, M, out_partial, hi_only=False):
+        store["hi"].append(("panel", hi_only))
         K = store["panel"][panel16.data_ptr()]
         W = store["w16"][W16.data_ptr()]
         assert K.shape == (n_rows, M) and W.shape[0] == n_rows, "panel read in the wrong orientation"
@@ -79,7 +80,8 @@ def emu(monkeypatch, lib):
             out_partial[s, :, :W.shape[1]] = (K[edges[s]:edges[s + 1]].T @ W[edges[s]:edges[s + 1]]).to(torch.float32)
         store["calls"].append(("panel", n_rows, M))
 
-    def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial):
+    def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial, hi_only=False):
+        store["hi"].append(("mmv", hi_only))
         K = store["panel"][panel16.data_ptr()]
         V = store["w16"][V16.data_ptr()]
         assert K.shape == (n_rows, M) and V.shape[0] == M, "panel read in the wrong orientation"
@@ -106,6 +108,7 @@ def emu(monkeypatch, lib):
     monkeypatch.setattr(ops, "PANEL_ROWS", 256)
     monkeypatch.setattr(ops, "RESIDENT_MULT", 1)
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", False)
+    monkeypatch.setattr(ops, "PANEL_HI_ONLY", False)
     return ops, store
 
 
@@ -287,3 +290,24 @@ def test_auto_mode_falls_back_to_streaming_when_the_panels_do_not_fit_after_all(
     calls["n"] = 0
     with pytest.raises(torch.OutOfMemoryError):
         ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 2.0, 3, mode="resident")
+
+
+def test_hi_only_tier_applies_to_filled_resident_panels_only(emu, monkeypatch):
+    """PANEL_HI_ONLY (experimental): the passes over FILLED resident panels read the hi plane only; the pass that
+    follows the tile in the same sweep (filling pass, streamed chunks) and everything in the default tier do not."""
+    ops, store = emu
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(700, 12, generator=g, dtype=DT)
+    C = X[:150]
+    y = torch.randn(700, 5, generator=g)
+    out = torch.empty((150, 5), dtype=torch.float32)
+    for hi in (False, True):
+        monkeypatch.setattr(ops, "PANEL_HI_ONLY", hi)
+        sw = ops.Sweeper(_FakePrepared(X), _FakePrepared(C), 3.0, 5, mode="resident", resident_chunks=2)   # 2 of 3 resident
+        store["hi"].clear()
+        sw.dmmv(None, y, out, 1.0, 1.0 / 700)                      # filling sweep: tile + panel per chunk
+        assert store["hi"] == [("panel", False)] * 3
+        store["hi"].clear()
+        sw.dmmv(torch.randn(150, 5, generator=g), None, out)
+        assert store["hi"] == [("mmv", hi), ("panel", hi)] * 2 + [("panel", False)]
