@@ -44,6 +44,9 @@ class FalkonOptions:
         # "inverse": apply T^-1 / A^-1 as GEMMs with explicit inverses built once per fit (default);
         # "trsm": four triangular solves per CG iteration, as upstream does
         self.precond_apply = ignored.pop("precond_apply", "inverse")
+        # "library": odf_precond_init (cuSOLVER potrf + cuBLAS sgemm); "blocked" (EXPERIMENTAL): the same factors through
+        # odf/precond_blocked.py, where every O(M^3) flop is a be.gemm call -- the hook for a tensor-core split GEMM
+        self.precond_build = ignored.pop("precond_build", "library")
         # "panel16": K is evaluated once per sweep, its tiles are spilled as fp16 hi/lo planes to a transient panel
         # and contracted by the tensor-core panel kernel; "panel": fp32 panel + fp32-FMA panel kernel;
         # "recompute": evaluate K twice (no panel workspace); "resident": the fp16-plane panels of every row chunk
@@ -433,7 +436,11 @@ class Falkon:
         if not split:
             prof = _SegTimer(Kmm.device) if os.environ.get("ODF_PRECOND_PROFILE") and Kmm.is_cuda else None
             if prof: prof.mark("kmm (since previous mark)")
-            Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
+            if getattr(opt, "precond_build", "library") == "blocked":
+                from . import precond_blocked
+                Tm, Am = precond_blocked.build(be, Kmm, lam, opt.pc_epsilon_32)
+            else:
+                Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
             if prof: prof.mark("precond_init")
             if opt.precond_apply == "inverse":
                 fT = _InvFactor(be, Tm, shard=shard)

@@ -517,6 +517,25 @@ def test_hi_only_fit_stays_inside_the_parity_bar(odf, monkeypatch):
 
 
 @EXPERIMENTAL
+def test_blocked_preconditioner_build_on_the_gpu(odf):
+    """precond_build="blocked": the factors through odf/precond_blocked.py (diagonal potrf + TRSM panels + GEMM trailing
+    updates, every O(M^3) flop a be.gemm call) against odf_precond_init, and a fit that uses them."""
+    from odf import ops
+    from odf import precond_blocked as pb
+    X, c, Y = orc.make_synthetic(9000, 128, 3, seed=2)
+    C = X[orc.shared_centres(c, 2500, seed=1)]
+    k = odf.GaussianKernel(15.0)
+    K = k(C.cuda())
+    T0, A0 = ops.precond_init(K.clone(), 1e-4, 1e-5)
+    T1, A1 = pb.build(ops, K.clone(), 1e-4, 1e-5, nb=1024)
+    assert rel(T1, T0) < 1e-5 and rel(A1, A0) < 1e-4
+    assert float(T1.tril(-1).abs().max()) == 0.0 and float(A1.tril(-1).abs().max()) == 0.0
+    base = _gpu_fit(odf, X, Y, C, 15.0, 1e-4).predict(X[:1000].cuda())
+    alt = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(precond_build="blocked")).predict(X[:1000].cuda())
+    assert rel(alt, base) < 5e-4
+
+
+@EXPERIMENTAL
 def test_overlapped_rhs_sweep_is_bitwise_the_default_fit(odf, monkeypatch):
     """overlap_rhs: the right-hand side sweep (which fills the resident panels) runs on a side stream while the main
     stream builds the preconditioner.  Same kernels in the same order per stream, so alpha is bitwise the default
