@@ -65,6 +65,17 @@ int odf_tile_splits(int64_t n_rows, int64_t n_cols, int64_t d, int kind);
 int odf_prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean,
                        float scale, int kind, void* hi, void* lo, float* sqnorm, float* opscale,
                        void* stream);
+/* EXPERIMENTAL: the fused tile as a split GEMM (3-pass fp16 / tf32 products, fp32 accumulation in TMEM) for the blocked
+ * preconditioner build (odf/precond_blocked.py; replaces cuBLAS sgemm inside falkon FalkonPreconditioner.init).
+ * odf_prepare_points_linear = odf_prepare_points without z-score and with a ZERO accumulator seed; odf_gemm_nt_split:
+ * C[m x n] = alpha A B^T + beta C for A [m x k], B [n x k] in that prepared form (k <= ~2048 per call: the tensor
+ * core adds with truncation, long contractions are sliced on the host and accumulated with beta = 1).            */
+int odf_prepare_points_linear(const float* X, int64_t n, int64_t d, int64_t ldx, int kind, void* hi, void* lo,
+                              float* sqnorm, float* opscale, void* stream);
+int odf_gemm_nt_split(int kind, const void* a_hi, const void* a_lo, const float* a_sqnorm,
+                      const float* a_opscale, int64_t m, const void* b_hi, const void* b_lo,
+                      const float* b_sqnorm, const float* b_opscale, int64_t n, int64_t k, float alpha,
+                      float beta, float* C, int64_t ldc, void* stream);
 /* In-place z-score only (same reference lines). */
 int odf_zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
                void* stream);

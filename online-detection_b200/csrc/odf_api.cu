@@ -11,7 +11,8 @@
 namespace odf {
 
 // ---- implemented in odf_vec.cu
-int prepare_points(const float*, int64_t, int64_t, int64_t, const float*, float, int, void*, void*, float*, float*, cudaStream_t);
+int prepare_points(const float*, int64_t, int64_t, int64_t, const float*, float, int, void*, void*, float*, float*, cudaStream_t,
+                   bool zero_seed = false);
 int zscore(float*, int64_t, int64_t, int64_t, const float*, float, cudaStream_t);
 int split_rhs(const float*, int64_t, int64_t, int64_t, float, float*, float*, int64_t, int, cudaStream_t);
 int finish_rows(const float*, int, int64_t, int, int64_t, float, const float*, int64_t, float*, int64_t, cudaStream_t);
@@ -203,6 +204,10 @@ int odf_prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const 
                        int kind, void* hi, void* lo, float* sqnorm, float* opscale, void* stream) {
   return prepare_points(X, n, d, ldx, mean, scale, kind, hi, lo, sqnorm, opscale, static_cast<cudaStream_t>(stream));
 }
+int odf_prepare_points_linear(const float* X, int64_t n, int64_t d, int64_t ldx, int kind, void* hi, void* lo,
+                              float* sqnorm, float* opscale, void* stream) {
+  return prepare_points(X, n, d, ldx, nullptr, 1.f, kind, hi, lo, sqnorm, opscale, static_cast<cudaStream_t>(stream), true);
+}
 int odf_zscore(float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale, void* stream) {
   return zscore(X, n, d, ldx, mean, scale, static_cast<cudaStream_t>(stream));
 }
@@ -338,6 +343,22 @@ int odf_gauss_kmm_prepared(int kind, const void* c_hi, const void* c_lo, const f
   L.d_pad = round_up(d, kblock_elems(kind)); L.T_pad = 16; L.mode = MODE_STORE;
   L.n_splits = odf_tile_splits(M, M, d, kind); L.sigma = sigma;
   L.out = K; L.ldo = ldk; L.split_stride = 0;
+  return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
+}
+
+int odf_gemm_nt_split(int kind, const void* a_hi, const void* a_lo, const float* a_sqnorm, const float* a_opscale,
+                      int64_t m, const void* b_hi, const void* b_lo, const float* b_sqnorm, const float* b_opscale,
+                      int64_t n, int64_t k, float alpha, float beta, float* C, int64_t ldc, void* stream) {
+  if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "unknown operand kind");
+  if (m <= 0 || n <= 0 || k <= 0 || ldc < n) return set_error(ODF_ERR_ARG, "gemm_nt_split: bad shape");
+  TileLaunch L{};
+  L.kind = kind;
+  L.r_hi = a_hi; L.r_lo = a_lo; L.r_norm = a_sqnorm; L.r_scale = a_opscale; L.n_rows = m;
+  L.q_hi = b_hi; L.q_lo = b_lo; L.q_norm = b_sqnorm; L.q_scale = b_opscale; L.n_cols = n;
+  L.d_pad = round_up(k, kblock_elems(kind)); L.T_pad = 16; L.mode = MODE_STORE;
+  L.n_splits = odf_tile_splits(m, n, k, kind); L.sigma = 1.f;
+  L.out = C; L.ldo = ldc; L.split_stride = 0;
+  L.linear = 1; L.lin_alpha = alpha; L.lin_beta = beta;
   return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
 }
 

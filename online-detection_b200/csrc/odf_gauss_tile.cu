@@ -99,7 +99,10 @@ __device__ __forceinline__ WorkItem decode_item(const TileParams& p, int idx) {
 
 // SPILL16 = 1: the epilogue also writes every K tile as two fp16 planes (hi = rn16(K), lo = rn16((K - hi) * 2^12))
 // in the tile-blocked layout odf_panel16.cu streams back with TMA: [plane][column tile][row block][16 groups][128 rows][8].
-template <int KIND, int SPILL16>
+// LINEAR = 1 (MODE_STORE only, EXPERIMENTAL): the split GEMM A B^T behind the blocked preconditioner build
+// (odf/precond_blocked.py).  Operands come from odf_prepare_points_linear (zero seed block, so the accumulator is
+// s_r s_q (x . c) exactly) and the epilogue stores lin_alpha (x . c) + lin_beta out instead of the Gaussian kernel.
+template <int KIND, int SPILL16, int LINEAR = 0>
 __global__ void __launch_bounds__(256, 1)
 gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
                   const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
@@ -423,6 +426,21 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
                 *reinterpret_cast<float4*>(prow + 4 * v) = t;
               }
             }
+          } else if (LINEAR) {
+            // MODE_STORE, linear: out = alpha (x . c) + beta out
+            const float a_ss = p.lin_alpha / (s_r * s_q);
+            if (grow < p.n_rows) {
+              float* orow = p.out + static_cast<int64_t>(grow) * p.ldo;
+              const int c0 = col0 + ch * 32;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                if (c0 + c < p.n_cols) {
+                  float v = a_ss * __uint_as_float(s[c]);
+                  if (p.lin_beta != 0.f) v = fmaf(p.lin_beta, orow[c0 + c], v);
+                  orow[c0 + c] = v;
+                }
+              }
+            }
           } else {
             // MODE_STORE: write K straight to global (row-major, ld = ldo)
 #pragma unroll
@@ -633,9 +651,15 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
       e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_TF32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_TF32, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_F16, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gauss_tile_kernel)");
     attr_set = true;
   }
+  if (L.linear && (L.mode != MODE_STORE || L.panel != nullptr || L.panel16 != nullptr))
+    return set_error(ODF_ERR_ARG, "the linear store variant is MODE_STORE without a spill");
   CUtensorMap mRh, mRl, mQh, mQl, mVh, mVl;
   int rc;
   if ((rc = make_map(&mRh, L.r_hi, L.n_rows, pitch, pitch, BM, esize))) return rc;
@@ -688,9 +712,15 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
     p.dbg = e ? atoi(e) : 0;
   }
   p.store_vec4 = (L.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) ? 1 : 0;
+  p.lin_alpha = L.lin_alpha;
+  p.lin_beta = L.lin_beta;
   const int n_items = p.n_rowblocks * p.n_splits;
   const int grid = n_items < sms ? n_items : sms;
-  if (L.kind == KIND_F16 && L.panel16 != nullptr)
+  if (L.linear && L.kind == KIND_F16)
+    gauss_tile_kernel<KIND_F16, 0, 1><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  else if (L.linear)
+    gauss_tile_kernel<KIND_TF32, 0, 1><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
+  else if (L.kind == KIND_F16 && L.panel16 != nullptr)
     gauss_tile_kernel<KIND_F16, 1><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);
   else if (L.kind == KIND_F16)
     gauss_tile_kernel<KIND_F16, 0><<<grid, 256, SMEM_BYTES, stream>>>(mRh, mRl, mQh, mQl, mVh, mVl, p);

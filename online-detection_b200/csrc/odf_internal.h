@@ -39,6 +39,9 @@ struct TileParams {
   int64_t panel16_plane;   // elements between the hi and the lo plane (n_coltiles * n_rowblocks * 128 * 128)
   int dbg;                 // bring-up timing experiments (env ODF_TILE_DEBUG; results are garbage when set):
                            // 1 = no TMA refills, 2 = no S MMAs, 4 = no epilogue math, 8 = no K.V MMAs, 16 = print clocks
+  // LINEAR store variant only (appended: the layout seen by the other instantiations is unchanged):
+  // out = lin_alpha * (x . c) + lin_beta * out, operands prepared with a zero seed block
+  float lin_alpha, lin_beta;
 };
 
 // Host-side launch description.
@@ -66,6 +69,8 @@ struct TileLaunch {
   const void *vt16_hi, *vt16_lo;   // optional fp16 split of V^T [T_pad x ldvt16] (odf_split_rhs16): enables the pair kernel
   int64_t ldvt16;
   const uint32_t* v_absmax;
+  int linear;                  // MODE_STORE only: store lin_alpha * (x . c) + lin_beta * out instead of the Gaussian kernel
+  float lin_alpha, lin_beta;
 };
 
 int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream);

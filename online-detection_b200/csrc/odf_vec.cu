@@ -88,7 +88,7 @@ template <> struct OpElem<KIND_F16> {
 //   [ features (d, zero padded to d_pad) | seed block: g_hi, g_lo, 0.. | ones block: 1, 1, 0.. ]
 // with g = -s^2 |x'|^2 / 2 (the rank-1 accumulator seed of the tile kernel).  Only `hi` carries the
 // two extra blocks.
-template <int KIND, bool VEC>
+template <int KIND, bool VEC, bool ZSEED = false>
 __global__ void __launch_bounds__(256)
 split_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx, const float* __restrict__ mean,
              float scale, typename OpElem<KIND>::type* __restrict__ hi,
@@ -104,7 +104,7 @@ split_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx, const f
   const float* xr = X + row * ldx;
   E* hr = hi + row * pitch;
   E* lr = lo + row * pitch;
-  const float g = -0.5f * __ldg(sqn + row) * s * s;
+  const float g = ZSEED ? 0.f : -0.5f * __ldg(sqn + row) * s * s;      // ZSEED: operands of the linear (GEMM) tile
   for (int c = lane * 4; c < pitch; c += 128) {
     float v[4];
     if (c < d_pad) {
@@ -513,7 +513,7 @@ int check_launch(const char* what) {
 
 // ---- internal C++ entry points used by odf_api.cu ------------------------------------------
 int prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean, float scale,
-                   int kind, void* hi, void* lo, float* sqn, float* opscale, cudaStream_t st) {
+                   int kind, void* hi, void* lo, float* sqn, float* opscale, cudaStream_t st, bool zero_seed) {
   if (n <= 0 || d <= 0 || ldx < d) return set_error(ODF_ERR_ARG, "prepare_points: bad shape");
   if (kind != KIND_TF32 && kind != KIND_F16) return set_error(ODF_ERR_ARG, "prepare_points: unknown operand kind");
   const int64_t n_pad = round_up(n, 128);
@@ -528,7 +528,15 @@ int prepare_points(const float* X, int64_t n, int64_t d, int64_t ldx, const floa
   const int di = static_cast<int>(d);
   if (vec) rownorm_kernel<true><<<gridA, 256, 0, st>>>(X, n, di, ldx, mean, scale, sqn, n_pad, maxbits);
   else rownorm_kernel<false><<<gridA, 256, 0, st>>>(X, n, di, ldx, mean, scale, sqn, n_pad, maxbits);
-  if (kind == KIND_F16) {
+  if (zero_seed) {
+    if (kind == KIND_F16) {
+      if (vec) split_kernel<KIND_F16, true, true><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<__half*>(hi), static_cast<__half*>(lo), d_pad, pitch, sqn, opscale);
+      else split_kernel<KIND_F16, false, true><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<__half*>(hi), static_cast<__half*>(lo), d_pad, pitch, sqn, opscale);
+    } else {
+      if (vec) split_kernel<KIND_TF32, true, true><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<float*>(hi), static_cast<float*>(lo), d_pad, pitch, sqn, opscale);
+      else split_kernel<KIND_TF32, false, true><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<float*>(hi), static_cast<float*>(lo), d_pad, pitch, sqn, opscale);
+    }
+  } else if (kind == KIND_F16) {
     if (vec) split_kernel<KIND_F16, true><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<__half*>(hi), static_cast<__half*>(lo), d_pad, pitch, sqn, opscale);
     else split_kernel<KIND_F16, false><<<gridB, 256, 0, st>>>(X, n, di, ldx, mean, scale, static_cast<__half*>(hi), static_cast<__half*>(lo), d_pad, pitch, sqn, opscale);
   } else {

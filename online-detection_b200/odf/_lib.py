@@ -24,6 +24,9 @@ SIGNATURES = {
     "odf_tpad": (c_int, [c_i64]),
     "odf_tile_splits": (c_int, [c_i64, c_i64, c_i64, c_int]),
     "odf_prepare_points": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "odf_prepare_points_linear": (c_int, [c_fp, c_i64, c_i64, c_i64, c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "odf_gemm_nt_split": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64, c_f, c_f, c_fp,
+                                  c_i64, c_fp]),
     "odf_zscore": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_f, c_fp]),
     "odf_split_rhs": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_i64, c_int, c_fp]),
     "odf_gauss_mmv_prepared": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64,

@@ -77,7 +77,7 @@ class Prepared:
 
     __slots__ = ("hi", "lo", "sqn", "opscale", "n", "d", "kind", "pitch")
 
-    def __init__(self, X, mean=None, scale=1.0, kind=None):
+    def __init__(self, X, mean=None, scale=1.0, kind=None, linear=False):
         L = _lib.load()
         X = _req(X, "X", 2)
         X, ldx = _rowmajor(X)
@@ -94,8 +94,14 @@ class Prepared:
         self.opscale = torch.empty((2,), dtype=torch.float32, device=dev)
         if mean is not None:
             mean = _req(mean, "mean").contiguous()
-        check(L.odf_prepare_points(ptr(X), self.n, self.d, ldx, ptr(mean), float(scale), self.kind, ptr(self.hi),
-                                   ptr(self.lo), ptr(self.sqn), ptr(self.opscale), _stream()), "odf_prepare_points")
+        if linear:
+            # operands of the split GEMM (odf_gemm_nt_split): no z-score, zero accumulator seed
+            assert mean is None and scale == 1.0
+            check(L.odf_prepare_points_linear(ptr(X), self.n, self.d, ldx, self.kind, ptr(self.hi), ptr(self.lo),
+                                              ptr(self.sqn), ptr(self.opscale), _stream()), "odf_prepare_points_linear")
+        else:
+            check(L.odf_prepare_points(ptr(X), self.n, self.d, ldx, ptr(mean), float(scale), self.kind, ptr(self.hi),
+                                       ptr(self.lo), ptr(self.sqn), ptr(self.opscale), _stream()), "odf_prepare_points")
         _count(2)
 
 
@@ -400,8 +406,44 @@ def precond_apply(Inv, Bin, Bout, transposed):
     return Bout
 
 
+# EXPERIMENTAL: route large GEMMs of the (blocked) preconditioner build through the fused tile as a 3-pass split GEMM on
+# the tensor cores instead of cuBLAS sgemm.  ODF_GEMM_SPLIT=1.  Off by default: not yet validated on the GPU.
+GEMM_SPLIT = os.environ.get("ODF_GEMM_SPLIT", "0") not in ("0", "")
+GEMM_SPLIT_MIN = 512        # smallest m, n, k worth the operand pre-pass
+GEMM_SPLIT_KSLICE = 1024    # the tensor core accumulates with truncation: contraction chains are cut here and the slices
+                            # are summed in fp32 round-to-nearest by the epilogue (beta = 1); tools/precision_study.py B
+
+
+def gemm_nt_split(A, B, C, alpha=1.0, beta=0.0, kslice=None, kind=None):
+    """C = alpha A B^T + beta C for row-major fp32 A [m x k], B [n x k] (row-strided views allowed) on the tensor cores:
+    each k-slice is split into fp16 hi/lo operands (odf_prepare_points_linear) and contracted by the fused tile with a
+    linear store epilogue (odf_gemm_nt_split): 3 passes, 2 x 11 bits per operand, fp32 accumulation."""
+    L = _lib.load()
+    A, B, C = _req(A, "A", 2), _req(B, "B", 2), _req(C, "C", 2)
+    m, k = A.shape
+    n = B.shape[0]
+    assert B.shape[1] == k and C.shape == (m, n) and C.stride(1) == 1
+    kslice = int(GEMM_SPLIT_KSLICE if kslice is None else kslice)
+    first = True
+    for k0 in range(0, k, kslice):
+        k1 = min(k, k0 + kslice)
+        pa = Prepared(A[:, k0:k1], kind=kind, linear=True)
+        pb = pa if (B is A) else Prepared(B[:, k0:k1], kind=pa.kind, linear=True)
+        check(L.odf_gemm_nt_split(pa.kind, ptr(pa.hi), ptr(pa.lo), ptr(pa.sqn), ptr(pa.opscale), m, ptr(pb.hi), ptr(pb.lo),
+                                  ptr(pb.sqn), ptr(pb.opscale), n, k1 - k0, float(alpha), float(beta if first else 1.0),
+                                  ptr(C), C.stride(0), _stream()), "odf_gemm_nt_split")
+        _count(1)
+        first = False
+    return C
+
+
 def gemm(A, B, C, trans_a=False, trans_b=False, alpha=1.0, beta=0.0):
-    """C = alpha op(A) op(B) + beta C on (possibly strided-row) fp32 views; true-fp32 cuBLAS sgemm."""
+    """C = alpha op(A) op(B) + beta C on (possibly strided-row) fp32 views; true-fp32 cuBLAS sgemm (or, with
+    GEMM_SPLIT and large shapes, the tensor-core split GEMM on explicitly transposed operands)."""
+    if GEMM_SPLIT and min(C.shape[0], C.shape[1], A.shape[0] if trans_a else A.shape[1]) >= GEMM_SPLIT_MIN:
+        X = A.t().contiguous() if trans_a else A                    # [m x k]
+        Y = B if trans_b else B.t().contiguous()                    # [n x k]
+        return gemm_nt_split(X, Y, C, alpha, beta)
     L = _lib.load()
     assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
     m, n = C.shape

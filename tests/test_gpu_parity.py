@@ -517,6 +517,49 @@ def test_hi_only_fit_stays_inside_the_parity_bar(odf, monkeypatch):
 
 
 @EXPERIMENTAL
+@pytest.mark.parametrize("m,n,k", [(300, 200, 64), (1000, 1500, 1000), (129, 257, 2500), (2048, 2048, 3000)])
+def test_split_gemm_matches_fp64(odf, m, n, k):
+    """odf_gemm_nt_split (the fused tile with a zero seed and a linear store epilogue): C = alpha A B^T + beta C against
+    the fp64 product, at sgemm-grade accuracy relative to |A||B|^T; strided views, k-slices, alpha / beta."""
+    from odf import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    A = torch.randn(m, k + 8, generator=g)[:, 4:4 + k] * torch.logspace(-1, 1, k)[None, :]      # row-strided view
+    B = torch.randn(n, k, generator=g)
+    C0 = torch.randn(m, n, generator=g)
+    ref = -0.5 * (A.double() @ B.double().T) + 2.0 * C0.double()
+    Cg = C0.cuda()
+    ops.gemm_nt_split(A.cuda(), B.cuda(), Cg, alpha=-0.5, beta=2.0)
+    scale = 0.5 * (A.double().abs() @ B.double().abs().T) + 2.0 * C0.double().abs()
+    assert float(((Cg.double().cpu() - ref).abs() / scale).max()) < 5e-6
+    sg = C0.cuda()
+    ops.gemm(A.cuda(), B.cuda(), sg, trans_b=True, alpha=-0.5, beta=2.0)                         # cuBLAS sgemm, for scale
+    assert rel(Cg, sg) < 2e-5
+    # symmetric product of one operand, beta = 0 over garbage
+    Cn = torch.full((m, m), float("nan"), device="cuda")
+    Ag = A.cuda()
+    ops.gemm_nt_split(Ag, Ag, Cn)
+    ref2 = A.double() @ A.double().T
+    assert float(((Cn.double().cpu() - ref2).abs() / (A.double().abs() @ A.double().abs().T)).max()) < 5e-6
+
+
+@EXPERIMENTAL
+def test_blocked_preconditioner_with_the_split_gemm(odf, monkeypatch):
+    """The blocked build with every large GEMM on the tensor cores (ops.GEMM_SPLIT) against odf_precond_init."""
+    from odf import ops
+    from odf import precond_blocked as pb
+    X, c, Y = orc.make_synthetic(9000, 128, 3, seed=2)
+    C = X[orc.shared_centres(c, 2500, seed=1)]
+    K = odf.GaussianKernel(15.0)(C.cuda())
+    T0, A0 = ops.precond_init(K.clone(), 1e-4, 1e-5)
+    monkeypatch.setattr(ops, "GEMM_SPLIT", True)
+    T1, A1 = pb.build(ops, K.clone(), 1e-4, 1e-5, nb=1024)
+    assert rel(T1, T0) < 1e-4 and rel(A1, A0) < 1e-3
+    base = _gpu_fit(odf, X, Y, C, 15.0, 1e-4).predict(X[:1000].cuda())
+    alt = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(precond_build="blocked")).predict(X[:1000].cuda())
+    assert rel(alt, base) < 1e-3
+
+
+@EXPERIMENTAL
 def test_blocked_preconditioner_build_on_the_gpu(odf):
     """precond_build="blocked": the factors through odf/precond_blocked.py (diagonal potrf + TRSM panels + GEMM trailing
     updates, every O(M^3) flop a be.gemm call) against odf_precond_init, and a fit that uses them."""
