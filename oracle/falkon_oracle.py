@@ -14,9 +14,10 @@ reference's on-line learners run through the third-party `falkon` package:
 
 PARITY UNPINNED for the FALKON arithmetic (Gaussian kernel products, preconditioner, CG): the reference
 ships no tests, golden vectors or fixtures for this path and the `falkon` package cannot be imported
-here, so that part of the oracle is pinned only by (i) the closed-form Nystrom kernel-ridge solution it
-must converge to, (ii) fp64-vs-fp32 self-agreement and (iii) hand-computed known-answer cases for the
-integer post-processing (tests/test_oracle.py).
+here, so that part of the oracle is pinned only by (i) the Nystrom kernel-ridge solution it must converge
+to -- in closed form and as computed by an independent library (scikit-learn Nystroem + Ridge) --,
+(ii) fp64-vs-fp32 self-agreement and (iii) hand-computed known-answer cases for the integer
+post-processing (tests/test_oracle.py).
 
 PINNED against the reference's own first-party code (tests/golden/make_reference_golden.py runs the
 UNMODIFIED py_od_utils.py, FALKONWrapper_with_centers_selection_incore.py, MyCenterSelector.py,
