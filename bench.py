@@ -277,7 +277,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__
     if local == 0:
-        __graft_entry__.build()
+        # stdout carries exactly ONE line (the JSON result): the build log (nvcc commands, "build ok") goes to stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            __graft_entry__.build()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     if world > 1:
         dist.barrier()
     import odf
