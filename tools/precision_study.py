@@ -55,10 +55,14 @@ def study_panel():
     torch.manual_seed(0)
     cases = [("C1-like  N=20000 M=1000 d=1024 T=21 sigma=15 lam=1e-3", 20000, 1000, 1024, 21, 15.0, 1e-3, 0.7),
              ("ill-cond N=20000 M=1000 d=1024 T=21 sigma=10 lam=1e-6", 20000, 1000, 1024, 21, 10.0, 1e-6, 0.7),
-             ("mask-like N=30000 M=1500 d=256 T=8 sigma=10 lam=1e-6", 30000, 1500, 256, 8, 10.0, 1e-6, 0.7)]
+             ("mask-like N=30000 M=1500 d=256 T=8 sigma=10 lam=1e-6", 30000, 1500, 256, 8, 10.0, 1e-6, 0.7),
+             ("tight clusters N=6000 M=500 d=1024 T=21 sigma=5 lam=1e-4 (noise 0.25)", 6000, 500, 1024, 21, 5.0, 1e-4, 0.25),
+             ("RANDOM LABELS N=8000 M=2000 d=256 T=8 sigma=10 lam=1e-6 (nothing to learn: alpha is large)", 8000, 2000, 256, 8, 10.0, 1e-6, 0.7)]
     real_kernel = orc.gaussian_kernel
     for name, N, M, d, T, sigma, lam, noise in cases:
         X, c, Y = orc.make_synthetic(N, d, T, seed=0, noise=noise)
+        if name.startswith("RANDOM"):
+            Y = torch.sign(torch.randn(N, T, generator=torch.Generator().manual_seed(9)))
         C = X[orc.shared_centres(c, M, seed=1)]
         Xt, _, _ = orc.make_synthetic(4000, d, T, seed=11, noise=noise)
         out = {}
