@@ -159,7 +159,8 @@ int odf_panel16_mmv(const void* panel16, int64_t n_rows, int64_t M, const void* 
 /* EXPERIMENTAL precision tier of the two panel contractions: only the hi plane is streamed (2 B per kernel value,
  * K to 11 bits; W / V keep their hi | lo split).  Same arguments and outputs as odf_panel16_tmm / odf_panel16_mmv.
  * A CPU emulation of the whole fit (tools/precision_study.py, profiles/r1_precision_study_cpu.log) puts the effect
- * on the decision scores at 1e-5 .. 3e-5 relative, against the 1e-3 parity bar; not yet validated on the GPU.   */
+ * on the decision scores at 3e-7 .. 3e-5 relative on learnable data and at 5e-4 on an over-fitted random-label
+ * problem, against the 1e-3 parity bar: an opt-in tier, never the default; not yet validated on the GPU.        */
 int odf_panel16_tmm_hi(const void* panel16, int64_t n_rows, int64_t M, const void* w16, const void* absmax,
                        int T_pad, int n_splits, float* out_partial, void* stream);
 int odf_panel16_mmv_hi(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax,
