@@ -172,6 +172,129 @@ def test_oracle_box_decode_matches_reference():
     assert np.array_equal(dec[clipped], G["decoded"][clipped])
 
 
+# ------------------------------------------------------------------------------------------ the RPN / segmentation flavours
+GF = np.load(os.path.join(HERE, "golden", "reference_flow_flavours.npz"))
+METAF = json.load(open(os.path.join(HERE, "golden", "reference_flow_flavours.json")))
+FLAVOURS = {"rpn": dict(kw={"is_rpn": True}, pos="rpn_pos", neg="rpn_neg", n=4, batches=3, seed="rpn",
+                        line="RPN's Online Classifier training time"),
+            "seg": dict(kw={"is_segmentation": True}, pos="seg_pos", neg="seg_neg", n=3, batches=1, seed="segmentation",
+                        line="Online Segmentation training time")}
+
+
+def tf(name):
+    return torch.from_numpy(GF[name])
+
+
+def flavour_inputs(tag):
+    f = FLAVOURS[tag]
+    pos = [tf("in_%s%d" % (f["pos"], i)).clone() for i in range(f["n"])]
+    neg = [[tf("in_%s%d_%d" % (f["neg"], i, j)).clone() for j in range(f["batches"])] for i in range(f["n"])]
+    st = "rpn" if tag == "rpn" else "seg"
+    stats = {"mean": tf("in_stats_%s_mean" % st), "std": tf("in_stats_%s_std" % st), "mean_norm": tf("in_stats_%s_mean_norm" % st)[0]}
+    return pos, neg, stats
+
+
+@pytest.mark.parametrize("tag", ["rpn", "seg"])
+def test_oracle_minibootstrap_reproduces_reference_flavours(tag):
+    """The reference's on-line RPN (`is_rpn=True`: RPN section of the config, one model per anchor class, an anchor
+    without positives -> None) and on-line segmentation (`is_segmentation=True`: ONLINE_SEGMENTATION section, one
+    negative tensor per class in a 1-list -> a single fit, no hard / easy selection) flavours, run from the reference's
+    own files (tests/golden/make_reference_golden_flavours.py), against the oracle's restatement of the loop."""
+    f, hy = FLAVOURS[tag], METAF["hyper"][tag]
+    pos, neg, stats = flavour_inputs(tag)
+    assert hy["num_classes"] - 1 == f["n"] == int(GF[tag + "_n_models"][0])
+    torch.manual_seed(METAF["seeds"][f["seed"]])
+
+    def train(Xc, y):
+        idx = orc.compute_indices_selection(y, hy["M"])
+        return (Xc[idx], orc.falkon_fit(Xc, y, Xc[idx], hy["sigma"], hy["lam"], dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7))
+
+    def predict(model, Xq):
+        return orc.falkon_predict(Xq, model[0], model[1].float().double(), hy["sigma"]).float()
+
+    for i in range(f["n"]):
+        if len(pos[i]) == 0:
+            assert bool(GF[tag + "_is_none"][i])
+            continue
+        p = orc.zscores(pos[i], stats["mean"], stats["mean_norm"]).float()
+        nb = [orc.zscores(b, stats["mean"], stats["mean_norm"]).float() for b in neg[i]]
+        model, cache = orc.minibootstrap(p, nb, train, predict, hard_thresh=hy["hard"], easy_thresh=hy["easy"])
+        assert torch.equal(cache, tf("%s_cache%d_neg" % (tag, i)))
+        assert torch.equal(model[0], tf("%s_model%d_centres" % (tag, i)))
+        assert rel(model[1], tf("%s_model%d_alpha" % (tag, i))) < 1e-6
+    # how the reference called the third-party package in these flavours: same in-core recipe, the section's sigma / lambda
+    ctors = [c for c in METAF["third_party_calls"][tag] if "ctor" in c]
+    assert len(ctors) == (f["n"] - int(GF[tag + "_is_none"].sum())) * f["batches"]
+    assert all(c["ctor"] == "InCoreFalkon" and c["maxiter"] == 20 and c["sigma"] == hy["sigma"] and c["penalty"] == hy["lam"]
+               and c["M"] <= hy["M"] for c in ctors)
+
+
+class _OracleClassifier:
+    """TEST-ONLY classifier for the product's drop-in OnlineRegionClassifier on the CPU: the product wrapper supplies the
+    configuration and the centre-selection rule (its own code, the reference's RNG calls), the oracle the arithmetic."""
+
+    def __init__(self, wrapper):
+        self.w = wrapper
+
+    def train(self, X, y, sigma=None, lam=None):
+        idx = self.w.compute_indices_selection(y)
+        idx = [idx] if isinstance(idx, int) else idx
+        sigma = self.w.sigma if sigma is None else sigma
+        lam = self.w.lam if lam is None else lam
+        alpha = orc.falkon_fit(X, y, X[idx], sigma, lam, maxiter=self.w.maxiter, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+        return {"centres": X[idx].clone(), "alpha": alpha.float(), "sigma": sigma}
+
+    def predict(self, model, X, y=None):
+        return orc.falkon_predict(X, model["centres"], model["alpha"].double(), model["sigma"]).float()
+
+
+@pytest.mark.parametrize("tag", ["rpn", "seg"])
+def test_product_region_classifier_host_loop_reproduces_reference_flavours(tag, tmp_path):
+    """The PRODUCT's drop-in OnlineRegionClassifier_incore module (configuration sections, class count, in-place
+    z-scoring, minibootstrap thresholds, None for an empty class, result.txt line) on the reference's inputs and RNG
+    seed, with the oracle standing in for the CUDA fits: same surviving negatives, same centres, same alpha."""
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    import OnlineRegionClassifier_incore as ocr
+    f = FLAVOURS[tag]
+    pos, neg, stats = flavour_inputs(tag)
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(yaml.dump(METAF["cfg"]))
+    torch.manual_seed(METAF["seeds"][f["seed"]])
+    wrapper = falkon.FALKONWrapper(str(cfg), **f["kw"])
+    hy = METAF["hyper"][tag]
+    assert (wrapper.sigma, wrapper.lam, wrapper.nyst_centers) == (hy["sigma"], hy["lam"], hy["M"])
+    rc = ocr.OnlineRegionClassifier(_OracleClassifier(wrapper), pos, neg, stats, cfg_path=str(cfg), **f["kw"])
+    assert (rc.num_classes, rc.sigma, rc.lam, rc.hard_tresh, rc.easy_tresh) == (hy["num_classes"], hy["sigma"], hy["lam"], hy["hard"], hy["easy"])
+    models, caches = rc.trainRegionClassifier(opts={"return_caches": True}, output_dir=str(tmp_path))
+    assert len(models) == f["n"] and [m is None for m in models] == GF[tag + "_is_none"].tolist()
+    for i, m in enumerate(models):
+        if m is None:
+            continue
+        assert torch.equal(caches[i]["neg"], tf("%s_cache%d_neg" % (tag, i)))
+        assert torch.equal(m["centres"], tf("%s_model%d_centres" % (tag, i)))
+        assert rel(m["alpha"], tf("%s_model%d_alpha" % (tag, i))) < 1e-6
+    assert open(tmp_path / "result.txt").read().startswith(f["line"]) and METAF["result_lines"][tag].startswith(f["line"])
+
+
+def test_product_region_classifier_host_loop_reproduces_reference_detection_flavour(tmp_path):
+    """Same check for the detection flavour (reference_flow.npz): the product's drop-in module with the oracle-backed
+    classifier on the CPU — the GPU test below repeats it with the CUDA fits."""
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    import OnlineRegionClassifier_incore as ocr
+    positives, negatives = inputs()
+    stats = {"mean": t("stats_mean"), "std": t("stats_std"), "mean_norm": t("stats_mean_norm")[0]}
+    cfg = cfg_file(tmp_path)
+    torch.manual_seed(SEEDS["minibootstrap"])
+    rc = ocr.OnlineRegionClassifier(_OracleClassifier(falkon.FALKONWrapper(cfg)), positives, negatives, stats, cfg_path=cfg)
+    models, caches = rc.trainRegionClassifier(opts={"return_caches": True}, output_dir=str(tmp_path))
+    for i in range(T_CLS):
+        assert torch.equal(caches[i]["neg"], t("cache%d_neg" % i))
+        assert torch.equal(models[i]["centres"], t("model%d_centres" % i))
+        assert rel(models[i]["alpha"], t("model%d_alpha" % i)) < 1e-6
+    assert torch.equal(positives[0], t("zscored_pos0"))                       # z-scored in place, like the reference
+    assert open(tmp_path / "result.txt").read().startswith("Detector's Online Classifier training time")
+
+
 # ------------------------------------------------------------------------------------------ GPU: product modules
 @pytest.fixture(scope="module")
 def odf():
