@@ -295,6 +295,37 @@ def test_product_region_classifier_host_loop_reproduces_reference_detection_flav
     assert open(tmp_path / "result.txt").read().startswith("Detector's Online Classifier training time")
 
 
+# ------------------------------------------------------------------------------------------ data formats either side of the path
+def test_product_loaders_and_helpers_match_reference_on_the_same_feature_caches(tmp_path, monkeypatch):
+    """The feature-cache file formats (positives_cl_{c}_batch_{b}, negatives_cl_{c}_batch_{b}, reg_{x,c,y}_batch_{b}) and
+    the helpers around them: the product's drop-in py_od_utils.py against the outputs of the reference's own
+    load_features_classifier (plain / cpu_tensor / sample_ratio / shuffled for a `detector` and an `RPN` directory /
+    is_segm), load_features_regressor (all rows / a seeded fraction), minibatch_positives, mask_iou and zScores on
+    the same files and RNG seeds (tests/golden/make_reference_golden_formats.py)."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(HERE, "golden"))
+    import format_fixture as fx
+    import py_od_utils as UT
+    assert "online-detection_b200" in UT.__file__
+    monkeypatch.setattr(UT, "_GPU", "cpu")
+    ref = np.load(os.path.join(HERE, "golden", "reference_formats.npz"))
+    cfg = fx.build(str(tmp_path))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = fx.run_all(UT, str(tmp_path), cfg)
+    got = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+    assert sorted(got) == sorted(ref.files)
+    for k in ref.files:
+        assert got[k].shape == ref[k].shape and got[k].dtype == ref[k].dtype, k
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    # spot checks of what the fixture exercises
+    assert ref["det_pos1"].shape == (0,) and int(ref["det_n_classes"][0]) == 3          # class without positive files
+    assert int(ref["det_shuffled_neg0_n"][0]) == 3 and ref["det_shuffled_neg0_0"].shape[0] == 40
+    assert int(ref["rpn_shuffled_neg0_n"][0]) == 2 and ref["rpn_shuffled_neg1_0"].shape[0] == 55
+    assert ref["seg_neg1"].shape == (0,) and np.isnan(ref["mask_iou"][4, 3])             # no negatives / empty masks
+
+
 # ------------------------------------------------------------------------------------------ GPU: product modules
 @pytest.fixture(scope="module")
 def odf():
