@@ -371,58 +371,80 @@ def voc07_ap(rec, prec):
     return ap
 
 
-def detection_map(dets, gts, num_classes, iou_thresh=0.5):
-    """VOC-style mAP restated from icw_eval.py:247-402 for synthetic boxes.
-    dets: list per image of (boxes[k,4], scores[k], labels[k]); gts: list per image of
-    (boxes[g,4], labels[g]).  Boxes get [:, 2:] += 1 before IoU (icw_eval.py:289-292)."""
-    aps = []
-    for c in range(1, num_classes):
-        scores, match = [], []
-        n_pos = 0
-        for (db, ds, dl), (gb, gl) in zip(dets, gts):
-            gsel = gb[gl == c]
-            n_pos += len(gsel)
-            dsel = dl == c
-            b, s = db[dsel], ds[dsel]
-            order = np.argsort(-s, kind="stable")
-            b, s = b[order], s[order]
-            scores.extend(s.tolist())
+def voc_area_ap(rec, prec):
+    """Area under the monotone precision envelope (icw_eval.py:383-400, use_07_metric=False)."""
+    mpre = np.concatenate(([0], np.nan_to_num(prec), [0]))
+    mrec = np.concatenate(([0], rec, [1]))
+    mpre = np.maximum.accumulate(mpre[::-1])[::-1]
+    i = np.where(mrec[1:] != mrec[:-1])[0]
+    return float(np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1]))
+
+
+def detection_ap(dets, gts, iou_thresh=0.5, use_07_metric=True):
+    """eval_detection_icw restated (mrcnn_modified/data/datasets/evaluation/icubworld/icw_eval.py:227-402, no
+    `difficult` objects): per-class AP array (index = label, nan where a class has no ground truth) and their nanmean.
+    dets: list per image of (boxes[k,4], scores[k], labels[k]); gts: list per image of (boxes[g,4], labels[g]).
+
+    As in the reference, predicted and ground-truth boxes get `[:, 2:] += 1` (:289-292) and are THEN compared with
+    maskrcnn-benchmark's `boxlist_iou`, which applies its own +1 convention to areas and intersections (SURVEY
+    Appendix B) — the effective widths are x2 - x1 + 2.  Per image and label the predictions are walked in
+    `argsort()[::-1]` order (:259-262), a ground-truth box is matched at most once (:302-314), and the global ranking is
+    again `argsort()[::-1]` of the concatenated scores (:331-332); precision is tp / (tp + fp) with nan for 0 / 0."""
+    n_pos, score, match = {}, {}, {}
+    for (db, ds, dl), (gb, gl) in zip(dets, gts):
+        db, ds, dl = np.asarray(db, dtype=np.float32).reshape(-1, 4), np.asarray(ds), np.asarray(dl)
+        gb, gl = np.asarray(gb, dtype=np.float32).reshape(-1, 4), np.asarray(gl)
+        for l in np.unique(np.concatenate((dl, gl)).astype(int)):
+            b, sc = db[dl == l], ds[dl == l]
+            order = sc.argsort()[::-1]
+            b, sc = b[order], sc[order]
+            g = gb[gl == l]
+            n_pos[l] = n_pos.get(l, 0) + len(g)
+            score.setdefault(l, []).extend(sc.tolist())
+            match.setdefault(l, [])
             if len(b) == 0:
                 continue
-            if len(gsel) == 0:
-                match.extend([0] * len(b))
+            if len(g) == 0:
+                match[l].extend([0] * len(b))
                 continue
-            bb = b.copy(); gg = gsel.copy()
-            bb[:, 2:] += 1; gg[:, 2:] += 1
-            area_b = (bb[:, 2] - bb[:, 0]) * (bb[:, 3] - bb[:, 1])
-            area_g = (gg[:, 2] - gg[:, 0]) * (gg[:, 3] - gg[:, 1])
-            lt = np.maximum(bb[:, None, :2], gg[None, :, :2])
-            rb = np.minimum(bb[:, None, 2:], gg[None, :, 2:])
-            wh = np.clip(rb - lt, 0, None)
-            inter = wh[..., 0] * wh[..., 1]
-            iou = inter / (area_b[:, None] + area_g[None, :] - inter)
-            gidx = iou.argmax(1)
-            gidx[iou.max(1) < iou_thresh] = -1
-            used = np.zeros(len(gsel), dtype=bool)
-            for g in gidx:
-                if g >= 0:
-                    if not used[g]:
-                        match.append(1)
-                    else:
-                        match.append(0)
-                    used[g] = True
+            bb, gg = b.copy(), g.copy()
+            bb[:, 2:] += 1
+            gg[:, 2:] += 1
+            iou = box_iou_plus1(bb, gg)
+            gidx = iou.argmax(axis=1)
+            gidx[iou.max(axis=1) < iou_thresh] = -1
+            used = np.zeros(len(g), dtype=bool)
+            for gi in gidx:
+                if gi >= 0:
+                    match[l].append(0 if used[gi] else 1)
+                    used[gi] = True
                 else:
-                    match.append(0)
-        if n_pos == 0:
-            continue
-        scores = np.array(scores); match = np.array(match)
-        order = np.argsort(-scores, kind="stable")
-        match = match[order]
-        tp = np.cumsum(match == 1); fp = np.cumsum(match == 0)
-        prec = tp / np.maximum(tp + fp, 1)
-        rec = tp / n_pos
-        aps.append(voc07_ap(rec, prec))
-    return float(np.mean(aps)) if aps else 0.0
+                    match[l].append(0)
+    if not n_pos:
+        return np.array([np.nan]), float("nan")
+    ap = np.full(max(n_pos) + 1, np.nan)
+    for l in n_pos:
+        sc, mt = np.array(score[l]), np.array(match[l], dtype=np.int8)
+        mt = mt[sc.argsort()[::-1]]
+        tp, fp = np.cumsum(mt == 1), np.cumsum(mt == 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            prec = tp / (fp + tp)
+        if n_pos[l] > 0:
+            rec = tp / n_pos[l]
+            ap[l] = voc07_ap(rec, prec) if use_07_metric else voc_area_ap(rec, prec)
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = float(np.nanmean(ap))
+    return ap, m
+
+
+def detection_map(dets, gts, num_classes=None, iou_thresh=0.5):
+    """VOC07 mAP as the reference's evaluator reports it (`detection_ap`, USE_VOC07_METRIC: True); 0 when no class has
+    ground truth.  `num_classes` is accepted for the older call sites and not needed."""
+    _ap, m = detection_ap(dets, gts, iou_thresh=iou_thresh, use_07_metric=True)
+    return 0.0 if np.isnan(m) else m
 
 
 # ------------------------------------------------------------------------------------------

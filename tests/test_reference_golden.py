@@ -326,6 +326,36 @@ def test_product_loaders_and_helpers_match_reference_on_the_same_feature_caches(
     assert ref["seg_neg1"].shape == (0,) and np.isnan(ref["mask_iou"][4, 3])             # no negatives / empty masks
 
 
+# ------------------------------------------------------------------------------------------ the detection evaluator (mAP)
+def test_oracle_ap_matches_the_reference_evaluator():
+    """oracle.detection_ap against the reference's own eval_detection_icw (icw_eval.py:227-402) on synthetic detections
+    with duplicates, false positives, a class without ground truth and one without detections: per-class AP (VOC07 and
+    area metric, IoU 0.5 and 0.7) and their nanmean, to rounding.  This is the function the "mAP within 0.1" check of
+    tests/test_gpu_parity.py is computed with."""
+    E = np.load(os.path.join(HERE, "golden", "reference_eval.npz"))
+    n = int(E["n_img"][0])
+    dets = [(E["in_det_boxes%d" % i], E["in_det_scores%d" % i], E["in_det_labels%d" % i]) for i in range(n)]
+    gts = [(E["in_gt_boxes%d" % i], E["in_gt_labels%d" % i]) for i in range(n)]
+    for thr in (0.5, 0.7):
+        for m07 in (True, False):
+            tag = "iou%02d_%s" % (int(thr * 10), "voc07" if m07 else "area")
+            ap, m = orc.detection_ap(dets, gts, iou_thresh=thr, use_07_metric=m07)
+            ref = E["ap_" + tag]
+            assert ap.shape == ref.shape and np.array_equal(np.isnan(ap), np.isnan(ref))
+            assert np.allclose(ap, ref, rtol=0, atol=1e-12, equal_nan=True)
+            assert abs(m - float(E["map_" + tag][0])) < 1e-12
+    ap1, _ = orc.detection_ap(dets[:1], gts[:1])
+    assert np.allclose(ap1, E["ap_single"], atol=1e-12, equal_nan=True)
+    assert abs(orc.detection_map(dets, gts) - float(E["map_iou05_voc07"][0])) < 1e-12
+    # the double +1 of the reference pipeline ([:, 2:] += 1, then boxlist_iou's own +1) is visible: a pair of boxes
+    # whose plain IoU is just below 0.5 but matches under the reference's effective widths
+    det = [(np.array([[0, 0, 9, 9]], np.float32), np.array([0.9], np.float32), np.array([1]))]
+    gt = [(np.array([[0, 3, 9, 12]], np.float32), np.array([1]))]
+    plain = (10 * 7) / (2 * 100 - 70)                                  # widths x2 - x1 + 1
+    assert plain < 0.55 < (11 * 8) / (2 * 121 - 88)                      # widths x2 - x1 + 2
+    assert abs(orc.detection_ap(det, gt, iou_thresh=0.55)[0][1] - 1.0) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------ GPU: product modules
 @pytest.fixture(scope="module")
 def odf():
