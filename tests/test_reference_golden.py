@@ -356,6 +356,26 @@ def test_oracle_ap_matches_the_reference_evaluator():
     assert abs(orc.detection_ap(det, gt, iou_thresh=0.55)[0][1] - 1.0) < 1e-12
 
 
+# ------------------------------------------------------------------------------------------ the detection post-processor
+def test_oracle_postprocessing_matches_the_reference_postprocessor():
+    """The reference's OnlineDetectionPostProcessor.forward (decode -> clip -> strict score threshold -> per-class NMS ->
+    concatenation in class order -> kthvalue top-K with >=), run from its own file (make_reference_golden_post.py), against
+    the oracle's decode_boxes + clip_to_image + filter_results: same detections in the same order, labels and scores
+    bit-exact, boxes to fp32 rounding; four threshold / top-K settings incl. "nothing survives".  Also the first-party
+    IoU twin compute_overlap_torch against box_iou_plus1."""
+    P = np.load(os.path.join(HERE, "golden", "reference_post.npz"))
+    dec = orc.clip_to_image(orc.decode_boxes(P["in_proposals"], P["in_deltas"], 640, 480), 640, 480)
+    for tag in ("k40", "k100", "tight", "none"):
+        thr, nms, k = P[tag + "_params"]
+        b, sc, lab, _ = orc.filter_results(dec, P["in_scores"], float(thr), float(nms), int(k))
+        assert np.array_equal(lab, P[tag + "_labels"]) and np.array_equal(sc, P[tag + "_scores"]), tag
+        assert b.shape == P[tag + "_boxes"].shape and (len(b) == 0 or float(np.abs(b - P[tag + "_boxes"]).max()) <= 1.3e-4), tag
+    assert len(P["k40_scores"]) == 40 and len(P["k100_scores"]) == 100 and len(P["none_scores"]) == 0
+    iou = orc.box_iou_plus1(P["iou_gt"][None, :], P["in_proposals"])[0]
+    twin = P["iou_twin"]
+    assert np.allclose(np.where(iou > 0, iou, 0), twin, rtol=0, atol=1e-6) and float(twin.max()) > 0.3 and float(twin.min()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------ GPU: product modules
 @pytest.fixture(scope="module")
 def odf():
