@@ -24,7 +24,11 @@ UNMODIFIED py_od_utils.py, FALKONWrapper_with_centers_selection_incore.py, MyCen
 OnlineRegionClassifier_incore.py and region_refiner.py + trainer on the CPU, with this oracle standing
 in for the absent `falkon` package; tests/test_reference_golden.py): centre selection with the
 reference's RNG draws, z-scoring, the minibootstrap loop (surviving negatives and centres bit-exact),
-feature statistics, COXY normalisation, RLS refiners (mu, T, T_inv, weights, losses), box decode.
+feature statistics, COXY normalisation, RLS refiners (mu, T, T_inv, weights, losses), box decode; the
+on-line RPN / segmentation flavours of the loop (make_reference_golden_flavours.py); the detection
+post-processor and the first-party IoU twin (make_reference_golden_post.py); the VOC-style evaluator
+behind the mAP criterion (make_reference_golden_eval.py); the feature-cache loaders are pinned for the
+product's py_od_utils directly (make_reference_golden_formats.py).
 """
 import math
 
