@@ -185,6 +185,10 @@ int odf_gauss_kmm_prepared(int kind, const void* c_hi, const void* c_lo, const f
 #define ODF_OP_KMM 2
 #define ODF_OP_PRECOND 3
 size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T);
+/* potrf scratch of odf_precond_init / odf_potrf_upper for an M x M matrix as cuSOLVER reports it on the current
+ * device (cusolverDnSpotrf_bufferSize; 0 if no device can be queried).  odf_workspace_bytes(ODF_OP_PRECOND, ..)
+ * returns max(this, a closed-form lower bound). */
+size_t odf_precond_workspace_bytes(int64_t M);
 /* out[n x T] = K(X, C) V          — kernel.mmv(X1, X2, v, out) */
 int odf_gauss_mmv(const float* X, int64_t n, int64_t ldx, const float* C, int64_t M, int64_t ldc,
                   int64_t d, const float* V, int64_t T, int64_t ldv, float sigma, float* out,
@@ -202,6 +206,15 @@ int odf_gauss_kmm(const float* C, int64_t M, int64_t ldc, int64_t d, float sigma
  * SYNCHRONOUS (reads the factorisation status); ODF_ERR_LINALG if a pivot fails.               */
 int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void* ws,
                      size_t ws_bytes, void* stream);
+/* The same factors (and, when Tinv / Ainv are not NULL, their explicit inverses: all four upper triangular with a zero
+ * strict lower triangle, pitch M) with every O(M^3) flop on the tensor cores: blocked Cholesky on row-major lower
+ * factors -- cuSOLVER potrf only on the 1024 x 1024 diagonal blocks, cuBLAS trsm for the row panels, the trailing
+ * updates, T T^T and the divide-and-conquer triangular inverses as 3-pass split-fp16 tcgen05 GEMMs (odf_gemm_nt_split's
+ * tile), contraction chains of at most 1024.  In: K = K_MM (overwritten with T).  SYNCHRONOUS (reads the pivots' status);
+ * ODF_ERR_LINALG if a diagonal block is not positive definite.  ws >= odf_precond_build_workspace_bytes(M).        */
+size_t odf_precond_build_workspace_bytes(int64_t M);
+int odf_precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws,
+                      size_t ws_bytes, void* stream);
 /* B [M x T] (pitch ldb) <- op(Tri)^-1 B with Tri upper triangular (pitch M), op by `which`.   */
 int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t ldb, int which,
                       void* stream);

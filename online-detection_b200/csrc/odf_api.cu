@@ -83,9 +83,20 @@ bool take_prepared(Arena& a, int64_t n, int64_t d, int kind, Prepared* p) {
 
 int tpad_of(int64_t T) { return T <= 16 ? 16 : (T <= 32 ? 32 : -1); }
 
-cublasHandle_t g_cublas = nullptr;
-cusolverDnHandle_t g_cusolver = nullptr;
+// library handles, one pair per device (a handle is bound to the device that was current when it was created);
+// the references below are re-pointed at the current device's pair by ensure_handles().  One host thread per device.
+cublasHandle_t g_cublas_dev[kMaxDevices] = {};
+cusolverDnHandle_t g_cusolver_dev[kMaxDevices] = {};
+thread_local cublasHandle_t g_cublas = nullptr;
+thread_local cusolverDnHandle_t g_cusolver = nullptr;
 int ensure_handles(cudaStream_t st) {
+  const int dev = current_device();
+  g_cublas = g_cublas_dev[dev];
+  g_cusolver = g_cusolver_dev[dev];
+  struct Publish {                 // store freshly created handles back on every exit path
+    int dev;
+    ~Publish() { g_cublas_dev[dev] = g_cublas; g_cusolver_dev[dev] = g_cusolver; }
+  } publish{dev};
   if (!g_cublas) {
     if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "cublasCreate failed");
     // triangular solves / syrk of the preconditioner stay in true fp32
@@ -176,6 +187,18 @@ int inv_upper_rec(const float* T, float* X, int64_t n, int64_t ld, cudaStream_t 
 }
 
 }  // namespace
+
+// the current device's library handles, bound to `st` (odf_precond.cu)
+int lib_handles(cudaStream_t st, cublasHandle_t* blas, cusolverDnHandle_t* solver) {
+  const int rc = ensure_handles(st);
+  if (rc) return rc;
+  *blas = g_cublas;
+  *solver = g_cusolver;
+  return ODF_OK;
+}
+size_t precond_build_workspace_bytes(int64_t M, int lwork);
+int precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
 }  // namespace odf
 
 using namespace odf;
@@ -362,6 +385,23 @@ int odf_gemm_nt_split(int kind, const void* a_hi, const void* a_lo, const float*
   return launch_gauss_tile(L, static_cast<cudaStream_t>(stream));
 }
 
+// Scratch odf_precond_init / odf_potrf_upper need for an M x M factorisation, as cuSOLVER reports it for the current
+// device (0 when no device / handle can be had: callers then fall back to the closed form in odf_workspace_bytes).
+size_t odf_precond_workspace_bytes(int64_t M) {
+  if (M <= 0 || M > 0x7fffffff) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (ensure_handles(nullptr) != ODF_OK) return 0;
+  int lwork = 0;
+  if (cusolverDnSpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_LOWER, static_cast<int>(M), nullptr, static_cast<int>(M), &lwork) !=
+      CUSOLVER_STATUS_SUCCESS)
+    return 0;
+  return al(sizeof(int) * 2) + al(sizeof(float) * static_cast<size_t>(lwork)) + 256;
+}
+
 // ---------------------------------------------------------------- convenience (plain fp32 in)
 size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T) {
   const int T_pad = tpad_of(T > 0 ? T : 1);
@@ -382,8 +422,11 @@ size_t odf_workspace_bytes(int op, int64_t n, int64_t M, int64_t d, int64_t T) {
     case ODF_OP_KMM:
       return prepared_bytes(M, d, kind);
     case ODF_OP_PRECOND: {
-      // potrf scratch: query needs a handle + device; use a generous closed form instead
-      return al(sizeof(float) * (static_cast<size_t>(M) * 256 + (1u << 20))) + 256;
+      // potrf scratch: asked from cuSOLVER when a device is current (odf_precond_workspace_bytes); this closed form
+      // is the lower bound used when it cannot be queried
+      const size_t q = odf_precond_workspace_bytes(M);
+      const size_t lb = al(sizeof(float) * (static_cast<size_t>(M) * 256 + (1u << 20))) + 256;
+      return q > lb ? q : lb;
     }
     default:
       return 0;
@@ -525,6 +568,25 @@ int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void
     return set_error(ODF_ERR_LINALG, buf);
   }
   return ODF_OK;
+}
+
+// Tensor-core build (odf_precond.cu): K_MM in, T / A and (optionally) their explicit inverses out, all upper triangular.
+size_t odf_precond_build_workspace_bytes(int64_t M) {
+  if (M <= 0 || M > 0x7fffffff) return 0;
+  int lwork = 0, ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && ensure_handles(nullptr) == ODF_OK) {
+    const int nb = static_cast<int>(M < 1024 ? M : 1024);
+    if (cusolverDnSpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_UPPER, nb, nullptr, static_cast<int>(M), &lwork) != CUSOLVER_STATUS_SUCCESS)
+      lwork = 0;
+  } else {
+    cudaGetLastError();
+  }
+  if (lwork < (1 << 20)) lwork = 1 << 20;                  // generous floor: the exact figure is re-checked inside the build
+  return precond_build_workspace_bytes(M, lwork);
+}
+int odf_precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws,
+                      size_t ws_bytes, void* stream) {
+  return precond_build(K, Am, Tinv, Ainv, M, lam, eps, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 /* Building blocks of the same preconditioner for the row-sharded multi-GPU fit, where the O(M^3) pieces are

@@ -53,7 +53,7 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // R_hi, R_lo, Q_hi, Q_lo
 constexpr int MAX_TPAD = 32;
 constexpr int V_ATOM_BYTES_MAX = MAX_TPAD * 128;         // one [T_pad x 32] box
 constexpr int V_BYTES = 2 * 4 * V_ATOM_BYTES_MAX;        // hi+lo, 4 atoms each
-constexpr int NUM_BARS = 2 * NS + 8;
+constexpr int NUM_BARS = 2 * NS + 9;
 constexpr int SMEM_BYTES = NS * STAGE_BYTES + V_BYTES + NUM_BARS * 8 + 16 + 1024;
 
 // TMEM column map (512 columns allocated)
@@ -121,7 +121,12 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
   // barrier indices
   const int B_FULL = 0, B_EMPTY = NS, B_SFULL = 2 * NS, B_PREADY = 2 * NS + 2,
             B_PVDONE = 2 * NS + 3, B_VFULL = 2 * NS + 4, B_VEMPTY = 2 * NS + 5,
-            B_WFULL = 2 * NS + 6, B_WEMPTY = 2 * NS + 7;
+            B_WFULL = 2 * NS + 6, B_WEMPTY = 2 * NS + 7, B_PREADY1 = 2 * NS + 8;
+  // "epilogue done with S buffer b" has ONE BARRIER PER BUFFER: with a single barrier an epilogue warp that runs a tile
+  // ahead of the others (rows past n_rows skip their stores; in MODE_STORE nothing else holds it back) arrives twice in
+  // one phase, the phase completes before the slow warps have read their rows and the issuer overwrites the buffer --
+  // wrong entries in the ragged last row block, or a dead-locked hand-shake (round-2 bring-up of the LINEAR variant).
+  auto PREADY = [&](uint32_t b) { return BAR(b ? B_PREADY1 : B_PREADY); };
 
   // warp index through a shuffle: tells ptxas it is warp-uniform (role branches stay uniform)
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -152,6 +157,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
     mbar_init(BAR(B_SFULL + 0), 1);
     mbar_init(BAR(B_SFULL + 1), 1);
     mbar_init(BAR(B_PREADY), 128);
+    mbar_init(BAR(B_PREADY1), 128);
     mbar_init(BAR(B_PVDONE), 1);
     mbar_init(BAR(B_VFULL), 1);
     mbar_init(BAR(B_VEMPTY), 1);
@@ -251,7 +257,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
       // second contraction (or, in MODE_STORE, just the hand-back of the S buffer) for tile n-1
       auto finish_prev = [&](uint32_t tile) {
         if (p.dbg & 64) return;                       // timing experiment: issuer + producer only
-        mbar_wait(BAR(B_PREADY), tile & 1);
+        mbar_wait(PREADY(tile & 1), (tile >> 1) & 1);
         if (mode_mmv) {
           mbar_wait(BAR(B_VFULL), tile & 1);
           if (pend_first) {
@@ -432,12 +438,28 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
             if (grow < p.n_rows) {
               float* orow = p.out + static_cast<int64_t>(grow) * p.ldo;
               const int c0 = col0 + ch * 32;
+              if (p.store_vec4 && c0 + 32 <= p.n_cols) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                if (c0 + c < p.n_cols) {
-                  float v = a_ss * __uint_as_float(s[c]);
-                  if (p.lin_beta != 0.f) v = fmaf(p.lin_beta, orow[c0 + c], v);
-                  orow[c0 + c] = v;
+                for (int v = 0; v < 8; ++v) {
+                  float4 t;
+                  t.x = a_ss * __uint_as_float(s[4 * v + 0]); t.y = a_ss * __uint_as_float(s[4 * v + 1]);
+                  t.z = a_ss * __uint_as_float(s[4 * v + 2]); t.w = a_ss * __uint_as_float(s[4 * v + 3]);
+                  float4* o4 = reinterpret_cast<float4*>(orow + c0 + 4 * v);
+                  if (p.lin_beta != 0.f) {
+                    const float4 o = *o4;
+                    t.x = fmaf(p.lin_beta, o.x, t.x); t.y = fmaf(p.lin_beta, o.y, t.y);
+                    t.z = fmaf(p.lin_beta, o.z, t.z); t.w = fmaf(p.lin_beta, o.w, t.w);
+                  }
+                  *o4 = t;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  if (c0 + c < p.n_cols) {
+                    float v = a_ss * __uint_as_float(s[c]);
+                    if (p.lin_beta != 0.f) v = fmaf(p.lin_beta, orow[c0 + c], v);
+                    orow[c0 + c] = v;
+                  }
                 }
               }
             }
@@ -470,7 +492,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
         }
         if (mode_mmv) tc_wait_st();
         tc_fence_before();
-        mbar_arrive(BAR(B_PREADY));
+        mbar_arrive(PREADY(b));
       }
       if (mode_mmv) {
         // W for this item is complete once the last tile's contraction has retired.
@@ -594,16 +616,7 @@ int make_map_plain_f32(CUtensorMap* m, const void* base, int64_t rows, int64_t c
 
 namespace {
 
-int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+int num_sms() { return device_sm_count(); }
 
 }  // namespace
 
@@ -642,7 +655,8 @@ int launch_gauss_tile(const TileLaunch& L, cudaStream_t stream) {
   if (L.n_rows <= 0 || L.n_cols <= 0) return set_error(ODF_ERR_ARG, "empty operand");
   if (L.mode == MODE_MMV && !(L.T_pad == 16 || L.T_pad == 32))
     return set_error(ODF_ERR_ARG, "T_pad must be 16 or 32");
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
+  bool& attr_set = attr_once.here();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gauss_tile_kernel<KIND_TF32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess)

@@ -55,7 +55,7 @@ constexpr int EPI_WARPS = 4;               // epilogue warps: 4 (one per TMEM la
 constexpr int NTHREADS = (4 + EPI_WARPS) * 32;
 constexpr int QN_SLOTS = 4;
 constexpr int QN_BYTES = QN_SLOTS * BN * 4;                // ring of |c|^2 for 4 column tiles
-constexpr int NUM_BARS = 2 * NS + 7 + 2 * QN_SLOTS;
+constexpr int NUM_BARS = 2 * NS + 8 + 2 * QN_SLOTS;
 constexpr int SMEM_BYTES = NS * STAGE_BYTES + V_BYTES + QN_BYTES + NUM_BARS * 8 + 16 + 1024;
 
 // TMEM: S / packed K buffers 0 and 1, then the three K.V accumulators (hi.hi, lo.hi, hi.lo), 32 columns each
@@ -136,7 +136,10 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int B_FULL = 0, B_EMPTY = NS, B_SFULL = 2 * NS, B_PREADY = 2 * NS + 2, B_VFULL = 2 * NS + 3,
             B_VEMPTY = 2 * NS + 4, B_WFULL = 2 * NS + 5, B_WEMPTY = 2 * NS + 6, B_QFULL = 2 * NS + 7,
-            B_QEMPTY = 2 * NS + 7 + QN_SLOTS;
+            B_QEMPTY = 2 * NS + 7 + QN_SLOTS, B_PREADY1 = 2 * NS + 7 + 2 * QN_SLOTS;
+  // one "epilogue done" barrier per S buffer: a single barrier lets an epilogue warp that runs a tile ahead arrive twice
+  // in one phase (see odf_gauss_tile.cu); nothing in this kernel delays a warp by a whole tile today, but nothing forbids it
+  auto PREADY = [&](uint32_t b) { return BAR(b ? B_PREADY1 : B_PREADY); };
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -161,6 +164,7 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
     mbar_init(BAR(B_SFULL + 0), 1);
     mbar_init(BAR(B_SFULL + 1), 1);
     mbar_init(BAR(B_PREADY), 2 * EPI_WARPS * 32);
+    mbar_init(BAR(B_PREADY1), 2 * EPI_WARPS * 32);
     for (int s = 0; s < QN_SLOTS; ++s) {
       mbar_init(BAR(B_QFULL + s), 1);
       mbar_init(BAR(B_QEMPTY + s), EPI_WARPS);
@@ -258,7 +262,7 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
       bool pend = false, pend_first = false, pend_last = false;
 
       auto finish_prev = [&](uint32_t tile) {
-        mbar_wait_cluster(BAR(B_PREADY), tile & 1);
+        mbar_wait_cluster(PREADY(tile & 1), (tile >> 1) & 1);
         mbar_wait_cluster(BAR(B_VFULL), tile & 1);
         if (pend_first) {
           mbar_wait_cluster(BAR(B_WEMPTY), (item_cnt & 1) ^ 1);
@@ -418,7 +422,7 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
         if (lane == 0) mbar_arrive(BAR(B_QEMPTY + slot));
         tc_wait_st();
         tc_fence_before();
-        mbar_arrive_leader(BAR(B_PREADY));
+        mbar_arrive_leader(PREADY(b));
       }
       // W for this item is complete once the last tile's contraction has retired.
       mbar_wait_warp(BAR(B_WFULL), item_cnt & 1);
@@ -465,16 +469,7 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
 
 // ----------------------------------------------------------------------------- host side
 namespace {
-int g2_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int g2_num_sms() { return device_sm_count(); }
 }  // namespace
 
 // The pair kernel serves MODE_MMV launches with enough rows to keep every pair busy.
@@ -495,7 +490,8 @@ int launch_gauss_tile2(const TileLaunch& L, cudaStream_t stream) {
   if (L.d_pad % BK != 0 || L.d_pad <= 0) return set_error(ODF_ERR_ARG, "d_pad must be a positive multiple of the k-block width");
   if (L.n_rows <= 0 || L.n_cols <= 0) return set_error(ODF_ERR_ARG, "empty operand");
   if (L.mode != MODE_MMV || !(L.T_pad == 16 || L.T_pad == 32)) return set_error(ODF_ERR_ARG, "pair tile: MODE_MMV with T_pad 16 or 32");
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
+  bool& attr_set = attr_once.here();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gauss_tile2_kernel<KIND_TF32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gauss_tile2_kernel<KIND_F16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

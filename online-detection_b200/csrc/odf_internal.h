@@ -120,6 +120,28 @@ int tile_default_splits(int64_t n_rows, int64_t n_cols, int64_t row_bytes);
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
 
+
+// Per-device one-shot state (cudaFuncSetAttribute is per device; a process may touch several GPUs).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= kMaxDevices) ? 0 : dev;
+}
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool& here() { return done[current_device()]; }
+};
+inline int device_sm_count() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+
 inline int64_t kblock_elems(int kind) { return kind == KIND_F16 ? 64 : 32; }
 // operand row pitch in elements: padded features + seed block + ones block
 inline int64_t operand_pitch(int64_t d, int kind) {

@@ -188,7 +188,8 @@ int launch_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows
       (reinterpret_cast<uintptr_t>(W) & 15) != 0)
     return set_error(ODF_ERR_ARG, "panel_tmm: bad shape (16-byte aligned P, W; ldp >= round_up(M,128), ldp % 4 == 0)");
   if (n_splits != panel_splits(n_rows, M)) return set_error(ODF_ERR_ARG, "panel_tmm: n_splits must come from odf_panel_splits");
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
+  bool& attr_set = attr_once.here();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(panel_tmm_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(panel_tmm_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);

@@ -447,16 +447,7 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
   if (warp == 2) tmem_dealloc(tmem_base, QTM_COLS);
 }
 
-int q_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int q_num_sms() { return device_sm_count(); }
 
 }  // namespace
 
@@ -488,7 +479,8 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
       (reinterpret_cast<uintptr_t>(W16) & 127) != 0 || (reinterpret_cast<uintptr_t>(out_partial) & 15) != 0 || !absmax || (reinterpret_cast<uintptr_t>(absmax) & 15) != 0)
     return set_error(ODF_ERR_ARG, "panel16_tmm: bad shape or alignment (P16, W16 128-byte aligned; T_pad 16 or 32)");
   if (n_splits != panel16_splits(n_rows, M)) return set_error(ODF_ERR_ARG, "panel16_tmm: n_splits must come from odf_panel16_splits");
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
+  bool& attr_set = attr_once.here();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(panel16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(panel16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
@@ -536,7 +528,8 @@ int launch_panel16_mmv(const void* P16, int64_t n_rows, int64_t M, const void* V
       (reinterpret_cast<uintptr_t>(V16) & 127) != 0 || (reinterpret_cast<uintptr_t>(out_partial) & 15) != 0 || !absmax || (reinterpret_cast<uintptr_t>(absmax) & 15) != 0)
     return set_error(ODF_ERR_ARG, "panel16_mmv: bad shape or alignment (P16, V16 128-byte aligned; T_pad 16 or 32)");
   if (n_splits != panel16_mmv_splits(n_rows, M)) return set_error(ODF_ERR_ARG, "panel16_mmv: n_splits must come from odf_panel16_mmv_splits");
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
+  bool& attr_set = attr_once.here();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(panel16_mmv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(panel16_mmv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM);

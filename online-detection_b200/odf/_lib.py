@@ -54,12 +54,15 @@ SIGNATURES = {
                                  c_i64, c_fp]),
     "odf_gauss_kmm_prepared": (c_int, [c_int, c_fp, c_fp, c_fp, c_fp, c_i64, c_i64, c_f, c_fp, c_i64, c_fp]),
     "odf_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_i64, c_i64]),
+    "odf_precond_workspace_bytes": (c_sz, [c_i64]),
     "odf_gauss_mmv": (c_int, [c_fp, c_i64, c_i64, c_fp, c_i64, c_i64, c_i64, c_fp, c_i64, c_i64, c_f,
                               c_fp, c_i64, c_fp, c_sz, c_fp]),
     "odf_gauss_dmmv": (c_int, [c_fp, c_i64, c_i64, c_fp, c_i64, c_i64, c_i64, c_fp, c_i64, c_fp, c_i64,
                                c_i64, c_f, c_fp, c_i64, c_fp, c_sz, c_fp]),
     "odf_gauss_kmm": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_i64, c_fp, c_sz, c_fp]),
     "odf_precond_init": (c_int, [c_fp, c_fp, c_i64, c_f, c_f, c_fp, c_sz, c_fp]),
+    "odf_precond_build_workspace_bytes": (c_sz, [c_i64]),
+    "odf_precond_build": (c_int, [c_fp, c_fp, c_fp, c_fp, c_i64, c_f, c_f, c_fp, c_sz, c_fp]),
     "odf_precond_solve": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_fp]),
     "odf_precond_invert": (c_int, [c_fp, c_fp, c_i64, c_fp]),
     "odf_precond_apply": (c_int, [c_fp, c_i64, c_fp, c_fp, c_i64, c_i64, c_int, c_fp]),

@@ -31,8 +31,10 @@ class FalkonOptions:
     def __init__(self, cg_tolerance=1e-7, cg_full_gradient_every=10, cg_epsilon_32=1e-7, pc_epsilon_32=1e-5,
                  debug=False, operand_kind=None, **ignored):
         # ignored upstream knobs: keops_active, min_cuda_iter_size_32/64, min_cuda_pc_size_32/64,
-        # store_kernel_d_threshold, use_cpu, no_single_kernel … (placement / caching choices that
-        # have no meaning here: everything runs on the GPU and K_nm is never materialised)
+        # store_kernel_d_threshold, use_cpu, no_single_kernel … (placement / caching choices of upstream:
+        # here everything runs on the GPU, and whether K_nm is kept for the fit is `sweep_mode` below --
+        # the default keeps its fp16-plane panels resident in HBM when they fit, as upstream's
+        # store_kernel_d_threshold=250 does for the reference's sizes)
         self.cg_tolerance = cg_tolerance
         self.cg_full_gradient_every = cg_full_gradient_every
         self.cg_epsilon_32 = cg_epsilon_32
@@ -44,16 +46,19 @@ class FalkonOptions:
         # "inverse": apply T^-1 / A^-1 as GEMMs with explicit inverses built once per fit (default);
         # "trsm": four triangular solves per CG iteration, as upstream does
         self.precond_apply = ignored.pop("precond_apply", "inverse")
-        # "library": odf_precond_init (cuSOLVER potrf + cuBLAS sgemm); "blocked" (EXPERIMENTAL): the same factors through
-        # odf/precond_blocked.py, where every O(M^3) flop is a be.gemm call -- the hook for a tensor-core split GEMM
-        self.precond_build = ignored.pop("precond_build", "library")
+        # "tc" (default): odf_precond_build -- blocked Cholesky on row-major lower factors with every O(M^3) flop a 3-pass
+        # split-fp16 tcgen05 GEMM (csrc/odf_precond.cu), explicit inverses included; falls back to "library" when a pivot
+        # fails.  "library": odf_precond_init (cuSOLVER potrf + cuBLAS sgemm) + odf_precond_invert.  "blocked": the same
+        # factors through odf/precond_blocked.py (host-side blocked build on be.gemm; kept for the CPU host-logic tests).
+        # ODF_PRECOND_BUILD overrides the default.
+        self.precond_build = ignored.pop("precond_build", None) or os.environ.get("ODF_PRECOND_BUILD") or "tc"
         # "panel16": K is evaluated once per sweep, its tiles are spilled as fp16 hi/lo planes to a transient panel
         # and contracted by the tensor-core panel kernel; "panel": fp32 panel + fp32-FMA panel kernel;
         # "recompute": evaluate K twice (no panel workspace); "resident": the fp16-plane panels of every row chunk
-        # stay in HBM in both orientations -- they are filled by the first two sweeps of the fit and every later
-        # sweep is two passes of the panel kernel at HBM speed, no kernel value is evaluated again (2 x 4 B per
-        # value: 81 GB at N = 1 M, M = 10 k); "auto" (default): "resident" when that fits in the free device
-        # memory, else "panel16".  ODF_SWEEP_MODE overrides the default.
+        # stay in HBM (one copy, 4 B per kernel value: 40.5 GB at N = 1 M, M = 10 k) -- they are filled by the
+        # right-hand-side sweep of the fit and every later sweep is two passes of the panel kernels at HBM speed
+        # (K v, then K^T w), no kernel value is evaluated again; "auto" (default): as many row chunks resident as
+        # fit into 85 % of the free device memory, the rest streamed as in "panel16".  ODF_SWEEP_MODE overrides.
         self.sweep_mode = ignored.pop("sweep_mode", None) or os.environ.get("ODF_SWEEP_MODE") or "auto"
         # run the right-hand side sweep K_nm^T y (which also fills the resident K panels: tensor pipe + HBM) on a side
         # stream while the main stream builds the preconditioner (SIMT GEMMs and latency-bound Cholesky panels); the
@@ -301,6 +306,12 @@ class Falkon:
                     centres = X[torch.randperm(X.shape[0], generator=g)[:self.M]]
                 else:
                     centres = self.center_selection.select(X, None)
+                centres = centres.to(dev).to(torch.float32).contiguous()
+                if world > 1:
+                    # every rank picked from its OWN rows: rank 0's choice is the fit's centre set (as in the
+                    # device-resident branch below); without this the ranks would all-reduce partials of different K_nm
+                    src = dist.get_global_rank(group, 0) if group is not None else 0
+                    dist.broadcast(centres, src=src, group=group)
             centres = centres.to(dev)
             main = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev)
@@ -430,13 +441,27 @@ class Falkon:
         shard = None
         if dist is not None and world > 1 and getattr(opt, "distributed_apply", True) and M >= 4 * world:
             shard = (dist, group, world, dist.get_rank(group))
+        build = getattr(opt, "precond_build", "library")
+        if build == "tc" and hasattr(be, "precond_build_tc") and opt.precond_apply == "inverse" \
+                and not getattr(opt, "distributed_precond", None):
+            # every rank runs the same deterministic build on the same K_MM: bitwise identical factors, no collective
+            try:
+                Tm, Am, Ti, Ai = be.precond_build_tc(Kmm, lam, opt.pc_epsilon_32)
+                if prof0:
+                    prof0.mark("tc build")
+                    prof0.report()
+                return _InvFactor(be, Tm, Ti, shard=shard), _InvFactor(be, Am, Ai, shard=shard)
+            except Exception as exc:  # noqa: BLE001  a failed pivot (ODF_ERR_LINALG): rebuild K_MM for the library path
+                if "Cholesky failed" not in str(exc):
+                    raise
+                Kmm = be.kmm(pc, sigma)
         want = getattr(opt, "distributed_precond", None)
         want = (world >= 4) if want is None else bool(want)
         split = dist is not None and world > 1 and want and M >= 4 * world and hasattr(be, "potrf_upper_")
         if not split:
             prof = _SegTimer(Kmm.device) if os.environ.get("ODF_PRECOND_PROFILE") and Kmm.is_cuda else None
             if prof: prof.mark("kmm (since previous mark)")
-            if getattr(opt, "precond_build", "library") == "blocked":
+            if build == "blocked":
                 from . import precond_blocked
                 Tm, Am = precond_blocked.build(be, Kmm, lam, opt.pc_epsilon_32)
             else:
@@ -558,17 +583,29 @@ class Falkon:
         cg = be.CgState(M, T, dev)
         cg.init(R)
         on_gpu = dev.type == "cuda"
-        flag_host = torch.zeros(1, dtype=torch.float32)
+        flags_host = torch.zeros(self.maxiter + 1, dtype=torch.float32)
         if on_gpu:
-            flag_host = flag_host.pin_memory()
-        flag_ev = None
+            flags_host = flags_host.pin_memory()
+        flag_evs = []
         done = 0
         for i in range(self.maxiter):
             # Converged at an earlier iteration?  The device-side flag has already frozen every
-            # update, so leaving late costs sweeps, never correctness; the poll never blocks.
-            if on_gpu:
-                if flag_ev is not None and flag_ev.query() and float(flag_host[0]) != 0.0:
+            # update, so leaving late costs sweeps, never correctness.
+            if on_gpu and dist is None:
+                # single device: non-blocking poll of the most recent flag copy that has landed
+                if any(ev.query() and float(flags_host[k]) != 0.0 for k, ev in enumerate(flag_evs)):
                     break
+            elif on_gpu:
+                # Row-sharded fit: the exit must be the SAME iteration on every rank, or the collectives of the loop
+                # (the sweep's all-reduce, the sharded applications' all-gathers) pair up with the final ones of a rank
+                # that already left.  The CG state is replicated bit for bit, so every rank sees the same flag VALUE;
+                # what differed was WHEN a non-blocking poll saw it.  Read the flag of iteration i-2 with a blocking
+                # wait on its own event (iteration i-1 is already queued behind it, so the device never idles): a
+                # deterministic function of the replicated state, hence a collective decision without a collective.
+                if i >= 2:
+                    flag_evs[i - 2].synchronize()
+                    if float(flags_host[i - 2]) != 0.0:
+                        break
             elif float(cg.converged_flag[0]) != 0.0:
                 break
             op(P, AP)
@@ -582,9 +619,10 @@ class Falkon:
             cg.beta(R, eps, tol)                     # rs_new, convergence flag, b = rs_new/(rs_old+eps)
             cg.xpby_b(P, R)                          # P = R + b P
             if on_gpu:
-                flag_host.copy_(cg.converged_flag, non_blocking=True)
-                flag_ev = torch.cuda.Event()
-                flag_ev.record()
+                flags_host[i:i + 1].copy_(cg.converged_flag, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                flag_evs.append(ev)
             done = i + 1
         # alpha = T^-1 A^-1 beta
         Tm.solve(Am.solve(beta, v, False), u, False)

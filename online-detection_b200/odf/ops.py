@@ -43,6 +43,11 @@ def _req(t, name, ndim=None):
         raise ValueError("%s must live on a CUDA device (the FALKON hot path has no CPU fallback)" % name)
     if t.dtype != torch.float32:
         raise ValueError("%s must be float32, got %s" % (name, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # libodf launches on the CURRENT device's current stream (one process per GPU): a tensor on another
+        # device would be read through a wrong-device launch.  Wrap the call in torch.cuda.device(t.device).
+        raise ValueError("%s lives on cuda:%d but the current device is cuda:%d (one device per process; use "
+                         "torch.cuda.set_device / torch.cuda.device)" % (name, t.device.index, torch.cuda.current_device()))
     if ndim is not None and t.dim() != ndim:
         raise ValueError("%s must be %d-D" % (name, ndim))
     return t
@@ -356,6 +361,24 @@ def precond_init(Tm, lam, eps):
     return Tm, Am
 
 
+def precond_build_tc(Kmm, lam, eps, inverses=True):
+    """Tensor-core build (odf_precond_build): K_MM (M x M, contiguous, overwritten with T) -> (T, A, T^-1, A^-1), all
+    upper triangular; the inverses are None when not asked for.  Raises OdfError (ODF_ERR_LINALG) on a failed pivot."""
+    L = _lib.load()
+    Kmm = _req(Kmm, "K_MM", 2)
+    M = Kmm.shape[0]
+    assert Kmm.is_contiguous() and Kmm.shape[1] == M
+    Am = torch.empty_like(Kmm)
+    Ti = torch.empty_like(Kmm) if inverses else None
+    Ai = torch.empty_like(Kmm) if inverses else None
+    wsb = int(L.odf_precond_build_workspace_bytes(M))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=Kmm.device)
+    check(L.odf_precond_build(ptr(Kmm), ptr(Am), ptr(Ti), ptr(Ai), M, float(lam), float(eps), ptr(ws), wsb, _stream()),
+          "odf_precond_build")
+    _count(8)       # own kernels outside the tile launches counted below are few; tile launches: see LAUNCHES note in bench
+    return Kmm, Am, Ti, Ai
+
+
 def potrf_upper_(A):
     """In-place Cholesky of a symmetric row-major matrix into its upper factor (A = U^T U)."""
     L = _lib.load()
@@ -543,16 +566,14 @@ class Sweeper:
     half re-evaluates K in the transposed orientation with the same fused tile (no panel workspace,
     2x tensor work).
 
-    mode "resident": the fp16-plane panels of ALL row chunks stay in HBM for the life of the Sweeper, in both
-    orientations (K_chunk and K_chunk^T, 2 x 4 B per kernel value: 81 GB for 1 M x 10 k, inside the 180 GB of
-    a B200).  The first two sweeps of a fit fill them as a by-product (the right-hand side sweep K^T y runs the
-    tile in the transposed orientation, the first operator application in the forward one, both with the spill
-    on); every later sweep evaluates no kernel value at all: K v and K^T w are two passes of the tensor-core
-    panel kernel over the resident planes, at HBM speed.  mode "auto" = "resident" when both panel sets fit in
-    the free device memory (resident_fits), else "panel16".
-    With RESIDENT_SINGLE_COPY only K_chunk is kept (half the memory): K v comes from the same panel through
-    odf_panel16_mmv (rows as the MMA's M dimension), and the right-hand side sweep fills the panels with a
-    forward tile pass."""
+    mode "resident": the fp16-plane panels of the row chunks stay in HBM for the life of the Sweeper.  Default
+    (RESIDENT_SINGLE_COPY): ONE copy, K_chunk, 4 B per kernel value (40.5 GB for 1 M x 10 k, inside the 180 GB of
+    a B200); the first sweep of a fit fills it as a by-product of a forward pass of the fused tile with the spill
+    on, every later sweep evaluates no kernel value at all: K v comes from the panel through odf_panel16_mmv (rows
+    as the MMA's M dimension) and K^T w through odf_panel16_tmm, two passes over the resident planes at HBM speed.
+    mode "auto" = as many row chunks resident as fit (resident_plan), the rest streamed through one transient panel
+    as in "panel16".  ODF_RESIDENT_SINGLE=0 selects the first version (K_chunk and K_chunk^T both resident, 2 x 4 B
+    per value, transposed tile pass for the right-hand side sweep)."""
 
     def __init__(self, rows, cols, sigma, T, mode="panel16", resident_chunks=None):
         auto = mode == "auto"
