@@ -208,13 +208,15 @@ int odf_precond_init(float* Tm, float* Am, int64_t M, float lam, float eps, void
                      size_t ws_bytes, void* stream);
 /* The same factors (and, when Tinv / Ainv are not NULL, their explicit inverses: all four upper triangular with a zero
  * strict lower triangle, pitch M) with every O(M^3) flop on the tensor cores: blocked Cholesky on row-major lower
- * factors -- cuSOLVER potrf only on the 1024 x 1024 diagonal blocks, cuBLAS trsm for the row panels, the trailing
- * updates, T T^T and the divide-and-conquer triangular inverses as 3-pass split-fp16 tcgen05 GEMMs (odf_gemm_nt_split's
- * tile), contraction chains of at most 1024.  In: K = K_MM (overwritten with T).  SYNCHRONOUS (reads the pivots' status);
- * ODF_ERR_LINALG if a diagonal block is not positive definite.  ws >= odf_precond_build_workspace_bytes(M).        */
+ * factors -- cuSOLVER potrf only on the diagonal blocks (2048 wide, ODF_PRECOND_NB), cuBLAS trsm for the row panels; the
+ * trailing updates, T T^T and the divide-and-conquer triangular inverses are 3-pass split-fp16 tcgen05 GEMMs
+ * (odf_gemm_nt_split's tile) with contraction chains of at most 1024; T^-1 is computed on an internal stream beside
+ * T T^T and the second factorisation.  In: K = K_MM (DESTROYED: it ends up holding the lower factor of T).
+ * SYNCHRONOUS (reads the pivots' status); ODF_ERR_LINALG if a diagonal block is not positive definite.
+ * ws >= odf_precond_build_workspace_bytes(M).                                                                      */
 size_t odf_precond_build_workspace_bytes(int64_t M);
-int odf_precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws,
-                      size_t ws_bytes, void* stream);
+int odf_precond_build(float* K, float* Tm, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps,
+                      void* ws, size_t ws_bytes, void* stream);
 /* B [M x T] (pitch ldb) <- op(Tri)^-1 B with Tri upper triangular (pitch M), op by `which`.   */
 int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t ldb, int which,
                       void* stream);
@@ -273,6 +275,27 @@ size_t odf_cg_workspace_bytes(int64_t M, int64_t T);
 int odf_potrf_upper(float* A, int64_t M, void* ws, size_t ws_bytes, void* stream);
 int odf_add_diag(float* A, int64_t M, float value, void* stream);
 int odf_zero_strict_lower(float* A, int64_t M, void* stream);
+
+/* ---- RLS box-refinement regressors, all classes / anchors in one call ------------------------------------------- */
+/* RegionRefinerTrainer.train / solve (src/modules/region-refiner/region_refiner_trainer/train_region_refiner.py:25-119), fp64 as
+ * the reference: for every class c over ITS rows, Xi = [X 1],  w_k = (Xi^T Xi + lam I)^-1 Xi^T y'_k (k < 4),
+ * losses = (Xi w_k - y'_k)^2 / 2.  X [n x d] fp32 (pitch ldx); Yw [n x 4] fp64 = the centred, whitened targets (per ORIGINAL
+ * row); perm [n] = row indices sorted by class; seg_host [n_classes + 1] (HOST) = class boundaries in perm; row_class [n] =
+ * class of perm[r].  Out: W [n_classes][4][d + 1] fp32 (bias last), losses [n][4] fp32 in perm order.  The normal matrices
+ * of all classes come from ONE launch on the fp64 tensor cores (upper 64 x 64 tiles of [X 1 y']^T [X 1 y']), the
+ * factorisations from cuSOLVER Dpotrf / Dpotrs on internal side streams.  SYNCHRONOUS; ODF_ERR_LINALG on a failed pivot;
+ * classes without rows are skipped.  ws >= odf_rls_workspace_bytes(n, d, n_classes).                               */
+size_t odf_rls_workspace_bytes(int64_t n, int64_t d, int64_t n_classes);
+int odf_rls_train(const float* X, int64_t n, int64_t d, int64_t ldx, const double* Yw, const int64_t* perm,
+                  const int64_t* seg_host, const int* row_class, int64_t n_classes, double lam, float* W, float* losses,
+                  void* ws, size_t ws_bytes, void* stream);
+/* RegionPredictor.predict (src/modules/region-refiner/region_predictor/predict_regions.py:16-80; the *_parallel heads
+ * roi_box_predictors.py:97-124, rpn.py:158-187) for one image, fused: y = feat Wp + bias (Wp [d x 4 C], class-major columns),
+ * per class y T_inv + mu, box decode with the predictor's eps-width convention, clamp to the image; out [n][C + 1][4] with
+ * the un-refined box in slot 0.  mean != NULL fuses zScores ((feat - mean) * zscale) into the feature load.        */
+int odf_rls_apply(const float* feat, int64_t n, int64_t d, int64_t ldf, const float* Wp, const float* bias,
+                  const float* Tinv, const float* mu, const float* ex_boxes, int64_t C, float img_w, float img_h, float eps,
+                  const float* mean, float zscale, float* out, void* stream);
 
 /* ---- index / integer side: minibootstrap selection, box decode, detection post-processing ---- */
 /* Stable stream compaction: idx_out[0..*count_out) = ascending indices i in [0, n) with

@@ -196,9 +196,17 @@ int lib_handles(cudaStream_t st, cublasHandle_t* blas, cusolverDnHandle_t* solve
   *solver = g_cusolver;
   return ODF_OK;
 }
+size_t rls_workspace_bytes(int64_t n, int64_t d, int64_t n_classes, int lwork);
+int rls_query_lwork(int64_t d, int* lwork);
+int rls_train(const float* X, int64_t n, int64_t d, int64_t ldx, const double* Yw, const int64_t* perm, const int64_t* seg_host,
+              const int* row_class, int64_t n_classes, double lam, float* W, float* losses, void* ws, size_t ws_bytes,
+              cudaStream_t st);
+int rls_apply(const float* feat, int64_t n, int64_t d, int64_t ldf, const float* Wp, const float* bias, const float* Tinv,
+              const float* mu, const float* ex_boxes, int64_t C, float img_w, float img_h, float eps, const float* mean, float zscale,
+              float* out, cudaStream_t st);
 size_t precond_build_workspace_bytes(int64_t M, int lwork);
-int precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws, size_t ws_bytes,
-                  cudaStream_t st);
+int precond_build(float* K, float* Tm, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws,
+                  size_t ws_bytes, cudaStream_t st);
 }  // namespace odf
 
 using namespace odf;
@@ -575,18 +583,18 @@ size_t odf_precond_build_workspace_bytes(int64_t M) {
   if (M <= 0 || M > 0x7fffffff) return 0;
   int lwork = 0, ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && ensure_handles(nullptr) == ODF_OK) {
-    const int nb = static_cast<int>(M < 1024 ? M : 1024);
+    const int nb = static_cast<int>(M < 4096 ? M : 4096);
     if (cusolverDnSpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_UPPER, nb, nullptr, static_cast<int>(M), &lwork) != CUSOLVER_STATUS_SUCCESS)
       lwork = 0;
   } else {
     cudaGetLastError();
   }
-  if (lwork < (1 << 20)) lwork = 1 << 20;                  // generous floor: the exact figure is re-checked inside the build
+  if (lwork < (1 << 22)) lwork = 1 << 22;                  // generous floor: the exact figure is re-checked inside the build
   return precond_build_workspace_bytes(M, lwork);
 }
-int odf_precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws,
+int odf_precond_build(float* K, float* Tm, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws,
                       size_t ws_bytes, void* stream) {
-  return precond_build(K, Am, Tinv, Ainv, M, lam, eps, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return precond_build(K, Tm, Am, Tinv, Ainv, M, lam, eps, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 /* Building blocks of the same preconditioner for the row-sharded multi-GPU fit, where the O(M^3) pieces are
@@ -685,6 +693,31 @@ int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout
                                  static_cast<int>(M), &zero, Bout, static_cast<int>(ldb));
   if (s != CUBLAS_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "cublasSgemm (precond_apply) failed");
   return ODF_OK;
+}
+
+// ---------------------------------------------------------------- RLS box refiners (odf_rls.cu)
+size_t odf_rls_workspace_bytes(int64_t n, int64_t d, int64_t n_classes) {
+  if (n <= 0 || d <= 0 || n_classes <= 0) return 0;
+  int lwork = 0, ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    lwork = 1 << 22;
+  } else if (rls_query_lwork(d, &lwork) != ODF_OK) {
+    lwork = 1 << 22;
+  }
+  return rls_workspace_bytes(n, d, n_classes, lwork);
+}
+int odf_rls_train(const float* X, int64_t n, int64_t d, int64_t ldx, const double* Yw, const int64_t* perm, const int64_t* seg_host,
+                  const int* row_class, int64_t n_classes, double lam, float* W, float* losses, void* ws, size_t ws_bytes,
+                  void* stream) {
+  return rls_train(X, n, d, ldx, Yw, perm, seg_host, row_class, n_classes, lam, W, losses, ws, ws_bytes,
+                   static_cast<cudaStream_t>(stream));
+}
+int odf_rls_apply(const float* feat, int64_t n, int64_t d, int64_t ldf, const float* Wp, const float* bias, const float* Tinv,
+                  const float* mu, const float* ex_boxes, int64_t C, float img_w, float img_h, float eps, const float* mean,
+                  float zscale, float* out, void* stream) {
+  return rls_apply(feat, n, d, ldf, Wp, bias, Tinv, mu, ex_boxes, C, img_w, img_h, eps, mean, zscale, out,
+                   static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------- CG vector kernels

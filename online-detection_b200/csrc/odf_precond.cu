@@ -42,9 +42,34 @@ int add_diag(float*, int64_t, float, cudaStream_t);
 
 namespace {
 
-constexpr int64_t NB = 1024;       // diagonal block of the blocked Cholesky, leaf of the triangular inverse
+constexpr int64_t NB = 1024;       // block column of the tensor-core updates, leaf of the triangular inverse
 constexpr int64_t KSLICE = 1024;   // longest tensor-core accumulation chain
 constexpr int N_SIDE = 4;          // side streams for the independent leaf inversions
+constexpr int64_t NBC_MAX = 4096;  // largest diagonal block handed to cuSOLVER
+
+// Diagonal block of the blocked Cholesky (ODF_PRECOND_NB = 1024 / 2048 / 4096).  cuSOLVER's own potrf is latency-bound at
+// these sizes but much better per column than a chain of small library calls (measured on B200: potrf 0.35 / 0.67 /
+// 1.43 ms at n = 1024 / 2048 / 4096, trsm against a 1024-wide triangle 0.5 ms): fewer, larger diagonal blocks shorten
+// the sequential chain, everything off the diagonal still runs on the tensor cores.
+int64_t chol_block() {
+  static int64_t nbc = 0;
+  if (nbc == 0) {
+    const char* e = getenv("ODF_PRECOND_NB");
+    int64_t v = e ? atoll(e) : 2048;
+    if (v < NB) v = NB;
+    if (v > NBC_MAX) v = NBC_MAX;
+    nbc = v / NB * NB;
+  }
+  return nbc;
+}
+bool potrf_via_copy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ODF_PRECOND_POTRF_COPY");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 
 inline size_t al256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
 
@@ -79,6 +104,29 @@ tril_to_triu_kernel(float* __restrict__ A, int64_t n, int64_t ld, int nt) {
     if (r < n && c < n && c >= r && (bi != bj || c > r)) A[r * ld + c] = tile[tx][ty + 8 * k];
   }
   (void)nt;
+}
+
+// out (upper, strict lower zeroed) = (lower triangle of in)^T, both n x n with pitch ld; one CTA per 32 x 32 tile of out
+__global__ void __launch_bounds__(256)
+tril_transpose_copy_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, int64_t ld) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int by = blockIdx.y, bx = blockIdx.x;                     // tile (by, bx) of out
+  const int64_t r0 = static_cast<int64_t>(by) * 32, c0 = static_cast<int64_t>(bx) * 32;
+  if (bx >= by) {
+    // tile (bx, by) of in, lower part only
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t r = c0 + ty + 8 * k, c = r0 + tx;
+      tile[ty + 8 * k][tx] = (r < n && c < n && c <= r) ? in[r * ld + c] : 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t r = r0 + ty + 8 * k, c = c0 + tx;
+    if (r < n && c < n) out[r * ld + c] = (bx >= by) ? tile[tx][ty + 8 * k] : 0.f;
+  }
 }
 
 // out [n x n] (pitch ldo) = in^T (pitch ldi)
@@ -173,6 +221,7 @@ struct Build {
   cusolverDnHandle_t sol;
   Operand a, b;
   float* scratch;          // [M x M]: X11^T of the node being combined
+  float* diag;             // [nbc x nbc] contiguous copy of the diagonal block being factorised
   float* potrf_work;
   int lwork;
   int* info;               // device: one int per potrf call
@@ -217,16 +266,31 @@ int tile_nt(Build& B, const Operand& A, int64_t a0, int64_t m, const Operand& Bo
 // ---- blocked Cholesky, row-major lower, in place -----------------------------------------------------------------------
 int chol_lower(Build& B, float* G, int64_t M) {
   const float one = 1.f;
+  const int64_t NBC = chol_block();
   int rc;
-  for (int64_t j0 = 0; j0 < M; j0 += NB) {
-    const int64_t jb = (M - j0 < NB) ? (M - j0) : NB;
+  for (int64_t j0 = 0; j0 < M; j0 += NBC) {
+    const int64_t jb = (M - j0 < NBC) ? (M - j0) : NBC;
     float* D = G + j0 * M + j0;
     if (B.n_info >= B.info_cap) return set_error(ODF_ERR_ARG, "precond_build: too many diagonal blocks");
-    // row-major lower L11 == column-major upper U = L11^T
     B.cat.begin(CAT_POTRF, B.st);
-    if (cusolverDnSpotrf(B.sol, CUBLAS_FILL_MODE_UPPER, static_cast<int>(jb), D, static_cast<int>(M), B.potrf_work, B.lwork,
-                         B.info + B.n_info++) != CUSOLVER_STATUS_SUCCESS)
-      return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf (diagonal block) failed to launch");
+    if (potrf_via_copy()) {
+      // contiguous TRANSPOSED copy: only the row-major lower triangle of the block is valid (the updates write lower block
+      // columns), and transposed it is the column-major lower triangle cuSOLVER's fast path reads (LOWER potrf: 0.35 ms at
+      // 1024 against 0.92 ms for the strided UPPER call); the factor is written back transposed
+      dim3 grid(static_cast<unsigned>((jb + 31) / 32), static_cast<unsigned>((jb + 31) / 32));
+      transpose_kernel<<<grid, 256, 0, B.st>>>(D, M, B.diag, jb, jb);
+      if ((rc = launch_ok("transpose (diagonal block in)"))) return rc;
+      if (cusolverDnSpotrf(B.sol, CUBLAS_FILL_MODE_LOWER, static_cast<int>(jb), B.diag, static_cast<int>(jb), B.potrf_work, B.lwork,
+                           B.info + B.n_info++) != CUSOLVER_STATUS_SUCCESS)
+        return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf (diagonal block) failed to launch");
+      transpose_kernel<<<grid, 256, 0, B.st>>>(B.diag, jb, D, M, jb);      // row-major lower L11 <- (column-major lower)^T
+      if ((rc = launch_ok("transpose (diagonal block)"))) return rc;
+    } else {
+      // row-major lower L11 == column-major upper U = L11^T
+      if (cusolverDnSpotrf(B.sol, CUBLAS_FILL_MODE_UPPER, static_cast<int>(jb), D, static_cast<int>(M), B.potrf_work, B.lwork,
+                           B.info + B.n_info++) != CUSOLVER_STATUS_SUCCESS)
+        return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf (diagonal block) failed to launch");
+    }
     B.cat.end(B.st);
     const int64_t m = M - j0 - jb;
     if (m == 0) break;
@@ -237,12 +301,16 @@ int chol_lower(Build& B, float* G, int64_t M) {
                     static_cast<int>(m), &one, D, static_cast<int>(M), P, static_cast<int>(M)) != CUBLAS_STATUS_SUCCESS)
       return set_error(ODF_ERR_CUDA, "cublasStrsm (Cholesky panel) failed");
     B.cat.end(B.st);
-    // trailing update, lower block columns only: G[J0:M, J0:J1] -= L[J0:M, j] L[J0:J1, j]^T
-    if ((rc = prep(B, B.a, P, M, m, jb))) return rc;
-    for (int64_t J0 = j0 + jb; J0 < M; J0 += NB) {
-      const int64_t Jb = (M - J0 < NB) ? (M - J0) : NB;
-      const int64_t off = J0 - (j0 + jb);
-      if ((rc = tile_nt(B, B.a, off, M - J0, B.a, off, Jb, jb, -1.f, 1.f, G + J0 * M + J0, M, CAT_UPDATE))) return rc;
+    // trailing update, lower block columns only, one k-slice of the panel at a time:
+    //   G[J0:M, J0:J1] -= L[J0:M, slice] L[J0:J1, slice]^T
+    for (int64_t ks = 0; ks < jb; ks += KSLICE) {
+      const int64_t kw = (jb - ks < KSLICE) ? (jb - ks) : KSLICE;
+      if ((rc = prep(B, B.a, P + ks, M, m, kw))) return rc;
+      for (int64_t J0 = j0 + jb; J0 < M; J0 += NB) {
+        const int64_t Jb = (M - J0 < NB) ? (M - J0) : NB;
+        const int64_t off = J0 - (j0 + jb);
+        if ((rc = tile_nt(B, B.a, off, M - J0, B.a, off, Jb, kw, -1.f, 1.f, G + J0 * M + J0, M, CAT_UPDATE))) return rc;
+      }
     }
   }
   return ODF_OK;
@@ -379,63 +447,81 @@ struct Trace {
   }
 };
 
-// per-device side streams / events, created once
+// per-device side streams / events, created once: two sets (the main build and the inverse of T that runs beside it)
 struct SideStreams {
   bool made = false;
   cudaStream_t side[N_SIDE];
   cublasHandle_t blas[N_SIDE];
-  cudaEvent_t fork, join[N_SIDE];
+  cudaStream_t aux;
+  cudaEvent_t fork[2], join[2][N_SIDE], aux_go, aux_done;
 };
 SideStreams g_side[kMaxDevices];
 
-int side_streams(Build& B) {
+int side_streams(Build& B, int set, cudaStream_t* aux, cudaEvent_t* aux_go, cudaEvent_t* aux_done) {
   SideStreams& S = g_side[current_device()];
   if (!S.made) {
-    for (int s = 0; s < N_SIDE; ++s) {
-      if (cudaStreamCreateWithFlags(&S.side[s], cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&S.join[s], cudaEventDisableTiming) != cudaSuccess)
-        return set_error(ODF_ERR_CUDA, "precond_build: cannot create side streams");
-      if (cublasCreate(&S.blas[s]) != CUBLAS_STATUS_SUCCESS) return set_error(ODF_ERR_CUDA, "precond_build: cublasCreate failed");
-      cublasSetMathMode(S.blas[s], CUBLAS_DEFAULT_MATH);          // true fp32
-      cublasSetStream(S.blas[s], S.side[s]);
+    bool ok = cudaStreamCreateWithFlags(&S.aux, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&S.aux_go, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&S.aux_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int s = 0; ok && s < N_SIDE; ++s) {
+      ok = cudaStreamCreateWithFlags(&S.side[s], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&S.join[0][s], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&S.join[1][s], cudaEventDisableTiming) == cudaSuccess &&
+           cublasCreate(&S.blas[s]) == CUBLAS_STATUS_SUCCESS;
+      if (ok) {
+        cublasSetMathMode(S.blas[s], CUBLAS_DEFAULT_MATH);          // true fp32
+        cublasSetStream(S.blas[s], S.side[s]);
+      }
     }
-    if (cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) != cudaSuccess)
-      return set_error(ODF_ERR_CUDA, "precond_build: cannot create events");
+    ok = ok && cudaEventCreateWithFlags(&S.fork[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&S.fork[1], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return set_error(ODF_ERR_CUDA, "precond_build: cannot create side streams");
     S.made = true;
   }
-  for (int s = 0; s < N_SIDE; ++s) { B.side[s] = S.side[s]; B.ev_join[s] = S.join[s]; B.side_blas[s] = S.blas[s]; }
-  B.ev_fork = S.fork;
+  for (int s = 0; s < N_SIDE; ++s) { B.side[s] = S.side[s]; B.ev_join[s] = S.join[set][s]; B.side_blas[s] = S.blas[s]; }
+  B.ev_fork = S.fork[set];
+  if (aux) { *aux = S.aux; *aux_go = S.aux_go; *aux_done = S.aux_done; }
   return ODF_OK;
 }
 
 size_t operand_slice_bytes(int64_t rows) { return al256(static_cast<size_t>(rows) * operand_pitch(KSLICE, KIND_F16) * 2); }
+size_t operand_set_bytes(int64_t M) { return 2 * operand_slice_bytes(M) + al256(sizeof(float) * round_up(M, 128)) + 256; }
 
 }  // namespace
 
 size_t precond_build_workspace_bytes(int64_t M, int lwork) {
-  const size_t op = 2 * operand_slice_bytes(M) + al256(sizeof(float) * round_up(M, 128)) + 256;
   const int64_t n_blocks = (M + NB - 1) / NB;
-  return 2 * op + al256(static_cast<size_t>(M) * M * 4) + al256(sizeof(float) * static_cast<size_t>(lwork > 0 ? lwork : 1)) +
-         al256(sizeof(int) * static_cast<size_t>(2 * n_blocks + 2)) + 1024;
+  const int64_t nbc = M < NBC_MAX ? M : NBC_MAX;
+  // two builds' worth of operand slices and scratch (the inverse of T runs on its own stream beside T T^T / chol(A))
+  return 4 * operand_set_bytes(M) + 2 * al256(static_cast<size_t>(M) * M * 4) + al256(static_cast<size_t>(nbc) * nbc * 4) +
+         al256(sizeof(float) * static_cast<size_t>(lwork > 0 ? lwork : 1)) + al256(sizeof(int) * static_cast<size_t>(2 * n_blocks + 2)) + 1024;
 }
 
-int precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws, size_t ws_bytes,
+// K: K_MM in, destroyed (it ends up holding the lower factor of T).  Tm, Am: T, A (upper).  Tinv, Ainv: their inverses or NULL.
+int precond_build(float* K, float* Tm, float* Am, float* Tinv, float* Ainv, int64_t M, float lam, float eps, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
-  if (M <= 0 || M > 0x7fffffff || !K || !Am) return set_error(ODF_ERR_ARG, "precond_build: bad arguments");
+  if (M <= 0 || M > 0x7fffffff || !K || !Tm || !Am || K == Tm) return set_error(ODF_ERR_ARG, "precond_build: bad arguments");
   if ((Tinv == nullptr) != (Ainv == nullptr)) return set_error(ODF_ERR_ARG, "precond_build: Tinv and Ainv go together");
-  Build B{};
+  Build B{}, B2{};
   B.st = st;
   int rc;
   if ((rc = lib_handles(st, &B.blas, &B.sol))) return rc;
-  if ((rc = side_streams(B))) return rc;
-  const int nb = static_cast<int>(M < NB ? M : NB);
-  if (cusolverDnSpotrf_bufferSize(B.sol, CUBLAS_FILL_MODE_UPPER, nb, K, static_cast<int>(M), &B.lwork) != CUSOLVER_STATUS_SUCCESS)
+  cudaStream_t aux;
+  cudaEvent_t aux_go, aux_done;
+  if ((rc = side_streams(B, 0, &aux, &aux_go, &aux_done))) return rc;
+  if ((rc = side_streams(B2, 1, nullptr, nullptr, nullptr))) return rc;
+  B2.st = aux;
+  const int nbq = static_cast<int>(M < chol_block() ? M : chol_block());
+  if (cusolverDnSpotrf_bufferSize(B.sol, CUBLAS_FILL_MODE_LOWER, nbq, K, nbq, &B.lwork) != CUSOLVER_STATUS_SUCCESS)
     return set_error(ODF_ERR_CUDA, "cusolverDnSpotrf_bufferSize failed");
+  int lw2 = 0;
+  if (cusolverDnSpotrf_bufferSize(B.sol, CUBLAS_FILL_MODE_UPPER, nbq, K, static_cast<int>(M), &lw2) == CUSOLVER_STATUS_SUCCESS && lw2 > B.lwork)
+    B.lwork = lw2;
   if (ws_bytes < precond_build_workspace_bytes(M, B.lwork)) return set_error(ODF_ERR_WORKSPACE, "precond_build: workspace too small");
   // carve the workspace
   uint8_t* p = static_cast<uint8_t*>(ws);
   auto take = [&](size_t bytes) { uint8_t* r = p; p += al256(bytes); return r; };
-  for (Operand* o : {&B.a, &B.b}) {
+  for (Operand* o : {&B.a, &B.b, &B2.a, &B2.b}) {
     o->hi = take(operand_slice_bytes(M));
     o->lo = take(operand_slice_bytes(M));
     o->sqn = reinterpret_cast<float*>(take(sizeof(float) * round_up(M, 128)));
@@ -443,6 +529,8 @@ int precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, floa
     o->rows_cap = M;
   }
   B.scratch = reinterpret_cast<float*>(take(static_cast<size_t>(M) * M * 4));
+  B2.scratch = reinterpret_cast<float*>(take(static_cast<size_t>(M) * M * 4));
+  B.diag = reinterpret_cast<float*>(take(static_cast<size_t>(nbq) * nbq * 4));
   B.potrf_work = reinterpret_cast<float*>(take(sizeof(float) * static_cast<size_t>(B.lwork > 0 ? B.lwork : 1)));
   B.info_cap = static_cast<int>(2 * ((M + NB - 1) / NB) + 2);
   B.info = reinterpret_cast<int*>(take(sizeof(int) * static_cast<size_t>(B.info_cap)));
@@ -456,27 +544,35 @@ int precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, floa
     const char* e2 = getenv("ODF_PRECOND_TRACE");
     B.cat.on = e2 && atoi(e2) >= 2;
   }
-  // T: K_MM + eps M I = L L^T (in place), X = L^-1, then both to their upper forms
+  const dim3 tgrid(static_cast<unsigned>((M + 31) / 32), static_cast<unsigned>((M + 31) / 32));
+  // T: K_MM + eps M I = L L^T (in place in K)
   if ((rc = add_diag(K, M, eps * static_cast<float>(M), st))) return rc;
   if ((rc = chol_lower(B, K, M))) return rc;
+  const int n_info_T = B.n_info;
   tr.mark("chol(T)");
-  if (Tinv && (rc = inv_lower(B, K, Tinv, M))) return rc;
-  tr.mark("inv(T)");
-  if ((rc = to_upper(B, K, M))) return rc;                       // K now holds T
-  if (Tinv && (rc = to_upper(B, Tinv, M))) return rc;
-  tr.mark("transposes");
+  // X = L^-1 on the aux stream, beside T T^T and the second factorisation (which are latency-bound on the diagonal blocks)
+  if (Tinv) {
+    if ((e = cudaEventRecord(aux_go, st)) != cudaSuccess || (e = cudaStreamWaitEvent(aux, aux_go, 0)) != cudaSuccess)
+      return set_cuda_error(e, "precond_build: fork (aux)");
+    if ((rc = inv_lower(B2, K, Tinv, M))) return rc;
+    if ((rc = to_upper(B2, Tinv, M))) return rc;
+    if ((e = cudaEventRecord(aux_done, aux)) != cudaSuccess) return set_cuda_error(e, "precond_build: event (aux)");
+  }
+  tril_transpose_copy_kernel<<<tgrid, 256, 0, st>>>(K, Tm, M, M);                  // T = L^T, upper, strict lower zeroed
+  if ((rc = launch_ok("tril_transpose_copy_kernel"))) return rc;
   // A: T T^T / M + lam I = L_A L_A^T
   if ((e = cudaMemsetAsync(Am, 0, static_cast<size_t>(M) * M * 4, st)) != cudaSuccess) return set_cuda_error(e, "precond_build: memset (A)");
-  if ((rc = ttt_lower(B, K, Am, M))) return rc;
+  if ((rc = ttt_lower(B, Tm, Am, M))) return rc;
   if ((rc = add_diag(Am, M, lam, st))) return rc;
-  tr.mark("T T^T");
+  tr.mark("T^T copy + T T^T");
   if ((rc = chol_lower(B, Am, M))) return rc;
   tr.mark("chol(A)");
   if (Ainv && (rc = inv_lower(B, Am, Ainv, M))) return rc;
   tr.mark("inv(A)");
   if ((rc = to_upper(B, Am, M))) return rc;
   if (Ainv && (rc = to_upper(B, Ainv, M))) return rc;
-  tr.mark("transposes");
+  if (Tinv && (e = cudaStreamWaitEvent(st, aux_done, 0)) != cudaSuccess) return set_cuda_error(e, "precond_build: join (aux)");
+  tr.mark("transposes + join inv(T)");
 
   std::vector<int> hinfo(static_cast<size_t>(B.n_info), 0);
   e = cudaMemcpyAsync(hinfo.data(), B.info, sizeof(int) * hinfo.size(), cudaMemcpyDeviceToHost, st);
@@ -487,9 +583,9 @@ int precond_build(float* K, float* Am, float* Tinv, float* Ainv, int64_t M, floa
   for (size_t i = 0; i < hinfo.size(); ++i) {
     if (hinfo[i] != 0) {
       char buf[200];
-      const size_t per = static_cast<size_t>((M + NB - 1) / NB);
-      snprintf(buf, sizeof buf, "Cholesky failed in the %s factor: diagonal block %zu, info=%d (matrix not positive definite)",
-               i < per ? "T" : "A", i % per, hinfo[i]);
+      const bool in_T = static_cast<int>(i) < n_info_T;
+      snprintf(buf, sizeof buf, "Cholesky failed in the %s factor: diagonal block %d, info=%d (matrix not positive definite)",
+               in_T ? "T" : "A", static_cast<int>(i) - (in_T ? 0 : n_info_T), hinfo[i]);
       return set_error(ODF_ERR_LINALG, buf);
     }
   }

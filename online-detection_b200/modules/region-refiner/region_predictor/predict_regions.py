@@ -3,11 +3,19 @@
 Reference: src/modules/region-refiner/region_predictor/predict_regions.py:7-80 — same surface
 (`RegionPredictor(cfg, models)(boxes, features, normalize_features, stats)`), same output layout
 (each BoxList's bbox becomes (n, num_classes, 4) with the un-refined box in slot 0).
-All classes are applied in ONE GEMM: features @ [W_1 | W_2 | ...] (d x 4(C-1)), followed by a
-batched 4x4 un-whitening, instead of the reference's per-class loop.
+All classes are applied by ONE fused libodf kernel per image (`odf_rls_apply`, csrc/odf_rls.cu): features @ [W_1 | W_2 | ...]
+(d x 4(C-1)) + bias, the 4x4 un-whitening per class, the box decode and the clipping -- instead of the reference's
+per-class loop of matmuls; the optional z-scoring of the features is fused into the kernel's feature load.
 """
+import os
+import sys
+
 import numpy as np
 import torch
+
+_PKG = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), os.pardir, os.pardir, os.pardir))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
 
 
 class RegionPredictor:
@@ -29,34 +37,23 @@ class RegionPredictor:
                 bs.append(w[-1])
                 Tinv.append(m["T_inv"].to(device))
                 mu.append(m["mu"].to(device))
-            self._packed = (torch.cat(Ws, dim=1), torch.cat(bs), torch.stack(Tinv), torch.stack(mu))
+            self._packed = (torch.cat(Ws, dim=1).float().contiguous(), torch.cat(bs).float().contiguous(),
+                            torch.stack(Tinv).float().contiguous(), torch.stack(mu).float().contiguous())
         return self._packed
 
     def predict(self, boxes, features, normalize_features=False, stats=None):
-        n_cls = len(self.cfg["CHOSEN_CLASSES"])
+        from odf import ops
         img_w, img_h = boxes[0].size
-        dev = torch.device("cuda")
+        dev = torch.device("cuda", torch.cuda.current_device())
         W, b, Tinv, mu = self._pack(dev)
         eps = float(np.spacing(1))
+        mean, zscale = None, 1.0
+        if normalize_features:
+            mean = stats["mean"].to(dev).float()
+            zscale = 20.0 / float(stats["mean_norm"].item())
         for i in range(len(boxes)):
             not_gt = np.nonzero(features[i]["gt"] == 0)
-            feat = torch.tensor(features[i]["feat"][not_gt, :][0], device=dev)
-            if normalize_features:
-                feat = (feat - stats["mean"]) * (20 / stats["mean_norm"].item())
-            ex = boxes[i].bbox.to(dev)
-            n = ex.shape[0]
-            Y = (feat @ W + b).view(n, n_cls - 1, 4)
-            Y = torch.einsum("nck,ckj->ncj", Y, Tinv) + mu                    # un-whiten per class
-            src_w = (ex[:, 2] - ex[:, 0] + eps)[:, None]
-            src_h = (ex[:, 3] - ex[:, 1] + eps)[:, None]
-            ctr_x = ex[:, 0:1] + 0.5 * src_w
-            ctr_y = ex[:, 1:2] + 0.5 * src_h
-            pcx = Y[..., 0] * src_w + ctr_x
-            pcy = Y[..., 1] * src_h + ctr_y
-            pw = torch.exp(Y[..., 2]) * src_w
-            ph = torch.exp(Y[..., 3]) * src_h
-            pred = torch.stack(((pcx - 0.5 * pw).clamp(min=0), (pcy - 0.5 * ph).clamp(min=0),
-                                (pcx + 0.5 * pw - 1).clamp(max=img_w - 1), (pcy + 0.5 * ph - 1).clamp(max=img_h - 1)),
-                               dim=2)
-            boxes[i].bbox = torch.cat((ex[:, None, :], pred), dim=1)
+            feat = torch.as_tensor(features[i]["feat"][not_gt, :][0], dtype=torch.float32, device=dev)
+            ex = boxes[i].bbox.to(dev).float()
+            boxes[i].bbox = ops.rls_apply(feat, W, b, Tinv, mu, ex, img_w, img_h, eps, mean, zscale)
         return boxes

@@ -62,12 +62,15 @@ SIGNATURES = {
     "odf_gauss_kmm": (c_int, [c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_i64, c_fp, c_sz, c_fp]),
     "odf_precond_init": (c_int, [c_fp, c_fp, c_i64, c_f, c_f, c_fp, c_sz, c_fp]),
     "odf_precond_build_workspace_bytes": (c_sz, [c_i64]),
-    "odf_precond_build": (c_int, [c_fp, c_fp, c_fp, c_fp, c_i64, c_f, c_f, c_fp, c_sz, c_fp]),
+    "odf_precond_build": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_f, c_f, c_fp, c_sz, c_fp]),
     "odf_precond_solve": (c_int, [c_fp, c_i64, c_fp, c_i64, c_i64, c_int, c_fp]),
     "odf_precond_invert": (c_int, [c_fp, c_fp, c_i64, c_fp]),
     "odf_precond_apply": (c_int, [c_fp, c_i64, c_fp, c_fp, c_i64, c_i64, c_int, c_fp]),
     "odf_gemm": (c_int, [c_int, c_int, c_i64, c_i64, c_i64, c_f, c_fp, c_i64, c_fp, c_i64, c_f, c_fp, c_i64, c_fp]),
     "odf_precond_apply_rows": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_i64, c_i64, c_i64, c_int, c_fp]),
+    "odf_rls_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
+    "odf_rls_train": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_fp, c_fp, c_i64, ctypes.c_double, c_fp, c_fp, c_fp, c_sz, c_fp]),
+    "odf_rls_apply": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_f, c_f, c_f, c_fp, c_f, c_fp, c_fp]),
     "odf_cg_init": (c_int, [c_fp, c_i64, c_i64, c_i64, c_fp, c_fp, c_sz, c_fp]),
     "odf_cg_alpha": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp, c_sz, c_fp]),
     "odf_cg_axpy_a": (c_int, [c_fp, c_fp, c_i64, c_i64, c_i64, c_f, c_fp, c_fp]),

@@ -362,21 +362,22 @@ def precond_init(Tm, lam, eps):
 
 
 def precond_build_tc(Kmm, lam, eps, inverses=True):
-    """Tensor-core build (odf_precond_build): K_MM (M x M, contiguous, overwritten with T) -> (T, A, T^-1, A^-1), all
-    upper triangular; the inverses are None when not asked for.  Raises OdfError (ODF_ERR_LINALG) on a failed pivot."""
+    """Tensor-core build (odf_precond_build): K_MM (M x M, contiguous, DESTROYED) -> (T, A, T^-1, A^-1), all upper
+    triangular; the inverses are None when not asked for.  Raises OdfError (ODF_ERR_LINALG) on a failed pivot."""
     L = _lib.load()
     Kmm = _req(Kmm, "K_MM", 2)
     M = Kmm.shape[0]
     assert Kmm.is_contiguous() and Kmm.shape[1] == M
-    Am = torch.empty_like(Kmm)
+    Tm, Am = torch.empty_like(Kmm), torch.empty_like(Kmm)
     Ti = torch.empty_like(Kmm) if inverses else None
     Ai = torch.empty_like(Kmm) if inverses else None
     wsb = int(L.odf_precond_build_workspace_bytes(M))
     ws = torch.empty((wsb,), dtype=torch.uint8, device=Kmm.device)
-    check(L.odf_precond_build(ptr(Kmm), ptr(Am), ptr(Ti), ptr(Ai), M, float(lam), float(eps), ptr(ws), wsb, _stream()),
+    check(L.odf_precond_build(ptr(Kmm), ptr(Tm), ptr(Am), ptr(Ti), ptr(Ai), M, float(lam), float(eps), ptr(ws), wsb, _stream()),
           "odf_precond_build")
-    _count(8)       # own kernels outside the tile launches counted below are few; tile launches: see LAUNCHES note in bench
-    return Kmm, Am, Ti, Ai
+    nb = -(-M // 1024)
+    _count(12 + 3 * nb * nb)     # transposes / fills / diagonal shifts + operand pre-passes and tile launches (~3 nb^2)
+    return Tm, Am, Ti, Ai
 
 
 def potrf_upper_(A):
@@ -896,6 +897,48 @@ def resident_plan(n_rows, M, device, budget=None):
     per_chunk = int(L.odf_panel16_bytes(chunk, M))
     k = int((budget - per_chunk) // per_chunk)                      # one transient panel + k resident ones
     return max(0, min(k, n_rows // chunk))
+
+
+# ---- RLS box refiners ---------------------------------------------------------------------------
+def rls_train(X, Yw, perm, seg_host, row_class, lam):
+    """All classes' ridge regressors in one call (odf_rls_train).  X [n x d] fp32 (cuda), Yw [n x 4] fp64 whitened targets
+    per ORIGINAL row, perm [n_sel] int64 row indices sorted by class, seg_host: python list of n_classes + 1 boundaries in
+    perm, row_class [n_sel] int32.  Returns (W [n_classes x 4 x (d + 1)] fp32, losses [n_sel x 4] fp32 in perm order)."""
+    L = _lib.load()
+    X = _req(X, "X", 2)
+    X, ldx = _rowmajor(X)
+    n_sel, d, C = int(perm.shape[0]), int(X.shape[1]), len(seg_host) - 1
+    assert Yw.dtype == torch.float64 and Yw.is_contiguous() and Yw.shape == (X.shape[0], 4) and Yw.is_cuda
+    assert perm.dtype == torch.int64 and perm.is_contiguous() and row_class.dtype == torch.int32 and row_class.is_contiguous()
+    assert seg_host[0] == 0 and seg_host[-1] == n_sel
+    dev = X.device
+    W = torch.zeros((C, 4, d + 1), dtype=torch.float32, device=dev)
+    losses = torch.empty((max(n_sel, 1), 4), dtype=torch.float32, device=dev)
+    wsb = int(L.odf_rls_workspace_bytes(n_sel, d, C))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    seg = (ctypes.c_int64 * (C + 1))(*[int(v) for v in seg_host])
+    check(L.odf_rls_train(ptr(X), n_sel, d, ldx, ptr(Yw), ptr(perm), ctypes.cast(seg, ctypes.c_void_p), ptr(row_class), C,
+                          float(lam), ptr(W), ptr(losses), ptr(ws), wsb, _stream()), "odf_rls_train")
+    _count(4)
+    return W, losses[:n_sel]
+
+
+def rls_apply(feat, Wp, bias, Tinv, mu, ex_boxes, img_w, img_h, eps, mean=None, zscale=1.0):
+    """Fused RLS apply + un-whitening + box decode for one image (odf_rls_apply): out [n x (C + 1) x 4]."""
+    L = _lib.load()
+    feat, ldf = _rowmajor(_req(feat, "feat", 2))
+    n, d = int(feat.shape[0]), int(feat.shape[1])
+    C = int(mu.shape[0])
+    assert Wp.shape == (d, 4 * C) and Wp.is_contiguous() and bias.shape == (4 * C,) and Tinv.shape == (C, 4, 4) and Tinv.is_contiguous()
+    ex = _req(ex_boxes, "boxes", 2).contiguous()
+    out = torch.empty((n, C + 1, 4), dtype=torch.float32, device=feat.device)
+    if n == 0:
+        return out
+    mean = None if mean is None else _req(mean, "mean").contiguous()
+    check(L.odf_rls_apply(ptr(feat), n, d, ldf, ptr(Wp), ptr(bias.contiguous()), ptr(Tinv), ptr(mu.contiguous()), ptr(ex), C,
+                          float(img_w), float(img_h), float(eps), ptr(mean), float(zscale), ptr(out), _stream()), "odf_rls_apply")
+    _count(1)
+    return out
 
 
 # ---- index side: selection / gather (minibootstrap), box decode, detection post-processing ----

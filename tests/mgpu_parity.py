@@ -1,9 +1,12 @@
-"""Multi-GPU parity script (run under torchrun on a GPU box; not collected by pytest):
+"""Multi-GPU parity script (run under torchrun on a GPU box; tests/test_gpu_multi.py spawns it when >= 2 GPUs are visible):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_parity.py
 
-Row-sharded NCCL fit (distributed and replicated preconditioner) vs the single-GPU fit of the same data on
-rank 0 and vs the fp64 CPU oracle: alpha and scores must agree within the 1e-3 parity bar."""
+Row-sharded NCCL fit (tensor-core, replicated-library and distributed-library preconditioner) vs the single-GPU fit of
+the same data on rank 0 and vs the fp64 CPU oracle: alpha bitwise identical on all ranks, scores within the 1e-3 parity
+bar; a fit that CONVERGES before maxiter (large cg_tolerance: every rank must leave the CG loop at the same iteration, or
+the collectives dead-lock / mis-pair -- ADVICE r1 high); host-resident rows with centres picked by the fit itself (rank
+0's choice must be broadcast -- ADVICE r1 medium)."""
 import os
 import sys
 
@@ -32,7 +35,8 @@ def main():
     lo, hi = (N * rank) // world, (N * (rank + 1)) // world
     ok = True
     res = {}
-    for name, opts in (("replicated_precond", {"distributed_precond": False}), ("distributed_precond", {"distributed_precond": True})):
+    for name, opts in (("tensor_core_precond", {}), ("replicated_precond", {"precond_build": "library", "distributed_precond": False}),
+                       ("distributed_precond", {"precond_build": "library", "distributed_precond": True})):
         m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=None,
                              options=odf.FalkonOptions(**opts))
         m.fit(X[lo:hi].to(dev), Y[lo:hi].to(dev), centres=C.to(dev))
@@ -47,6 +51,34 @@ def main():
             print("%s: alpha bitwise identical on all ranks: %s   precond_ms=%.1f cg_ms=%.1f" % (
                 name, bool(flag.item()), m.fit_times_["precond_ms"], m.fit_times_["cg_ms"]))
         ok &= bool(flag.item())
+    # early convergence: a tolerance the CG reaches after a few iterations
+    m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=1e-2, M=M, process_group=None,
+                         options=odf.FalkonOptions(cg_tolerance=1.0))
+    m.fit(X[lo:hi].to(dev), Y[lo:hi].to(dev), centres=C.to(dev))
+    its = torch.tensor([float(m.fit_times_["cg_iters"])], device=dev)
+    lo_i, hi_i = its.clone(), its.clone()
+    dist.all_reduce(lo_i, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_i, op=dist.ReduceOp.MAX)
+    a0 = m.alpha_.clone()
+    dist.broadcast(a0, src=0)
+    same = torch.tensor([1.0 if torch.equal(a0, m.alpha_) else 0.0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("early exit: CG left after %d..%d iterations on the ranks (maxiter 20), alpha identical: %s"
+              % (int(lo_i.item()), int(hi_i.item()), bool(same.item())))
+    ok &= bool(same.item()) and int(lo_i.item()) == int(hi_i.item()) and int(hi_i.item()) < 20
+    # host-resident rows, centres chosen by the fit: every rank must end up with rank 0's centre set
+    m = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M, process_group=None, seed=3)
+    m.fit(X[lo:hi].contiguous(), Y[lo:hi].contiguous())
+    c0 = m.ny_points_.clone()
+    dist.broadcast(c0, src=0)
+    a0 = m.alpha_.clone()
+    dist.broadcast(a0, src=0)
+    same = torch.tensor([1.0 if (torch.equal(c0, m.ny_points_) and torch.equal(a0, m.alpha_)) else 0.0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("host rows + own centre selection: centres and alpha identical on all ranks: %s" % bool(same.item()))
+    ok &= bool(same.item())
     if rank == 0:
         single = odf.InCoreFalkon(kernel=odf.GaussianKernel(sigma), penalty=lam, M=M)
         single.fit(X.to(dev), Y.to(dev), centres=C.to(dev))
