@@ -32,7 +32,11 @@ WORKLOADS = {
     "c4": (5_000_000, 256, 5_000, 15, 50.0, 1e-3),
     "c3": (20_000_000, 256, 30_000, 21, 10.0, 1e-6),     # per-pixel mask head; needs --gpus 8 (or --n for one GPU's share)
     "c5": (1_000_000, 1024, 10_000, 30, 20.0, 1e-3),     # batched predict K(X, C) alpha (--workload c5 times predict, not fit)
+    # the reference's own regime (config_online_detection_icwt30.yaml): 30 classes x 10 minibootstrap batches
+    # of 2000 negatives, 2048-d RoI features, M = 2000, sigma 5, lambda 1e-4: N = classes, d, M, T = batches (see run_mb)
+    "mb": (30, 2048, 2_000, 10, 5.0, 1e-4),
 }
+RLS_SHAPES = ((50_000, 256, 15, 0.01), (50_000, 1024, 15, 0.01), (50_000, 2048, 30, 1000.0))   # n, d, classes, lambda (RPN / RPN / detector)
 CPU_SAMPLE = (50_000, 2_000)        # rows / centres of the CPU-baseline sample (ODF_CPU_SAMPLE="rows,centres" overrides)
 PARITY_SLICE = int(os.environ.get("ODF_PARITY_SLICE", "65536"))            # rows scored against the oracle with the GPU alpha
 PARITY_SUBFIT = tuple(int(v) for v in os.environ.get("ODF_PARITY_SUBFIT", "200000,4000").split(","))   # rows, centres of the fit compared with the fp64 oracle
@@ -464,6 +468,8 @@ def run_ours(args):
     import odf
     from odf import ops
 
+    if args.workload == "mb":
+        return run_mb(args, odf, ops, dist, world, rank, dev)
     N, d, M, T, sigma, lam = WORKLOADS[args.workload]
     if args.n:
         N = args.n
@@ -614,6 +620,10 @@ def run_ours(args):
         parity = parity_report(odf, ops, dist, world, rank, dev, model, Xh, Yh, centres, mean, scale, sigma, lam, M)
     if world > 1:
         dist.barrier()
+    # ---- BASELINE config 4 "plus RLS box-refinement regressors": the batched trainer at n ~ 50 k, d + 1 in {257, 1025, 2049}
+    rls = None
+    if args.workload == "c4" and rank == 0:
+        rls = rls_leg(dev)
     # ---- the same-config GPU / CPU pair at BASELINE config 1 (rank 0 of a single-GPU run) ------------------------------
     pair = None
     if rank == 0 and world == 1 and not args.no_c1_pair and not args.no_cpu_baseline:
@@ -650,7 +660,7 @@ def run_ours(args):
                           "over the measured fit time; with resident sweeps most of them are never executed -- fit_s is the "
                           "primary number, executed_tensor_tflops the work the tensor pipe really did",
             "executed_tensor_tflops": executed_tflops, "streaming_fit_s": (streaming or {}).get("fit_s"),
-            "streaming_value": (streaming or {}).get("value"), "parity": parity, "c1_pair": pair,
+            "streaming_value": (streaming or {}).get("value"), "parity": parity, "c1_pair": pair, "rls": rls,
             "sweep_mode_note": ("K panels (fp16 hi/lo planes, 4 B per kernel value%s, %.1f GB/GPU) filled by the first sweep%s of "
                                 "EVERY fit and kept in HBM for its remaining sweeps (two panel-kernel passes each, no kernel "
                                 "value re-evaluated); nothing is carried over between fits"
@@ -660,6 +670,153 @@ def run_ours(args):
             "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def rls_leg(dev):
+    """RegionRefinerTrainer.train (all classes in one libodf call) on synthetic COXY of BASELINE config 4's sizes, timed
+    with CUDA events around the public call; accuracy against the per-class fp64 restatement on one class."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "online-detection_b200", "modules", "region-refiner"))
+    from region_refiner_trainer import RegionRefinerTrainer
+    from oracle import falkon_oracle as orc
+    import contextlib
+    import io
+    out = []
+    for (n, d, n_cls, lam) in RLS_SHAPES:
+        g = torch.Generator().manual_seed(d)
+        X = torch.randn(n, d, generator=g) * 0.5
+        labels = torch.randint(1, n_cls + 1, (n, 1), generator=g).float()
+        Y = X[:, :4] * 0.3 + 0.1 * torch.randn(n, 4, generator=g)
+        cfg = {"CHOSEN_CLASSES": ["__background__"] + ["c%d" % i for i in range(1, n_cls + 1)]}
+        COXY = {"C": labels.to(dev), "O": None, "X": X.to(dev), "Y": Y.to(dev)}
+        tr = RegionRefinerTrainer(cfg, lam, is_rpn=False)
+        times = []
+        for rep in range(3):
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with contextlib.redirect_stdout(io.StringIO()):
+                models = tr(COXY)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            times.append(e0.elapsed_time(e1))
+        sel = (labels.view(-1) == 1).nonzero()[:, 0]
+        ref = orc.rls_train_class(X[sel], Y[sel], lam)
+        W = torch.stack([models[0]["Beta"][str(k)]["weights"] for k in range(4)], 1).cpu().double()
+        Wr = torch.stack([ref["Beta"][str(k)]["weights"] for k in range(4)], 1).double()
+        out.append({"n": n, "d_plus_1": d + 1, "classes": n_cls, "lambda": lam, "rls_ms": min(times), "first_call_ms": times[0],
+                    "weights_rel_err_vs_fp64_per_class_solve": float((W - Wr).abs().max() / Wr.abs().max()),
+                    "gram_fp64_tflops": 1e-9 * n * (d + 5.0) ** 2 / min(times)})
+    return {"what": "RegionRefinerTrainer.train: all classes in one odf_rls_train call (fp64 tensor-core Gram, cuSOLVER Dpotrf/Dpotrs)",
+            "shapes": out}
+
+
+def run_mb(args, odf, ops, dist, world, rank, dev):
+    """The reference's real regime: one-vs-all classifiers trained by minibootstrap through the drop-in
+    OnlineRegionClassifier_incore.trainRegionClassifier -- 30 classes x 10 batches of 2000 negatives, 2048-d features,
+    M = 2000 -- i.e. 300 small refits (N a few thousand rows, T = 1) plus 570 scoring passes.  One step = the whole
+    trainRegionClassifier call.  CPU baseline: the oracle's loop (same decisions) on a bounded number of classes."""
+    import contextlib
+    import io
+    import tempfile
+    import torch
+    import yaml
+    if rank != 0:
+        return
+    for p in ("modules", os.path.join("modules", "region-classifier")):
+        sys.path.insert(0, os.path.join(ROOT, "online-detection_b200", p))
+    import FALKONWrapper_with_centers_selection_incore as falkon
+    import OnlineRegionClassifier_incore as ocr
+    from oracle import falkon_oracle as orc
+    n_cls, d, M, n_batches, sigma, lam = WORKLOADS["mb"]
+    if args.n:
+        n_cls = args.n
+    P, B = 3000, 2000
+    cfg = {"CHOSEN_CLASSES": ["__background__"] + ["obj%d" % i for i in range(n_cls)],
+           "ONLINE_REGION_CLASSIFIER": {"CLASSIFIER": {"sigma": sigma, "lambda": lam, "M": M},
+                                        "MINIBOOTSTRAP": {"HARD_THRESH": -0.7, "EASY_THRESH": -0.9}}}
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "cfg.yaml")
+    with open(path, "w") as fh:
+        yaml.dump(cfg, fh)
+    g = torch.Generator().manual_seed(0)
+    protos = torch.randn(n_cls + 1, d, generator=g)
+
+    def draw(k, n):
+        x = protos[k] + 0.7 * torch.randn(n, d, generator=g)
+        return x * (20.0 / x.norm(dim=1).mean())
+
+    positives = [draw(t + 1, P) for t in range(n_cls)]
+    # negatives: background plus a share of other classes' objects (the hard ones)
+    negatives = []
+    for t in range(n_cls):
+        bs = []
+        for b in range(n_batches):
+            x = draw(0, B)
+            k = torch.randint(1, n_cls + 1, (B // 10,), generator=g)
+            k[k == t + 1] = 0
+            x[:B // 10] = (protos[k] + 0.7 * torch.randn(B // 10, d, generator=g)) * (20.0 / x.norm(dim=1).mean()) / 1.0
+            bs.append(x)
+        negatives.append(bs)
+    stats = {"mean": torch.zeros(d, device=dev), "std": torch.ones(d, device=dev), "mean_norm": torch.tensor(20.0, device=dev)}
+
+    def one_pass():
+        torch.manual_seed(1)
+        clf = falkon.FALKONWrapper(path)
+        rc = ocr.OnlineRegionClassifier(clf, [p.to(dev) for p in positives], [[b.to(dev) for b in bs] for bs in negatives], stats,
+                                        cfg_path=path)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return rc.trainRegionClassifier(opts={"normalized": True, "return_caches": True})
+
+    one_pass()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        models, caches = one_pass()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    launches = ops.LAUNCHES - l0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    # CPU: the oracle's loop on the first classes (bounded), fp32, all threads
+    n_cpu = min(2, n_cls)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+
+    def train_fn(X, y):
+        idx = orc.compute_indices_selection(y, M, generator=gen)
+        return (X[idx], orc.falkon_fit(X, y, X[idx], sigma, lam, dtype=torch.float32, cache_knm=True))
+
+    def predict_fn(model, X):
+        return orc.falkon_predict(X, model[0], model[1], sigma, dtype=torch.float32)
+    t0 = time.perf_counter()
+    same_sets = True
+    for t in range(n_cpu):
+        gen = torch.Generator().manual_seed(100 + t)
+        _model, neg_left = orc.minibootstrap(positives[t], negatives[t], train_fn, predict_fn)
+        # the GPU run draws its centres from torch's global RNG: the surviving sets are compared in size only
+        same_sets &= abs(int(neg_left.shape[0]) - int(caches[t]["neg"].shape[0])) <= max(20, int(0.02 * neg_left.shape[0]))
+    cpu_s = (time.perf_counter() - t0) / n_cpu * n_cls
+    refits = n_cls * n_batches
+    print(json.dumps({
+        "metric": "minibootstrap_train_s", "value": ms * 1e-3, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": 1,
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "none", "vs_baseline": None, "dtype": "f32 (3-pass split-fp16 tensor-core products)",
+        "data": "synthetic",
+        "config": {"workload": "mb: OnlineRegionClassifier_incore.trainRegionClassifier, %d classes x %d batches of %d negatives, %d positives, "
+                               "d=%d, M=%d, sigma=%g, lambda=%g (config_online_detection_icwt30.yaml)" % (n_cls, n_batches, B, P, d, M, sigma, lam),
+                   "l2_policy": "each refit works on a few thousand rows (fits in L2): this workload is launch / latency bound"},
+        "refits": refits, "ms_per_refit_and_scoring": ms / refits, "clocks": clocks, "gpu_launches": launches,
+        "surviving_negatives_per_class": [int(c["neg"].shape[0]) for c in caches],
+        "cpu_baseline": {"value": cpu_s, "unit": "s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "the oracle's minibootstrap loop (fp32, K_NM cached per refit) on %d of the %d classes, scaled to all classes" % (n_cpu, n_cls),
+                         "surviving_set_sizes_agree": bool(same_sets)},
+        "e2e": {"value": ms * 1e-3, "unit": "s", "h2d_bytes_per_step": int(n_cls * (P + n_batches * B) * d * 4), "d2h_bytes_per_step": 0,
+                "note": "features are uploaded inside the step (positives / negatives .to(device) in one_pass)"},
+        "roofline": None}))
 
 
 def run_predict(args, odf, ops, dist, world, rank, dev, Xh, Xd, centres, mean, scale, N, d, M, T, sigma, n_local):
@@ -718,14 +875,13 @@ def run_predict(args, odf, ops, dist, world, rank, dev, Xh, Xd, centres, mean, s
         pass
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     # e2e: raw host features in, scores back on the host
-    Xd.copy_(Xh, non_blocking=True)
+    host_scores = model.predict(Xh, zscore=(mean, scale))
     sync_all()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        Xd.copy_(Xh, non_blocking=True)
-        Xz = ops.zscore_(Xd, mean, scale)
-        host_scores = model.predict(Xz).cpu()
+        # the public call with HOST (pinned) rows: chunked upload behind the tile, z-score fused, scores back on the host
+        host_scores = model.predict(Xh, zscore=(mean, scale))
     t1.record()
     sync_all()
     ms_e2e = mx(t0.elapsed_time(t1)) / args.steps

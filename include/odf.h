@@ -221,12 +221,12 @@ int odf_precond_build(float* K, float* Tm, float* Am, float* Tinv, float* Ainv, 
 int odf_precond_solve(const float* Tri, int64_t M, float* B, int64_t T, int64_t ldb, int which,
                       void* stream);
 
-/* Explicit inverse of an upper-triangular factor (Inv = Tri^-1, upper, pitch M; one TRSM against
- * the identity, done once per fit) and its application as a plain GEMM:
- *   Bout = Inv B (transposed = 0)   or   Bout = Inv^T B (transposed = 1),   B, Bout: M x T, pitch ldb.
- * This replaces the 4 latency-bound triangular solves per CG iteration by bandwidth-bound GEMMs;
- * it is algebraically the same preconditioner (any invertible T~, A~ used consistently leaves the
- * fixed point of the preconditioned system unchanged up to the regulariser lam T~^T T~).          */
+/* Explicit inverse of an upper-triangular factor (Inv = Tri^-1, upper, pitch M; done once per fit) and its application
+ *   Bout = Inv B (transposed = 0)   or   Bout = Inv^T B (transposed = 1),   B, Bout: M x T, pitch ldb,
+ * by an own kernel that reads only the triangle of Inv and accumulates in fp64 (csrc/odf_tri.cu; ODF_PRECOND_APPLY=cublas
+ * selects the full-square cuBLAS sgemm of round 1).  This replaces the 4 latency-bound triangular solves per CG iteration;
+ * it is algebraically the same preconditioner (any invertible T~, A~ used consistently leaves the fixed point of the
+ * preconditioned system unchanged up to the regulariser lam T~^T T~).                                             */
 int odf_precond_invert(const float* Tri, float* Inv, int64_t M, void* stream);
 int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T,
                       int64_t ldb, int transposed, void* stream);

@@ -196,6 +196,8 @@ int lib_handles(cudaStream_t st, cublasHandle_t* blas, cusolverDnHandle_t* solve
   *solver = g_cusolver;
   return ODF_OK;
 }
+int tri_apply(const float* U, int64_t M, const float* Bm, int64_t ldb, int64_t T, float* out, int64_t ldo, int64_t row0, int64_t row1,
+              int transposed, cudaStream_t st);
 size_t rls_workspace_bytes(int64_t n, int64_t d, int64_t n_classes, int lwork);
 int rls_query_lwork(int64_t d, int* lwork);
 int rls_train(const float* X, int64_t n, int64_t d, int64_t ldx, const double* Yw, const int64_t* perm, const int64_t* seg_host,
@@ -671,21 +673,29 @@ int odf_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, float al
 int odf_precond_apply_rows(const float* Inv, int64_t M, int64_t r0, int64_t r1, const float* Bin, float* Bout_rows,
                            int64_t T, int64_t ldb, int64_t ldo, int transposed, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc;
-  if ((rc = ensure_handles(st))) return rc;
   if (r0 < 0 || r1 > M || r0 >= r1 || T <= 0 || ldb < T || ldo < T) return set_error(ODF_ERR_ARG, "precond_apply_rows: bad shape");
-  if (!transposed)        // Inv[r0:r1, r0:M] . Bin[r0:M, :]
-    return gemm_rm(false, false, r1 - r0, T, M - r0, 1.f, Inv + r0 * M + r0, M, Bin + r0 * ldb, ldb, 0.f, Bout_rows, ldo);
-  // Inv[0:r1, r0:r1]^T . Bin[0:r1, :]
-  return gemm_rm(true, false, r1 - r0, T, r1, 1.f, Inv + r0, M, Bin, ldb, 0.f, Bout_rows, ldo);
+  int rc;
+  for (int64_t t0 = 0; t0 < T; t0 += 32) {
+    const int64_t tw = (T - t0 < 32) ? (T - t0) : 32;
+    if ((rc = tri_apply(Inv, M, Bin + t0, ldb, tw, Bout_rows + t0, ldo, r0, r1, transposed, st))) return rc;
+  }
+  return ODF_OK;
 }
 
+// Bout = op(Inv) Bin for an upper-triangular Inv: own kernel (csrc/odf_tri.cu) that reads only the triangle and accumulates
+// in fp64; ODF_PRECOND_APPLY=cublas selects round 1's full-square cuBLAS sgemm.
 int odf_precond_apply(const float* Inv, int64_t M, const float* Bin, float* Bout, int64_t T, int64_t ldb,
                       int transposed, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Bin == Bout) return set_error(ODF_ERR_ARG, "precond_apply is out of place");
+  static int use_cublas = -1;
+  if (use_cublas < 0) {
+    const char* e = getenv("ODF_PRECOND_APPLY");
+    use_cublas = (e && strcmp(e, "cublas") == 0) ? 1 : 0;
+  }
+  if (!use_cublas) return odf_precond_apply_rows(Inv, M, 0, M, Bin, Bout, T, ldb, ldb, transposed, stream);
   int rc;
   if ((rc = ensure_handles(st))) return rc;
-  if (Bin == Bout) return set_error(ODF_ERR_ARG, "precond_apply is out of place");
   // row-major Bout = op(Inv) Bin   <=>   column-major Bout' (T x M) = Bin' (T x M) * op'(Inv')
   const float one = 1.f, zero = 0.f;
   cublasStatus_t s = cublasSgemm(g_cublas, CUBLAS_OP_N, transposed ? CUBLAS_OP_T : CUBLAS_OP_N, static_cast<int>(T),

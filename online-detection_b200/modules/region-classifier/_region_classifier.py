@@ -261,6 +261,26 @@ class OnlineRegionClassifierBase(rcA.RegionClassifierAbstract):
         return model
 
     # ------------------------------------------------------------------ per-image scoring
+    def _parallel_head(self, model):
+        """nystrom_parallel / alpha_parallel of the trained classes, as the reference's inference heads build them
+        (roi_box_predictors.py:140-160): the centres of all classes stacked, alpha block-diagonal (one column per class;
+        a class without a model keeps an all-zero column and is reported as -1 below, as the sequential loop would leave
+        it).  One call of kernel.mmv then scores every class of an image: one operand pre-pass (with the z-score fused)
+        and one launch of the fused tile instead of one of each per class."""
+        live = [(c, m) for c, m in enumerate(model[:self.num_classes - 1]) if m is not None]
+        if not live:
+            return None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        total = sum(int(m.ny_points_.shape[0]) for _c, m in live)
+        alpha = torch.zeros((total, self.num_classes - 1), dtype=torch.float32, device=dev)
+        row = 0
+        for c, m in live:
+            k = int(m.ny_points_.shape[0])
+            alpha[row:row + k, c] = m.alpha_.to(dev).reshape(-1)
+            row += k
+        centres = torch.cat([m.ny_points_.to(device=dev, dtype=torch.float32) for _c, m in live])
+        return live[0][1].kernel, centres, alpha, [c for c, _m in live]
+
     def testRegionClassifier(self, model, test_boxes):
         print("Online Region Classifier testing")
         predictions = []
@@ -273,6 +293,9 @@ class OnlineRegionClassifierBase(rcA.RegionClassifierAbstract):
             pass
         if self.HOST_CACHE and torch.is_tensor(self.mean):
             self.mean, self.std, self.mean_norm = self.mean.to("cuda"), self.std.to("cuda"), self.mean_norm.to("cuda")
+        # libodf models (their kernel caches the stacked operands between images): score all classes in one call
+        odf_models = any(m is not None and hasattr(getattr(m, "kernel", None), "_cached") for m in model)
+        head = self._parallel_head(model) if odf_models else None
         for entry in test_boxes:
             if entry is None:
                 continue
@@ -280,11 +303,19 @@ class OnlineRegionClassifierBase(rcA.RegionClassifierAbstract):
             boxes = entry["boxes"][not_gt, :][0]
             X_test = torch.tensor(entry["feat"][not_gt, :][0], device="cuda")
             t0 = time.time()
-            if self.mean_norm != 0:
-                X_test = self.zScores(X_test)
             scores = -torch.ones((len(boxes), self.num_classes))
-            for c in range(self.num_classes - 1):
-                scores[:, c + 1] = torch.squeeze(self.classifier.predict(model[c], X_test))
+            if head is not None:
+                kernel, centres, alpha, live = head
+                zs = None
+                if self.mean_norm != 0:
+                    zs = (self.mean.to(device=X_test.device, dtype=torch.float32), 20.0 / self.mean_norm.item())
+                s = kernel.mmv(X_test.float(), centres, alpha, zscore=zs)
+                scores[:, [c + 1 for c in live]] = s[:, live].cpu()
+            else:
+                if self.mean_norm != 0:
+                    X_test = self.zScores(X_test)
+                for c in range(self.num_classes - 1):
+                    scores[:, c + 1] = torch.squeeze(self.classifier.predict(model[c], X_test))
             total += time.time() - t0
             b = BoxList(torch.from_numpy(boxes), (entry["img_size"][0], entry["img_size"][1]), mode="xyxy")
             b.add_field("scores", scores.to("cpu"))

@@ -48,9 +48,8 @@ class FalkonOptions:
         self.precond_apply = ignored.pop("precond_apply", "inverse")
         # "tc" (default): odf_precond_build -- blocked Cholesky on row-major lower factors with every O(M^3) flop a 3-pass
         # split-fp16 tcgen05 GEMM (csrc/odf_precond.cu), explicit inverses included; falls back to "library" when a pivot
-        # fails.  "library": odf_precond_init (cuSOLVER potrf + cuBLAS sgemm) + odf_precond_invert.  "blocked": the same
-        # factors through odf/precond_blocked.py (host-side blocked build on be.gemm; kept for the CPU host-logic tests).
-        # ODF_PRECOND_BUILD overrides the default.
+        # fails.  "library": odf_precond_init (cuSOLVER potrf + cuBLAS sgemm) + odf_precond_invert (round 1's build; column
+        # blocks of it are split over the ranks with distributed_precond=True).  ODF_PRECOND_BUILD overrides the default.
         self.precond_build = ignored.pop("precond_build", None) or os.environ.get("ODF_PRECOND_BUILD") or "tc"
         # "panel16": K is evaluated once per sweep, its tiles are spilled as fp16 hi/lo planes to a transient panel
         # and contracted by the tensor-core panel kernel; "panel": fp32 panel + fp32-FMA panel kernel;
@@ -84,6 +83,17 @@ class GaussianKernel:
     def __init__(self, sigma, opt=None):
         self.sigma = float(sigma)
         self.opt = opt
+        self._cache = []          # [(X2 tensor, version, Prepared)], [(v tensor, version, ranges, split right-hand sides)]
+
+    # caches are device-side conveniences: never pickled / deep-copied with a model
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_cache"] = []
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self.__dict__.setdefault("_cache", [])
 
     def _kind(self):
         return getattr(self.opt, "operand_kind", None) if self.opt is not None else None
@@ -94,11 +104,26 @@ class GaussianKernel:
         kind = like.kind if isinstance(like, ops.Prepared) else self._kind()
         return ops.Prepared(X, kind=kind)
 
+    def _cached(self, tag, t, make):
+        """Per-kernel cache for operands that come back call after call as the SAME tensor object (the reference's
+        *_parallel heads keep `nystrom_parallel` / `alpha_parallel` as attributes and pass them for every image): the
+        entry holds the tensor itself (its storage cannot be recycled while cached) and its version counter."""
+        for k, obj, ver, val in self._cache:
+            if k == tag and obj is t and ver == t._version:
+                return val
+        val = make()
+        self._cache = [e for e in self._cache if e[0] != tag][-2:] + [(tag, t, t._version, val)]
+        return val
+
     def __repr__(self):
         return "GaussianKernel(sigma=%g)" % self.sigma
 
     # K(X1, X2) @ v
-    def mmv(self, X1, X2, v, out=None, opt=None):
+    def mmv(self, X1, X2, v, out=None, opt=None, zscore=None):
+        """falkon GaussianKernel.mmv(X1, X2, v, out=None).  `zscore=(mean, scale)` (extension) takes X1 as RAW features and
+        fuses OnlineRegionClassifier.zScores, (x - mean) * scale, into the operand pre-pass.  A block-structured v with
+        more than 32 columns (the `alpha_parallel` of the *_parallel heads) is contracted block by block against its own
+        centre rows: every kernel value is evaluated once, not once per 32 columns."""
         squeeze = v.dim() == 1
         if squeeze:
             v = v[:, None]
@@ -108,9 +133,18 @@ class GaussianKernel:
             out = torch.empty((n, T), dtype=torch.float32, device=v.device)
         if n == 0:
             return out[:, 0] if squeeze else out
-        cols = self._prep(X2, like=X1)
-        rows = self._prep(X1, like=cols)
-        ops.mmv_into(rows, cols, v, self.sigma, out)
+        if isinstance(X2, ops.Prepared):
+            cols = X2
+        else:
+            cols = self._cached("cols", X2, lambda: ops.Prepared(X2, kind=X1.kind if isinstance(X1, ops.Prepared) else self._kind()))
+        if isinstance(X1, ops.Prepared):
+            rows = X1
+        elif zscore is not None:
+            rows = ops.Prepared(X1, zscore[0], float(zscore[1]), kind=cols.kind)
+        else:
+            rows = self._prep(X1, like=cols)
+        ranges, rhs = self._cached("rhs", v, lambda: (ops.column_block_ranges(v), []))
+        ops.mmv_into(rows, cols, v, self.sigma, out, col_ranges=ranges, rhs_cache=rhs)
         return out[:, 0] if squeeze else out
 
     # K(X1, X2)^T (K(X1, X2) v + w)
@@ -270,6 +304,8 @@ class Falkon:
         st["_prep_cache"] = None
         st["process_group"] = False
         st["_ops"] = None
+        st.pop("_rhs_cache", None)
+        st.pop("_rhs_cache_key", None)
         return st
 
     def __setstate__(self, st):
@@ -278,6 +314,8 @@ class Falkon:
     def __setattr__(self, k, v):
         if k == "ny_points_":
             object.__setattr__(self, "_prep_cache", None)
+        if k == "alpha_":
+            object.__setattr__(self, "_rhs_cache_key", None)
         object.__setattr__(self, k, v)
 
     # ------------------------------------------------------------------ fit
@@ -461,11 +499,7 @@ class Falkon:
         if not split:
             prof = _SegTimer(Kmm.device) if os.environ.get("ODF_PRECOND_PROFILE") and Kmm.is_cuda else None
             if prof: prof.mark("kmm (since previous mark)")
-            if build == "blocked":
-                from . import precond_blocked
-                Tm, Am = precond_blocked.build(be, Kmm, lam, opt.pc_epsilon_32)
-            else:
-                Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
+            Tm, Am = be.precond_init(Kmm, lam, opt.pc_epsilon_32)
             if prof: prof.mark("precond_init")
             if opt.precond_apply == "inverse":
                 fT = _InvFactor(be, Tm, shard=shard)
@@ -637,18 +671,70 @@ class Falkon:
                                                                  kind=self.options.operand_kind))
         return self._prep_cache
 
-    def predict(self, X, y=None):
+    PREDICT_CHUNK = 131072          # rows per upload chunk of a host-resident predict
+
+    def predict(self, X, y=None, zscore=None):
+        """falkon Falkon.predict(X) -> (n x T) on X's device.  `zscore=(mean, scale)` (extension) takes X as RAW features
+        and fuses the z-scoring into the operand pre-pass.  HOST-resident X (the reference's `--CPU` flavour parks the
+        features there) is scored chunk by chunk: the upload of chunk i + 1 runs on a side stream while the tile scores
+        chunk i, and the scores come back with one copy at the end -- end to end the call costs max(upload, compute)
+        instead of their sum."""
         if self.alpha_ is None or self.ny_points_ is None:
             raise RuntimeError("Falkon model is not fitted")
         be = self._be
         alpha = self.alpha_ if self.alpha_.dim() == 2 else self.alpha_[:, None]
-        out = torch.empty((X.shape[0], alpha.shape[1]), dtype=torch.float32, device=X.device)
+        T = alpha.shape[1]
         if X.shape[0] == 0:
-            return out
+            return torch.empty((0, T), dtype=torch.float32, device=X.device)
         pc = self._centres_prepared()
-        be.mmv_into(be.Prepared(X.to(torch.float32), kind=getattr(pc, "kind", None)), pc, alpha.to(torch.float32),
-                    self.kernel.sigma, out)
-        return out
+        alpha = alpha.to(torch.float32)
+        zs = (None, 1.0) if zscore is None else (zscore[0], float(zscore[1]))
+        rhs = self._rhs_cache if getattr(self, "_rhs_cache_key", None) == (alpha.data_ptr(), alpha._version) else None
+        if rhs is None:
+            rhs = []
+            object.__setattr__(self, "_rhs_cache", rhs)
+            object.__setattr__(self, "_rhs_cache_key", (alpha.data_ptr(), alpha._version))
+        host = X.device.type == "cpu" and pc.hi.is_cuda and getattr(be, "__name__", "") == ops.__name__
+        if not host:
+            out = torch.empty((X.shape[0], T), dtype=torch.float32, device=X.device)
+            rows = be.Prepared(X.to(torch.float32), zs[0], zs[1], kind=getattr(pc, "kind", None))
+            if getattr(be, "__name__", "") == ops.__name__:
+                ops.mmv_into(rows, pc, alpha, self.kernel.sigma, out, rhs_cache=rhs)
+            else:
+                be.mmv_into(rows, pc, alpha, self.kernel.sigma, out)
+            return out
+        dev = pc.hi.device
+        n, d = X.shape
+        chunk = min(int(self.PREDICT_CHUNK), n)
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        out = torch.empty((n, T), dtype=torch.float32, device=dev)
+        bufs = [torch.empty((chunk, d), dtype=torch.float32, device=dev) for _ in range(2)]
+        done = [None, None]                      # event: the tile has finished reading buffer k
+        for b in bufs:
+            b.record_stream(side)
+        side.wait_stream(main)
+        starts = list(range(0, n, chunk))
+        ready = []
+        for i, r0 in enumerate(starts):
+            r1 = min(n, r0 + chunk)
+            k = i & 1
+            with torch.cuda.stream(side):
+                if done[k] is not None:
+                    side.wait_event(done[k])
+                bufs[k][:r1 - r0].copy_(X[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ready.append(ev)
+            main.wait_event(ev)
+            rows = be.Prepared(bufs[k][:r1 - r0], zs[0], zs[1], kind=getattr(pc, "kind", None))
+            ops.mmv_into(rows, pc, alpha, self.kernel.sigma, out[r0:r1], rhs_cache=rhs)
+            done[k] = torch.cuda.Event()
+            done[k].record(main)
+        res = torch.empty((n, T), dtype=torch.float32, pin_memory=X.is_pinned())
+        res.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return res
 
     def __repr__(self):
         return "%s(M=%d, penalty=%g, kernel=%r, maxiter=%d)" % (type(self).__name__, self.M, self.penalty,

@@ -430,10 +430,6 @@ def precond_apply(Inv, Bin, Bout, transposed):
     return Bout
 
 
-# EXPERIMENTAL: route large GEMMs of the (blocked) preconditioner build through the fused tile as a 3-pass split GEMM on
-# the tensor cores instead of cuBLAS sgemm.  ODF_GEMM_SPLIT=1.  Off by default: not yet validated on the GPU.
-GEMM_SPLIT = os.environ.get("ODF_GEMM_SPLIT", "0") not in ("0", "")
-GEMM_SPLIT_MIN = 512        # smallest m, n, k worth the operand pre-pass
 GEMM_SPLIT_KSLICE = 1024    # the tensor core accumulates with truncation: contraction chains are cut here and the slices
                             # are summed in fp32 round-to-nearest by the epilogue (beta = 1); tools/precision_study.py B
 
@@ -462,12 +458,8 @@ def gemm_nt_split(A, B, C, alpha=1.0, beta=0.0, kslice=None, kind=None):
 
 
 def gemm(A, B, C, trans_a=False, trans_b=False, alpha=1.0, beta=0.0):
-    """C = alpha op(A) op(B) + beta C on (possibly strided-row) fp32 views; true-fp32 cuBLAS sgemm (or, with
-    GEMM_SPLIT and large shapes, the tensor-core split GEMM on explicitly transposed operands)."""
-    if GEMM_SPLIT and min(C.shape[0], C.shape[1], A.shape[0] if trans_a else A.shape[1]) >= GEMM_SPLIT_MIN:
-        X = A.t().contiguous() if trans_a else A                    # [m x k]
-        Y = B if trans_b else B.t().contiguous()                    # [n x k]
-        return gemm_nt_split(X, Y, C, alpha, beta)
+    """C = alpha op(A) op(B) + beta C on (possibly strided-row) fp32 views; true-fp32 cuBLAS sgemm (the library flavour of the
+    row-sharded preconditioner build; the tensor-core GEMM of the default build is gemm_nt_split / odf_precond_build)."""
     L = _lib.load()
     assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
     m, n = C.shape
@@ -541,20 +533,58 @@ def axpby(out, alpha, A, beta=0.0, B=None):
 
 
 # ---- composite operators ----------------------------------------------------------------------
-def mmv_into(rows, cols, v, sigma, out):
+def column_block_ranges(v, block=32):
+    """Block structure of a right-hand side whose column blocks touch only part of the centre rows -- the `alpha_parallel`
+    of the reference's *_parallel heads (roi_box_predictors.py:140-160, rpn.py:201-227, roi_mask_predictors.py:72-99): one
+    non-zero row block per class.  Returns [(row_lo, row_hi)] per `block` columns (row_lo rounded down to a multiple of
+    128), or None when there is a single column block (nothing to gain).  One device -> host read; callers cache it."""
+    T = v.shape[1]
+    if T <= block:
+        return None
+    nz = (v != 0)
+    out = []
+    idx = torch.arange(v.shape[0], device=v.device)
+    big = v.shape[0]
+    lo_hi = []
+    for t0 in range(0, T, block):
+        rows_nz = nz[:, t0:t0 + block].any(dim=1)
+        lo = torch.where(rows_nz, idx, torch.full_like(idx, big)).min()
+        hi = torch.where(rows_nz, idx, torch.full_like(idx, -1)).max()
+        lo_hi.append(torch.stack((lo, hi)))
+    for lo, hi in torch.stack(lo_hi).cpu().tolist():
+        out.append((0, 0) if hi < 0 else (int(lo) // 128 * 128, int(hi) + 1))
+    return out
+
+
+def mmv_into(rows, cols, v, sigma, out, col_ranges=None, rhs_cache=None):
+    """out = K(rows, cols) v, 32 right-hand sides per launch of the fused tile.  `col_ranges` (column_block_ranges): every
+    column block is contracted against ITS centre rows only, so a block-structured v costs one evaluation of each kernel
+    value in total instead of one per column block.  `rhs_cache`: a list that keeps the split right-hand sides between
+    calls with the same v (filled on the first call)."""
     T = v.shape[1]
     dev = out.device
-    for t0 in range(0, T, 32):
+    for bi, t0 in enumerate(range(0, T, 32)):
         t1 = min(T, t0 + 32)
-        rhs = SplitRhs(cols.n, t1 - t0, dev).fill(v[:, t0:t1])
-        part = alloc_partial(rows, cols, rhs.T_pad, dev)
-        mmv_partial(rows, cols, rhs, sigma, part)
+        lo, hi = (0, cols.n) if col_ranges is None else col_ranges[bi]
+        dst = out[:, t0:t1]
+        if hi <= lo:
+            dst.zero_()
+            continue
+        cview = cols if (lo == 0 and hi == cols.n) else RowView(cols, lo, hi)
+        if rhs_cache is not None and len(rhs_cache) > bi:
+            rhs = rhs_cache[bi]
+        else:
+            rhs = SplitRhs(cview.n, t1 - t0, dev).fill(v[lo:hi, t0:t1])
+            if rhs_cache is not None:
+                rhs_cache.append(rhs)
+        part = alloc_partial(rows, cview, rhs.T_pad, dev)
+        mmv_partial(rows, cview, rhs, sigma, part)
         if out.stride(1) == 1:
-            finish_rows(part, t1 - t0, out[:, t0:t1])
+            finish_rows(part, t1 - t0, dst)
         else:
             tmp = torch.empty((rows.n, t1 - t0), dtype=torch.float32, device=dev)
             finish_rows(part, t1 - t0, tmp)
-            out[:, t0:t1].copy_(tmp)
+            dst.copy_(tmp)
 
 
 class Sweeper:

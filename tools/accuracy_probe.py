@@ -2,7 +2,7 @@
 d 1024, T 30, sigma 20, lambda 1e-3: the bench's parity sub-fit), one fp64 oracle fit on the CPU, and GPU fits that differ
 in ONE arithmetic choice each: how the preconditioner is applied (explicit inverse GEMM vs triangular solves), how it is
 built (tensor-core vs library), how the sweeps evaluate K (resident panels vs streamed tile), the operand kind.
-    python tools/accuracy_probe.py [N M]
+    python tools/accuracy_probe.py [N M [d T sigma lambda]]        ODF_PRECOND_APPLY=cublas: round 1's fp32 sgemm applications
 """
 import os
 import sys
@@ -24,6 +24,9 @@ def rel(a, b):
 def main():
     N, M = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (200000, 4000)
     d, T, sigma, lam = 1024, 30, 20.0, 1e-3
+    if len(sys.argv) > 6:
+        d, T, sigma, lam = int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5]), float(sys.argv[6])
+    print("N=%d M=%d d=%d T=%d sigma=%g lambda=%g" % (N, M, d, T, sigma, lam), flush=True)
     torch.set_num_threads(os.cpu_count() or 1)
     X, c, Y = orc.make_synthetic(N + 8192, d, T, seed=0)
     Xt, X, Y = X[N:], X[:N].contiguous(), Y[:N].contiguous()
