@@ -183,3 +183,29 @@ def test_batched_test_region_classifier_matches_the_per_class_loop(odf, tmp_path
         want = torch.cat([torch.full((50, 1), -1.0)] + [m.predict(Xz).cpu() for m in models], 1)
         got = p.get_field("scores")
         assert got.shape == (50, 4) and float((got - want).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("M,T", [(1, 1), (31, 3), (64, 32), (1000, 30), (2000, 1), (4097, 21), (10000, 30), (5000, 45)])
+def test_triangular_apply_matches_fp64(odf, M, T):
+    """odf_precond_apply / odf_precond_apply_rows (csrc/odf_tri.cu): out = U B and U^T B for an upper-triangular U whose
+    strict lower part holds garbage that must not be read, against the fp64 product; an application is an exactly rounded
+    linear map (fp64 accumulation), so the error is the final rounding to fp32."""
+    from odf import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 37 + T)
+    U = torch.randn(M, M, device="cuda", generator=g)
+    Ut = U.triu()
+    U = Ut + torch.full_like(U, float("nan")).tril(-1)          # the kernel must not touch the strict lower triangle
+    B = torch.randn(M, T, device="cuda", generator=g)
+    for tr in (False, True):
+        ref = (Ut.double().T if tr else Ut.double()) @ B.double()
+        out = torch.full_like(B, float("nan"))
+        ops.precond_apply(U, B, out, tr)
+        assert torch.isfinite(out).all()
+        assert float((out.double() - ref).abs().max()) <= 1.01 * 2.0 ** -24 * float(ref.abs().max())
+        # row ranges (the row-sharded application of a multi-GPU fit), including ragged ends
+        for r0, r1 in ((0, M), (M // 3, M), (M // 5, max(M // 5 + 1, (2 * M) // 3))):
+            if r1 <= r0:
+                continue
+            rows = torch.full((r1 - r0, T), float("nan"), device="cuda")
+            ops.precond_apply_rows(U, r0, r1, B, rows, tr)
+            assert torch.equal(rows, out[r0:r1]) or float((rows.double() - ref[r0:r1]).abs().max()) <= 1.01 * 2.0 ** -24 * float(ref.abs().max())

@@ -13,5 +13,5 @@ for tr in (False, True, False, True):
     ops.precond_apply(U, B, out, tr)
 torch.cuda.synchronize()
 PY
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tri_apply -s 2 -c 2 -f -o gpurun_out/r2k_tri_apply python /tmp/apply_one.py > gpurun_out/r2k_ncu.log 2>&1
-tail -3 gpurun_out/r2k_ncu.log; ls -la gpurun_out/r2k_tri_apply.ncu-rep
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tri_apply -s 2 -c 2 -f -o gpurun_out/r2p_tri_apply python /tmp/apply_one.py > gpurun_out/r2p_ncu.log 2>&1
+tail -3 gpurun_out/r2p_ncu.log; ls -la gpurun_out/r2p_tri_apply.ncu-rep
