@@ -156,6 +156,20 @@ int odf_panel16_tmm(const void* panel16, int64_t n_rows, int64_t M, const void* 
 int odf_panel16_mmv_splits(int64_t n_rows, int64_t M);
 int odf_panel16_mmv(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax,
                     int T_pad, int n_splits, float* out_partial, void* stream);
+/* ONE pass over a resident panel per sweep (csrc/odf_panel16_sweep.cu): for every group g of 4 row blocks (512 rows),
+ *   out_partial[g][c][0..T_pad) = sum_{r in group g} K[r][c] W[r][.],   W = K V   (K^T (K v) of falkon GaussianKernel.dmmv,
+ * reached from InCoreFalkon.fit, src/modules/region-classifier/FALKONWrapper_with_centers_selection_incore.py:68, with
+ * w = None as in every CG iteration).  The K v half of a group is read from HBM, its K^T w half two groups later from
+ * the L2: the panel is streamed from HBM once per sweep instead of twice (odf_panel16_mmv + odf_panel16_tmm).  W is split
+ * to fp16 hi | lo with one power-of-two scale per row block and column (computed on the fly; the two-pass path uses one
+ * scale per column).  v16 / absmax as for odf_panel16_mmv; w16 [round_up(n_rows,128) x 64] fp16 and `work`
+ * (odf_panel16_sweep_work_bytes, 256-byte aligned) are scratch; n_slabs = odf_panel16_sweep_slabs(n_rows) slabs of
+ * [M x T_pad] are written, to be summed in index order (odf_finish_rows).  Deterministic.                        */
+int odf_panel16_sweep_slabs(int64_t n_rows);
+size_t odf_panel16_sweep_work_bytes(int64_t n_rows, int64_t M);
+int odf_panel16_sweep(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax,
+                      int T_pad, void* w16, void* work, size_t work_bytes, float* out_partial, int n_slabs,
+                      void* stream);
 /* EXPERIMENTAL precision tier of the two panel contractions: only the hi plane is streamed (2 B per kernel value,
  * K to 11 bits; W / V keep their hi | lo split).  Same arguments and outputs as odf_panel16_tmm / odf_panel16_mmv.
  * A CPU emulation of the whole fit (tools/precision_study.py, profiles/r1_precision_study_cpu.log) puts the effect

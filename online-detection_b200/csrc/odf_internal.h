@@ -93,6 +93,10 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
 int panel16_mmv_splits(int64_t n_rows, int64_t M);
 int launch_panel16_mmv(const void* P16, int64_t n_rows, int64_t M, const void* V16, const uint32_t* absmax, int T_pad,
                        int n_splits, float* out_partial, cudaStream_t st, int hi_only = 0);
+int panel16_sweep_slabs(int64_t n_rows);
+size_t panel16_sweep_work_bytes(int64_t n_rows, int64_t M);
+int launch_panel16_sweep(const void* P16, int64_t n_rows, int64_t M, const void* V16, const uint32_t* absmax_v, int T_pad,
+                         void* W16, void* work, size_t work_bytes, float* out_partial, int n_slabs, cudaStream_t st);
 int finish_w16(const float* partial, int S, int64_t n, int T_pad, int64_t T, const float* addend, int64_t ld_add,
                float* Wf, uint32_t* absmax, void* W16, cudaStream_t st);
 // power-of-two scaling of W for the fp16 split: s * max|W| in [2^14, 2^15)

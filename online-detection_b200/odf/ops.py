@@ -300,6 +300,25 @@ def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial, hi_only=False):
     _count(1)
 
 
+def panel16_sweep(panel16, V16, absmax_v, n_rows, M, W16, work, out_partial):
+    """out_partial[g] = K[rows of group g]^T (K[rows of group g] V) for every 512-row group of a RESIDENT panel, in one
+    pass: K v of a group streams from HBM, K^T w of the same group two groups later from the L2 (odf_panel16_sweep)."""
+    L = _lib.load()
+    S, M_, T_pad = out_partial.shape
+    assert M_ == M and S == int(L.odf_panel16_sweep_slabs(n_rows)) and out_partial.is_contiguous()
+    assert work.dtype == torch.uint8 and work.numel() >= int(L.odf_panel16_sweep_work_bytes(n_rows, M))
+    ev = None
+    if PANEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(L.odf_panel16_sweep(ptr(panel16), n_rows, M, ptr(V16), ptr(absmax_v), T_pad, ptr(W16), ptr(work), work.numel(),
+                              ptr(out_partial), S, _stream()), "odf_panel16_sweep")
+    if ev is not None:
+        ev[1].record()
+        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_sweep_kernel"))
+    _count(2)
+
+
 def finish_rows(partial, T, out, scale=1.0, addend=None):
     L = _lib.load()
     S, n, T_pad = partial.shape
@@ -679,6 +698,12 @@ class Sweeper:
             self.absmax_v = torch.zeros((32,), dtype=torch.int32, device=dev)
             self.pslabs = [int(L.odf_panel16_splits(r1 - r0, M)) for (r0, r1) in self.chunks]
             self.part3 = torch.empty((sum(self.pslabs), M, Tp), dtype=torch.float32, device=dev)
+            # one-pass sweeps over filled resident panels (odf_panel16_sweep): one slab per 512-row group
+            self.fused = bool(RESIDENT_FUSED) and self.single and self.n_res > 0
+            if self.fused:
+                self.fslabs = [int(L.odf_panel16_sweep_slabs(r1 - r0)) for (r0, r1) in self.chunks[:self.n_res]]
+                self.part3f = torch.empty((sum(self.fslabs) + sum(self.pslabs[self.n_res:]), M, Tp), dtype=torch.float32, device=dev)
+                self.fwork = u8(max(int(L.odf_panel16_sweep_work_bytes(n, M)) for n in sizes))
         elif mode == "panel":
             self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
             self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
@@ -776,11 +801,19 @@ class Sweeper:
                 self.Vpad[0, :, :T].copy_(v)
                 finish_w16(self.Vpad, T, self.Vf, self.absmax_v, self.V16)
         slab = 0
+        # filled panels and no addend (every CG iteration): K v and K^T (K v) of a resident chunk in ONE pass over its panel
+        fused = self.fused and not fill and v is not None and w is None and not hi
+        part3 = self.part3f if fused else self.part3
         for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
             n = r1 - r0
             resident = i < self.n_res
             panel = self.fwd[i] if resident else self.transient
             tile = fill or not resident
+            if fused and resident:
+                S = self.fslabs[i]
+                panel16_sweep(panel, self.V16, self.absmax_v, n, M, self.W16, self.fwork, part3[slab:slab + S])
+                slab += S
+                continue
             if tile:
                 mmv_partial(view, self.cols, self.v_rhs, self.sigma, self.part1[n], panel16=panel)
             if v is None:
@@ -795,12 +828,12 @@ class Sweeper:
                 panel16_mmv(panel, self.V16, self.absmax_v, n, M, kv, hi_only=hi)           # K_chunk v, same panel
                 finish_w16(kv, T, self.Wf, self.absmax, self.W16, None if w is None else w[r0:r1])
             S = self.pslabs[i]
-            panel16_tmm(panel, self.W16, self.absmax, n, M, self.part3[slab:slab + S], hi_only=hi and not tile)  # K_chunk^T (K_chunk v + w)
+            panel16_tmm(panel, self.W16, self.absmax, n, M, part3[slab:slab + S], hi_only=hi and not tile)  # K_chunk^T (K_chunk v + w)
             slab += S
         self.have_fwd = True
         if self.n_res == len(self.chunks):
             self.part1 = None                                       # only the filling pass needs the tile's slabs
-        return finish_rows(self.part3, T, out, scale)
+        return finish_rows(part3[:slab], T, out, scale)
 
     def record_stream(self, stream):
         """Mark every buffer of the Sweeper as in use on `stream` (torch.Tensor.record_stream): needed when a sweep is
@@ -886,6 +919,9 @@ class Sweeper:
 # EXPERIMENTAL precision tier: resident sweeps stream the hi plane only (K to 11 bits, 2 B per value) once the panels
 # are filled.  ODF_PANEL_HI_ONLY=1.  Off by default: emulated on the CPU only so far (tools/precision_study.py).
 PANEL_HI_ONLY = os.environ.get("ODF_PANEL_HI_ONLY", "0") not in ("0", "")
+# one pass over a filled resident panel per sweep (odf_panel16_sweep: K v from HBM, K^T w of the same rows from the L2)
+# instead of two (odf_panel16_mmv + odf_panel16_tmm).  ODF_RESIDENT_FUSED=0 selects the two-pass sweeps.
+RESIDENT_FUSED = os.environ.get("ODF_RESIDENT_FUSED", "0") not in ("0", "")
 RESIDENT_FRACTION = 0.85   # share of the free device memory the resident panels may take in mode "auto"
 # keep only K_chunk (default) instead of K_chunk and K_chunk^T: K v then comes from the same panel through
 # odf_panel16_mmv, half the memory and no transposed tile pass.  ODF_RESIDENT_SINGLE=0 selects the two-copy variant.
