@@ -240,16 +240,21 @@ def tile_roofline(tile_events, steps, step_ms, peaks, traffic_json):
                     "split): algorithmic flops count each product once, so frac is capped at 1/3; "
                     "executed_frac_of_peak is the tensor-pipe work actually issued over the same cuBLAS bf16 peak"}
 
+TRAFFIC_JSON = "r2_ncu_traffic.json"      # DRAM bytes per launch from the committed ncu --set full captures
+PANEL_BYTES_PER_VALUE = 3.0      # odf_panel16_bytes: 2 B hi plane (fp16) + 1 B lo plane (rni((K - hi) 2^19) + 128)
+
+
 def panel_roofline(panel_events, steps, step_ms, peaks, traffic_json):
-    """The tensor-core panel contractions (HBM bound): each launch streams one fp16-plane panel, 4 B per kernel
-    value: panel16_kernel (K^T w) and, in the resident sweeps, panel16_mmv_kernel (K v from the same panel)."""
+    """The tensor-core panel contractions (HBM bound): each launch streams one K panel, 3 B per kernel value (fp16 hi
+    plane + one-byte fixed-point residual): panel16_kernel (K^T w) and, in the resident sweeps, panel16_mmv_kernel (K v
+    from the same panel)."""
     hbm_peak = peaks.get("hbm_gbs") or 6650.0
     per = {}
     for (a, b, n_, m_, _tp, *name) in panel_events:
         k = name[0] if name else "panel16_kernel"
         e = per.setdefault(k, [0.0, 0.0, 0])
         e[0] += a.elapsed_time(b)
-        e[1] += 4.0 * ((n_ + 127) // 128 * 128) * ((m_ + 127) // 128 * 128)
+        e[1] += PANEL_BYTES_PER_VALUE * ((n_ + 127) // 128 * 128) * ((m_ + 127) // 128 * 128)
         e[2] += 1
     t_ms, t_bytes, t_n = (sum(e[i] for e in per.values()) for i in range(3))
     p_gbs = t_bytes / max(t_ms, 1e-9) / 1e6
@@ -274,8 +279,9 @@ def panel_roofline(panel_events, steps, step_ms, peaks, traffic_json):
             "algorithmic_bytes_per_launch": t_bytes / max(t_n, 1),
             "share_of_step": t_ms / steps / step_ms,
             "per_kernel": {k: {"launches": e[2], "avg_launch_ms": e[0] / e[2], "GB/s": e[1] / e[0] / 1e6} for k, e in per.items()},
-            "note": "each launch streams one fp16 hi/lo K panel (4 B per kernel value) and contracts it with tcgen05 "
-                    "kind::f16 MMAs; a read-only stream, so it can exceed the read+write copy figure used as peak"}
+            "note": "each launch streams one K panel (3 B per kernel value: fp16 hi plane + one-byte fixed-point residual, widened "
+                    "to fp16 in shared memory) and contracts it with tcgen05 kind::f16 MMAs; a read-only stream, so it can "
+                    "exceed the read+write copy figure used as peak"}
 
 
 # ------------------------------------------------------------------------------ parity (outside the timed region)
@@ -337,8 +343,15 @@ def parity_report(odf, ops, dist, world, rank, dev, model, Xh, Yh, centres, mean
     t0 = time.perf_counter()
     a_ref = orc.falkon_fit(Xn, Ysub, Cn_s, sigma, lam, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7, cache_knm=True)
     t_fit = time.perf_counter() - t0
-    s_ref = orc.mmv((Xte.double() - mean64) * scale, Cn_s, a_ref, sigma)
+    Xte_n = (Xte.double() - mean64) * scale
+    s_ref = orc.mmv(Xte_n, Cn_s, a_ref, sigma)
     sf = _score_agreement(s_gpu, s_ref)
+    # the same algorithm in plain fp32 on the CPU (what upstream computes in float32): the noise floor of the comparison --
+    # 20 CG iterations amplify 1e-7 perturbations by three to four orders of magnitude on this problem
+    t0 = time.perf_counter()
+    a32 = orc.falkon_fit(Xn.float(), Ysub, Cn_s.float(), sigma, lam, dtype=torch.float32, cache_knm=True)
+    sf["cpu_fp32_port_vs_fp64_oracle"] = _score_agreement(orc.mmv(Xte_n, Cn_s, a32.double(), sigma), s_ref)
+    sf["cpu_fp32_port_fit_s"] = time.perf_counter() - t0
     # residual of the regularised normal equations, fp64, both alphas
     Kmm = orc.gaussian_kernel(Cn_s, Cn_s, sigma) + 1e-5 * m_s * torch.eye(m_s, dtype=torch.float64)
     A2 = torch.cat((sub.alpha_.cpu().double(), a_ref), 1)          # both alphas side by side: one pass over K
@@ -555,7 +568,7 @@ def run_ours(args):
         pass
     traffic_json = {}
     try:
-        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v12_traffic.json")))
+        traffic_json = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_JSON)))
     except Exception:  # noqa: BLE001
         pass
     sweep_mode = model.fit_times_.get("sweep_mode")
@@ -661,7 +674,7 @@ def run_ours(args):
                           "primary number, executed_tensor_tflops the work the tensor pipe really did",
             "executed_tensor_tflops": executed_tflops, "streaming_fit_s": (streaming or {}).get("fit_s"),
             "streaming_value": (streaming or {}).get("value"), "parity": parity, "c1_pair": pair, "rls": rls,
-            "sweep_mode_note": ("K panels (fp16 hi/lo planes, 4 B per kernel value%s, %.1f GB/GPU) filled by the first sweep%s of "
+            "sweep_mode_note": ("K panels (fp16 hi plane + 1-byte residual plane, 3 B per kernel value%s, %.1f GB/GPU) filled by the first sweep%s of "
                                 "EVERY fit and kept in HBM for its remaining sweeps (two panel-kernel passes each, no kernel "
                                 "value re-evaluated); nothing is carried over between fits"
                                 % ("" if ops.RESIDENT_SINGLE_COPY else ", both orientations", ops.resident_bytes(n_local, M) / 1e9,

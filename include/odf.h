@@ -111,10 +111,11 @@ int odf_gauss_mmv_prepared_spill(int kind, const void* r_hi, const void* r_lo, c
 int odf_panel_splits(int64_t n_rows, int64_t M);
 int odf_panel_tmm(const float* P, int64_t ldp, const float* W, int64_t n_rows, int64_t M, int T_pad,
                   int n_splits, float* out_partial, void* stream);
-/* Tensor-core variant of the spill + panel pair (the default sweep): the tile writes its K tiles as two fp16
- * planes, hi = rn16(K) and lo = rn16((K - hi) 2^12), tile-blocked
+/* Tensor-core variant of the spill + panel pair (the default sweep): the tile writes its K tiles as two planes,
+ * hi = rn16(K) (fp16) and lo = rni((K - hi) 2^19) + 128 (ONE BYTE: the residual in fixed point, 2^-20 absolute on
+ * K <= 1; 3 B per kernel value), both tile-blocked
  * [plane][column tile][row block][16 groups of 8 centres][128 rows][8] (odf_panel16_bytes(n_rows, n_cols) bytes,
- * 128-byte aligned); odf_finish_w16 reduces the partial slabs of the first contraction into W = K v (+ addend)
+ * 128-byte aligned; the panel kernels widen the lo bytes to fp16 in shared memory); odf_finish_w16 reduces the partial slabs of the first contraction into W = K v (+ addend)
  * [n_rows x T_pad] and splits it into W16 [round_up(n_rows,128) x 64] fp16 (hi | lo, per-column power-of-two
  * scales derived from max|W[:, t]|, left in absmax[32]); odf_panel16_tmm streams the planes once from HBM and contracts
  * out_partial[s][c][0..T_pad) = sum_r K[r][c] W[r][.] with tcgen05 kind::f16 MMAs on MN-major operands
@@ -156,20 +157,6 @@ int odf_panel16_tmm(const void* panel16, int64_t n_rows, int64_t M, const void* 
 int odf_panel16_mmv_splits(int64_t n_rows, int64_t M);
 int odf_panel16_mmv(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax,
                     int T_pad, int n_splits, float* out_partial, void* stream);
-/* ONE pass over a resident panel per sweep (csrc/odf_panel16_sweep.cu): for every group g of 4 row blocks (512 rows),
- *   out_partial[g][c][0..T_pad) = sum_{r in group g} K[r][c] W[r][.],   W = K V   (K^T (K v) of falkon GaussianKernel.dmmv,
- * reached from InCoreFalkon.fit, src/modules/region-classifier/FALKONWrapper_with_centers_selection_incore.py:68, with
- * w = None as in every CG iteration).  The K v half of a group is read from HBM, its K^T w half two groups later from
- * the L2: the panel is streamed from HBM once per sweep instead of twice (odf_panel16_mmv + odf_panel16_tmm).  W is split
- * to fp16 hi | lo with one power-of-two scale per row block and column (computed on the fly; the two-pass path uses one
- * scale per column).  v16 / absmax as for odf_panel16_mmv; w16 [round_up(n_rows,128) x 64] fp16 and `work`
- * (odf_panel16_sweep_work_bytes, 256-byte aligned) are scratch; n_slabs = odf_panel16_sweep_slabs(n_rows) slabs of
- * [M x T_pad] are written, to be summed in index order (odf_finish_rows).  Deterministic.                        */
-int odf_panel16_sweep_slabs(int64_t n_rows);
-size_t odf_panel16_sweep_work_bytes(int64_t n_rows, int64_t M);
-int odf_panel16_sweep(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax,
-                      int T_pad, void* w16, void* work, size_t work_bytes, float* out_partial, int n_slabs,
-                      void* stream);
 /* EXPERIMENTAL precision tier of the two panel contractions: only the hi plane is streamed (2 B per kernel value,
  * K to 11 bits; W / V keep their hi | lo split).  Same arguments and outputs as odf_panel16_tmm / odf_panel16_mmv.
  * A CPU emulation of the whole fit (tools/precision_study.py, profiles/r1_precision_study_cpu.log) puts the effect

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libodf.so")
-SOURCES = ["odf_gauss_tile.cu", "odf_gauss_tile2.cu", "odf_panel.cu", "odf_panel16.cu", "odf_panel16_sweep.cu", "odf_vec.cu", "odf_post.cu", "odf_precond.cu", "odf_rls.cu", "odf_tri.cu", "odf_api.cu"]
+SOURCES = ["odf_gauss_tile.cu", "odf_gauss_tile2.cu", "odf_panel.cu", "odf_panel16.cu", "odf_vec.cu", "odf_post.cu", "odf_precond.cu", "odf_rls.cu", "odf_tri.cu", "odf_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]

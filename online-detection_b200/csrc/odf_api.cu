@@ -348,13 +348,6 @@ int odf_panel16_mmv_hi(const void* panel16, int64_t n_rows, int64_t M, const voi
   return launch_panel16_mmv(panel16, n_rows, M, v16, static_cast<const uint32_t*>(absmax), T_pad, n_splits, out_partial,
                             static_cast<cudaStream_t>(stream), 1);
 }
-int odf_panel16_sweep_slabs(int64_t n_rows) { return panel16_sweep_slabs(n_rows); }
-size_t odf_panel16_sweep_work_bytes(int64_t n_rows, int64_t M) { return panel16_sweep_work_bytes(n_rows, M); }
-int odf_panel16_sweep(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax, int T_pad,
-                      void* w16, void* work, size_t work_bytes, float* out_partial, int n_slabs, void* stream) {
-  return launch_panel16_sweep(panel16, n_rows, M, v16, static_cast<const uint32_t*>(absmax), T_pad, w16, work, work_bytes,
-                              out_partial, n_slabs, static_cast<cudaStream_t>(stream));
-}
 int odf_panel16_mmv_splits(int64_t n_rows, int64_t M) { return panel16_mmv_splits(n_rows, M); }
 int odf_panel16_mmv(const void* panel16, int64_t n_rows, int64_t M, const void* v16, const void* absmax, int T_pad,
                     int n_splits, float* out_partial, void* stream) {

@@ -97,7 +97,7 @@ __device__ __forceinline__ WorkItem decode_item(const TileParams& p, int idx) {
 
 }  // namespace
 
-// SPILL16 = 1: the epilogue also writes every K tile as two fp16 planes (hi = rn16(K), lo = rn16((K - hi) * 2^12))
+// SPILL16 = 1: the epilogue also writes every K tile as two planes (hi = rn16(K) fp16, lo = rni((K - hi) * 2^19) + 128 bytes)
 // in the tile-blocked layout odf_panel16.cu streams back with TMA: [plane][column tile][row block][16 groups][128 rows][8].
 // LINEAR = 1 (MODE_STORE only, EXPERIMENTAL): the split GEMM A B^T behind the blocked preconditioner build
 // (odf/precond_blocked.py).  Operands come from odf_prepare_points_linear (zero seed block, so the accumulator is
@@ -378,7 +378,11 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
           if (p.dbg & 4) {
           } else if (mode_mmv) {
             uint32_t lo[32];
-            uint32_t ph[SPILL16 ? 16 : 1], pl[SPILL16 ? 16 : 1];
+            uint32_t ph[SPILL16 ? 16 : 1], pl[SPILL16 ? 8 : 1];
+            if (SPILL16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pl[i] = 0u;
+            }
             // tf32 split on the integer pipe: hi = K rounded to 11 bits (add half an ulp, clear 13 bits), lo = K - hi
             // exactly; the tensor core reads only the upper 19 bits of lo (2^-21 K).  Two cvt.rna per element
             // would share the 16-lane XU pipe with ex2 and made the epilogue the bottleneck at d <= 256.
@@ -398,9 +402,8 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
               if (SPILL16) {
                 const __half2 h = __floats2half2_rn(k0, k1);
                 const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn((k0 - hf.x) * 4096.f, (k1 - hf.y) * 4096.f);
                 ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+                pl[c >> 2] |= (lo8_of(k0 - hf.x) << (8 * (c & 3))) | (lo8_of(k1 - hf.y) << (8 * (c & 3) + 8));
               }
             }
             if (ch == 0 && n > 0) mbar_wait_warp(BAR(B_PVDONE), (n - 1) & 1);  // K_lo buffer free
@@ -411,12 +414,13 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
               // 512 contiguous bytes (with one row per thread and row-major tiles every STG touched 32 lines and the
               // LSU, not HBM, bounded the spill).  Rows past n_rows of the last block come from zero-filled
               // operands (finite K) and are written too; the matching W16 rows are zero.
-              __half* dst = p.panel16 + (((static_cast<int64_t>(j) * p.n_rowblocks + (w.row0 >> 7)) * 16 + ch * 4) * 128 + row) * 8;
+              const int64_t e0 = (((static_cast<int64_t>(j) * p.n_rowblocks + (w.row0 >> 7)) * 16 + ch * 4) * 128 + row) * 8;
+              __half* dst = p.panel16 + e0;
+              uint8_t* dlo = reinterpret_cast<uint8_t*>(p.panel16 + p.panel16_plane) + e0;     // one byte per value
 #pragma unroll
               for (int v = 0; v < 4; ++v) {
                 *reinterpret_cast<uint4*>(dst + v * 1024) = make_uint4(ph[4 * v], ph[4 * v + 1], ph[4 * v + 2], ph[4 * v + 3]);
-                *reinterpret_cast<uint4*>(dst + p.panel16_plane + v * 1024) =
-                    make_uint4(pl[4 * v], pl[4 * v + 1], pl[4 * v + 2], pl[4 * v + 3]);
+                *reinterpret_cast<uint2*>(dlo + v * 1024) = make_uint2(pl[2 * v], pl[2 * v + 1]);
               }
             }
             if (!SPILL16 && p.panel != nullptr && grow < p.n_rows) {
@@ -595,6 +599,21 @@ int make_map_plain_f16(CUtensorMap* m, const void* base, int64_t rows, int64_t c
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled (plain fp16 map) failed");
+  return ODF_OK;
+}
+
+// The same for bytes (the lo plane of the K panel).
+int make_map_plain_u8(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(ODF_ERR_CUDA, "cuTensorMapEncodeTiled (plain byte map) failed");
   return ODF_OK;
 }
 

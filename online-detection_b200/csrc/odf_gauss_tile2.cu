@@ -393,6 +393,11 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
           tc_wait_ld();
           if (p.dbg & 4) continue;
           uint32_t kp[32];                       // [0,16): hi pairs, [16,32): lo pairs (columns 2i, 2i+1 of the chunk)
+          uint32_t pl[SPILL16 ? 8 : 1];          // the spilled lo plane: one byte per value (lo8_of)
+          if (SPILL16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pl[i] = 0u;
+          }
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             float d0 = fmaf(m2inv, __uint_as_float(s[c]), rn + qn[c]);
@@ -405,16 +410,18 @@ gauss_tile2_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_consta
             const __half2 l = __floats2half2_rn((k0 - hf.x) * 4096.f, (k1 - hf.y) * 4096.f);
             kp[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
             kp[16 + (c >> 1)] = *reinterpret_cast<const uint32_t*>(&l);
+            if (SPILL16) pl[c >> 2] |= (lo8_of(k0 - hf.x) << (8 * (c & 3))) | (lo8_of(k1 - hf.y) << (8 * (c & 3) + 8));
           }
           tmem_st32(t_s + ch * 32, kp);          // in place: the chunk's 32 fp32 columns now hold its packed K
           if (SPILL16 && my_rb < rb128) {
-            __half* dst = p.panel16 + (((static_cast<int64_t>(j) * rb128 + my_rb) * 16 + ch * 4) * 128 + row) * 8;
+            const int64_t e0 = (((static_cast<int64_t>(j) * rb128 + my_rb) * 16 + ch * 4) * 128 + row) * 8;
+            __half* dst = p.panel16 + e0;
+            uint8_t* dlo = reinterpret_cast<uint8_t*>(p.panel16 + p.panel16_plane) + e0;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               // st.global.cs: written once, read once by the panel kernel -> first in line for eviction
               __stcs(reinterpret_cast<uint4*>(dst + v * 1024), make_uint4(kp[4 * v], kp[4 * v + 1], kp[4 * v + 2], kp[4 * v + 3]));
-              __stcs(reinterpret_cast<uint4*>(dst + p.panel16_plane + v * 1024),
-                     make_uint4(kp[16 + 4 * v], kp[17 + 4 * v], kp[18 + 4 * v], kp[19 + 4 * v]));
+              __stcs(reinterpret_cast<uint2*>(dlo + v * 1024), make_uint2(pl[2 * v], pl[2 * v + 1]));
             }
           }
         }

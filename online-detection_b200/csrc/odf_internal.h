@@ -84,6 +84,7 @@ int make_map_plain_f32(::CUtensorMap_st* m, const void* base, int64_t rows, int6
                        int box_cols);
 int make_map_sw128(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int esize);
 int make_map_plain_f16(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
+int make_map_plain_u8(::CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 int panel_splits(int64_t n_rows, int64_t M);
 // fp16-plane panel (tensor-core contraction, odf_panel16.cu)
 size_t panel16_bytes(int64_t n_rows, int64_t M);
@@ -93,12 +94,16 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
 int panel16_mmv_splits(int64_t n_rows, int64_t M);
 int launch_panel16_mmv(const void* P16, int64_t n_rows, int64_t M, const void* V16, const uint32_t* absmax, int T_pad,
                        int n_splits, float* out_partial, cudaStream_t st, int hi_only = 0);
-int panel16_sweep_slabs(int64_t n_rows);
-size_t panel16_sweep_work_bytes(int64_t n_rows, int64_t M);
-int launch_panel16_sweep(const void* P16, int64_t n_rows, int64_t M, const void* V16, const uint32_t* absmax_v, int T_pad,
-                         void* W16, void* work, size_t work_bytes, float* out_partial, int n_slabs, cudaStream_t st);
 int finish_w16(const float* partial, int S, int64_t n, int T_pad, int64_t T, const float* addend, int64_t ld_add,
                float* Wf, uint32_t* absmax, void* W16, cudaStream_t st);
+// lo plane of the K panel: the residual K - rn16(K) (|.| <= 2^-12 for K <= 1) in fixed point, one byte:
+// u = clamp(rni(r 2^19), -128, 127) + 128   (2^-20 absolute; widened back to fp16 by widen_lo8 in odf_panel16_common.cuh)
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t lo8_of(float r) {
+  const int i = max(-128, min(127, __float2int_rn(r * 524288.f)));
+  return static_cast<uint32_t>(i + 128);
+}
+#endif
 // power-of-two scaling of W for the fp16 split: s * max|W| in [2^14, 2^15)
 __host__ __device__ inline float w16_scale_from_bits(uint32_t absmax_bits, bool inverse) {
   const int e = static_cast<int>((absmax_bits >> 23) & 0xffu);

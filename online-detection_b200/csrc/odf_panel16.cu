@@ -1,6 +1,8 @@
 // Second half of a K^T (K v) sweep on the tensor cores: the fused tile (odf_gauss_tile.cu, SPILL16) leaves the K
-// tiles of one row chunk in HBM as two fp16 planes, hi = rn16(K) and lo = rn16((K - hi) * 2^12), tile-blocked as
-//     P16[plane][column tile j][row block rb][group g of 8 centres][128 rows][8]      (32 KB per (j, rb) and plane)
+// tiles of one row chunk in HBM as two planes, hi = rn16(K) (fp16) and lo = rni((K - hi) * 2^19) + 128 (ONE BYTE: the
+// residual in fixed point, 2^-20 absolute on K <= 1 -- 3 B per kernel value instead of the 4 B of an fp16 lo plane,
+// a quarter less HBM traffic for kernels that do nothing but stream the panel), tile-blocked as
+//     P16[plane][column tile j][row block rb][group g of 8 centres][128 rows][8]      (32 KB / 16 KB per (j, rb))
 // (the tile's epilogue owns one row per thread: with this order a warp-wide 16-byte store covers 512 contiguous bytes)
 // and this kernel contracts them with the finished W = K v + w of the same rows,
 //     out_partial[s][c][t] = sum_{r in row range s} K[r][c] * W[r][t],
@@ -19,8 +21,9 @@
 // warps drain the (double-buffered) accumulators into registers, combine the three terms and keep the running sums in
 // fp32 round-to-nearest.  Row ranges write separate slabs that odf_finish_rows reduces in index order (deterministic).
 //
-// Persistent, warp-specialised (256 threads, 1 CTA / SM): warp 0 TMA producer (5 stages of 64 rows = 40 KB: 200 KB
-// in flight per SM), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue (thread = TMEM lane = centre).
+// Persistent, warp-specialised (384 threads, 1 CTA / SM): warp 0 TMA producer (5 stages of 64 rows: 32 KB of loads each,
+// 160 KB in flight per SM), warps 8-11 widen the stage's lo bytes to fp16 in place (widen_lo8), warp 1 MMA issuer, warp 2
+// TMEM allocator, warps 4-7 epilogue (thread = TMEM lane = centre).
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include "odf_ptx.cuh"
@@ -49,27 +52,30 @@ struct Panel16Params {
 // HI_ONLY = 1 (experimental precision tier): only the hi plane is streamed (2 B per kernel value, 11 bits of
 // K): the lo loads, the acc2 MMAs and the lo.hi term of the read-out are dropped.
 template <int HI_ONLY>
-__global__ void __launch_bounds__(256, 1)
-panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmW, const Panel16Params p) {
+__global__ void __launch_bounds__(QTHREADS, 1)
+panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmW,
+               const Panel16Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QNS * QSTAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + QBARS);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  const int B_FULL = 0, B_EMPTY = QNS, B_AFULL = 2 * QNS, B_AEMPTY = 2 * QNS + 2;
+  const int B_FULL = 0, B_EMPTY = QNS, B_AFULL = 2 * QNS, B_AEMPTY = 2 * QNS + 2, B_CONV = 2 * QNS + 4;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmP);
+    tma_prefetch_desc(&tmL);
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < QNS; ++s) {
       mbar_init(BAR(B_FULL + s), 1);
       mbar_init(BAR(B_EMPTY + s), 1);
+      mbar_init(BAR(B_CONV + s), 4);
     }
     mbar_init(BAR(B_AFULL + 0), 1);
     mbar_init(BAR(B_AFULL + 1), 1);
@@ -105,13 +111,14 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
           // [total x 1024] fp16 view, one row per (plane, j, rb, g) holding [128 rows][8]; a box is 16 g x 32 rows
           const int y = (j * p.n_rb + (st >> 1)) * 16;
           const int x = (st & 1) * 512;
-          mbar_arrive_expect_tx(full, HI_ONLY ? QSTAGE - 2 * QBOX : QSTAGE);
+          mbar_arrive_expect_tx(full, HI_ONLY ? QSTAGE - 2 * QBOX : QSTAGE - QBOX);
           // the planes are read exactly once (evict first); W16 is shared by every column tile (evict last)
           tma_load_2d_hint(dst + 0 * QBOX, &tmP, full, x, y, kEvictFirst);
           tma_load_2d_hint(dst + 1 * QBOX, &tmP, full, x + 256, y, kEvictFirst);
           if (!HI_ONLY) {
-            tma_load_2d_hint(dst + 2 * QBOX, &tmP, full, x, p.plane_rows + y, kEvictFirst);
-            tma_load_2d_hint(dst + 3 * QBOX, &tmP, full, x + 256, p.plane_rows + y, kEvictFirst);
+            // lo bytes: two boxes of [16 centre groups][32 rows][8 B] = 4 KB, into the upper half of the fp16 lo area
+            tma_load_2d_hint(dst + 3 * QBOX, &tmL, full, x, y, kEvictFirst);
+            tma_load_2d_hint(dst + 3 * QBOX + QBOX / 2, &tmL, full, x + 256, y, kEvictFirst);
           }
           tma_load_2d_hint(dst + 4 * QBOX, &tmW, full, 0, st * QR, kEvictLast);
           if (++stage == QNS) { stage = 0; phase ^= 1; }
@@ -137,6 +144,7 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
           const uint32_t t_acc = tmem_base + (g & 1) * 128;
           if (first) mbar_wait(BAR(B_AEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
           mbar_wait(BAR(B_FULL + stage), phase);
+          if (!HI_ONLY) mbar_wait(BAR(B_CONV + stage), phase);     // the lo bytes have been widened to fp16
           tc_fence_after();
           const uint32_t sd = sdesc0 + stage * (QSTAGE >> 4);
 #pragma unroll
@@ -159,8 +167,8 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ======================= epilogue =======================
+  } else if (warp >= 4 && warp < 8) {
+    // ======================= epilogue (warps 4-7) =======================
     const int q = warp & 3;
     const int row = q * 32 + lane;                        // centre inside the column tile (= TMEM lane)
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -182,10 +190,10 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         float tmp[32];
         __syncwarp();
         if (!HI_ONLY) {
-          tmem_ld32(t_acc + 64, r);                       // lo.hi  (x 2^-12)
+          tmem_ld32(t_acc + 64, r);                       // lo.hi  (x 2^-19)
           tc_wait_ld();
 #pragma unroll
-          for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * (1.f / 4096.f);
+          for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * kLoScale;
         } else {
 #pragma unroll
           for (int t = 0; t < 32; ++t) tmp[t] = 0.f;
@@ -213,6 +221,26 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             t4.z = acc[4 * v + 2] * w16_scale_from_bits(mx.z, true); t4.w = acc[4 * v + 3] * w16_scale_from_bits(mx.w, true);
             *reinterpret_cast<float4*>(orow + 4 * v) = t4;
           }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ======================= converters (warps 8-11): lo bytes -> fp16, in place =======================
+    if (!HI_ONLY) {
+      const int ctid = static_cast<int>(threadIdx.x) - 256;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int s = it / p.n_ct;
+        const int st0 = s * p.stages_per_item;
+        const int st1 = min(st0 + p.stages_per_item, p.n_stages);
+        for (int st = st0; st < st1; ++st) {
+          mbar_wait_warp(BAR(B_FULL + stage), phase);
+          widen_lo8(smem + stage * QSTAGE + 2 * QBOX, ctid);
+          fence_proxy_async();                            // generic-proxy writes before the tensor core's reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_CONV + stage));
+          if (++stage == QNS) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -247,7 +275,7 @@ struct Panel16VParams {
 };
 
 template <int HI_ONLY>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(QTHREADS, 1)
 panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -255,7 +283,7 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + QBARS);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  const int B_FULL = 0, B_EMPTY = QNS, B_AFULL = 2 * QNS, B_AEMPTY = 2 * QNS + 2;
+  const int B_FULL = 0, B_EMPTY = QNS, B_AFULL = 2 * QNS, B_AEMPTY = 2 * QNS + 2, B_CONV = 2 * QNS + 4;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -265,6 +293,7 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
     for (int s = 0; s < QNS; ++s) {
       mbar_init(BAR(B_FULL + s), 1);
       mbar_init(BAR(B_EMPTY + s), 1);
+      mbar_init(BAR(B_CONV + s), 4);
     }
     mbar_init(BAR(B_AFULL + 0), 1);
     mbar_init(BAR(B_AFULL + 1), 1);
@@ -299,9 +328,10 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
           const uint32_t dst = smem_u32(smem) + stage * VSTAGE;
           // 8 centre groups of column tile j = st / 2, half st % 2: 16 KB of contiguous panel per plane
           const __half* src = p.P + ((static_cast<int64_t>(st >> 1) * p.n_rb + rb) * 16 + (st & 1) * 8) * 1024;
-          mbar_arrive_expect_tx(full, HI_ONLY ? VSTAGE - VA : VSTAGE);
+          mbar_arrive_expect_tx(full, HI_ONLY ? VSTAGE - VA : VSTAGE - VA / 2);
           bulk_g2s_hint(dst, src, VA, full, kEvictFirst);
-          if (!HI_ONLY) bulk_g2s_hint(dst + VA, src + p.plane_elems, VA, full, kEvictFirst);
+          // lo bytes of the same 8 centre groups: 8 KB, into the upper half of the fp16 lo area
+          if (!HI_ONLY) bulk_g2s_hint(dst + VA + VA / 2, reinterpret_cast<const uint8_t*>(p.P) + 2 * p.plane_elems + (src - p.P), VA / 2, full, kEvictFirst);
           tma_load_2d_hint(dst + 2 * VA, &tmV, full, 0, st * QR, kEvictLast);
           if (++stage == QNS) { stage = 0; phase ^= 1; }
         }
@@ -326,6 +356,7 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
           const uint32_t t_acc = tmem_base + (g & 1) * 128;
           if (first) mbar_wait(BAR(B_AEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
           mbar_wait(BAR(B_FULL + stage), phase);
+          if (!HI_ONLY) mbar_wait(BAR(B_CONV + stage), phase);     // the lo bytes have been widened to fp16
           tc_fence_after();
           const uint32_t sd = sdesc0 + stage * (VSTAGE >> 4);
 #pragma unroll
@@ -347,8 +378,8 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ======================= epilogue =======================
+  } else if (warp >= 4 && warp < 8) {
+    // ======================= epilogue (warps 4-7) =======================
     const int q = warp & 3;
     const int row = q * 32 + lane;                        // row inside the row block (= TMEM lane)
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -370,10 +401,10 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
         float tmp[32];
         __syncwarp();
         if (!HI_ONLY) {
-          tmem_ld32(t_acc + 64, r);                       // lo.hi  (x 2^-12)
+          tmem_ld32(t_acc + 64, r);                       // lo.hi  (x 2^-19)
           tc_wait_ld();
 #pragma unroll
-          for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * (1.f / 4096.f);
+          for (int t = 0; t < 32; ++t) tmp[t] = __uint_as_float(r[t]) * kLoScale;
         } else {
 #pragma unroll
           for (int t = 0; t < 32; ++t) tmp[t] = 0.f;
@@ -404,6 +435,26 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
         }
       }
     }
+  } else if (warp >= 8) {
+    // ======================= converters (warps 8-11): lo bytes -> fp16, in place =======================
+    if (!HI_ONLY) {
+      const int ctid = static_cast<int>(threadIdx.x) - 256;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int s = it / p.n_rb;
+        const int st0 = s * p.stages_per_item;
+        const int st1 = min(st0 + p.stages_per_item, p.n_stages);
+        for (int st = st0; st < st1; ++st) {
+          mbar_wait_warp(BAR(B_FULL + stage), phase);
+          widen_lo8(smem + stage * VSTAGE + VA, ctid);
+          fence_proxy_async();                            // generic-proxy writes before the tensor core's reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_CONV + stage));
+          if (++stage == QNS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -415,9 +466,9 @@ int q_num_sms() { return device_sm_count(); }
 
 }  // namespace
 
-// bytes of the fp16-plane panel of one chunk: 2 planes x padded rows x padded centres x 2 B
+// bytes of the panel of one chunk: padded rows x padded centres x (2 B hi plane + 1 B lo plane)
 size_t panel16_bytes(int64_t n_rows, int64_t M) {
-  return static_cast<size_t>(round_up(n_rows, 128)) * static_cast<size_t>(round_up(M, 128)) * 4;
+  return static_cast<size_t>(round_up(n_rows, 128)) * static_cast<size_t>(round_up(M, 128)) * 3;
 }
 
 // Row ranges per column tile: chosen so that the slowest CTA of the persistent grid streams as few stages as possible
@@ -460,7 +511,7 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
   p.M = static_cast<int>(M);
   p.T_pad = T_pad;
   const int64_t plane_rows = static_cast<int64_t>(p.n_ct) * p.n_rb * 16;
-  if (2 * plane_rows > 0x7fffffffll) return set_error(ODF_ERR_ARG, "panel16_tmm: chunk too large for 32-bit TMA coordinates");
+  if (plane_rows > 0x7fffffffll) return set_error(ODF_ERR_ARG, "panel16_tmm: chunk too large for 32-bit TMA coordinates");
   p.plane_rows = static_cast<int>(plane_rows);
   {
     const char* e = getenv("ODF_P16_SWAP");
@@ -468,15 +519,16 @@ int launch_panel16_tmm(const void* P16, int64_t n_rows, int64_t M, const void* W
   }
   p.absmax = absmax;
   p.out = out_partial;
-  CUtensorMap tmP, tmW;
+  CUtensorMap tmP, tmL, tmW;
   int rc;
-  if ((rc = make_map_plain_f16(&tmP, P16, 2 * plane_rows, 1024, 1024, 16, 256))) return rc;
+  if ((rc = make_map_plain_f16(&tmP, P16, plane_rows, 1024, 1024, 16, 256))) return rc;
+  if ((rc = make_map_plain_u8(&tmL, static_cast<const uint8_t*>(P16) + plane_rows * 2048, plane_rows, 1024, 1024, 16, 256))) return rc;
   if ((rc = make_map_sw128(&tmW, W16, static_cast<int64_t>(p.n_rb) * 128, 64, 64, QR, 2))) return rc;
   const int n_items = p.n_ct * p.n_rsplit;
   const int sms = q_num_sms();
   const int grid = n_items < sms ? n_items : sms;
-  if (hi_only) panel16_kernel<1><<<grid, 256, QSMEM, st>>>(tmP, tmW, p);
-  else panel16_kernel<0><<<grid, 256, QSMEM, st>>>(tmP, tmW, p);
+  if (hi_only) panel16_kernel<1><<<grid, QTHREADS, QSMEM, st>>>(tmP, tmL, tmW, p);
+  else panel16_kernel<0><<<grid, QTHREADS, QSMEM, st>>>(tmP, tmL, tmW, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "panel16_kernel launch");
   return ODF_OK;
@@ -522,8 +574,8 @@ int launch_panel16_mmv(const void* P16, int64_t n_rows, int64_t M, const void* V
   const int n_items = p.n_rb * p.n_csplit;
   const int sms = q_num_sms();
   const int grid = n_items < sms ? n_items : sms;
-  if (hi_only) panel16_mmv_kernel<1><<<grid, 256, QSMEM, st>>>(tmV, p);
-  else panel16_mmv_kernel<0><<<grid, 256, QSMEM, st>>>(tmV, p);
+  if (hi_only) panel16_mmv_kernel<1><<<grid, QTHREADS, QSMEM, st>>>(tmV, p);
+  else panel16_mmv_kernel<0><<<grid, QTHREADS, QSMEM, st>>>(tmV, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "panel16_mmv_kernel launch");
   return ODF_OK;

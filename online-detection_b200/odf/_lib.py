@@ -45,9 +45,6 @@ SIGNATURES = {
     "odf_finish_w16": (c_int, [c_fp, c_int, c_i64, c_int, c_i64, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp]),
     "odf_panel16_splits": (c_int, [c_i64, c_i64]),
     "odf_panel16_tmm": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),
-    "odf_panel16_sweep_slabs": (c_int, [c_i64]),
-    "odf_panel16_sweep_work_bytes": (c_sz, [c_i64, c_i64]),
-    "odf_panel16_sweep": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_fp, c_fp, c_sz, c_fp, c_int, c_fp]),
     "odf_panel16_mmv_splits": (c_int, [c_i64, c_i64]),
     "odf_panel16_mmv": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),
     "odf_panel16_tmm_hi": (c_int, [c_fp, c_i64, c_i64, c_fp, c_fp, c_int, c_int, c_fp, c_fp]),

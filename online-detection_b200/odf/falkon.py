@@ -51,10 +51,10 @@ class FalkonOptions:
         # fails.  "library": odf_precond_init (cuSOLVER potrf + cuBLAS sgemm) + odf_precond_invert (round 1's build; column
         # blocks of it are split over the ranks with distributed_precond=True).  ODF_PRECOND_BUILD overrides the default.
         self.precond_build = ignored.pop("precond_build", None) or os.environ.get("ODF_PRECOND_BUILD") or "tc"
-        # "panel16": K is evaluated once per sweep, its tiles are spilled as fp16 hi/lo planes to a transient panel
+        # "panel16": K is evaluated once per sweep, its tiles are spilled as an fp16 hi plane + a one-byte residual plane to a transient panel
         # and contracted by the tensor-core panel kernel; "panel": fp32 panel + fp32-FMA panel kernel;
         # "recompute": evaluate K twice (no panel workspace); "resident": the fp16-plane panels of every row chunk
-        # stay in HBM (one copy, 4 B per kernel value: 40.5 GB at N = 1 M, M = 10 k) -- they are filled by the
+        # stay in HBM (one copy, 3 B per kernel value: 30.3 GB at N = 1 M, M = 10 k) -- they are filled by the
         # right-hand-side sweep of the fit and every later sweep is two passes of the panel kernels at HBM speed
         # (K v, then K^T w), no kernel value is evaluated again; "auto" (default): as many row chunks resident as
         # fit into 85 % of the free device memory, the rest streamed as in "panel16".  ODF_SWEEP_MODE overrides.

@@ -165,7 +165,7 @@ class RowView:
 def mmv_partial(rows, cols, rhs, sigma, partial, panel=None, panel16=None):
     """partial[s] = K(rows, cols restricted to split s) @ rhs  — the fused tcgen05 tile.
     With `panel` ([rows.n x pad_rows(cols.n)] fp32) the K tiles are also spilled for panel_tmm; with `panel16`
-    (uint8 buffer of odf_panel16_bytes) they are spilled as fp16 hi/lo planes for panel16_tmm."""
+    (uint8 buffer of odf_panel16_bytes) they are spilled as an fp16 hi plane and a one-byte residual plane (3 B per value) for panel16_tmm."""
     L = _lib.load()
     assert rows.d == cols.d and rows.kind == cols.kind and rhs.m == cols.n
     S = int(partial.shape[0])
@@ -298,25 +298,6 @@ def panel16_mmv(panel16, V16, absmax, n_rows, M, out_partial, hi_only=False):
         ev[1].record()
         PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_mmv_kernel<hi>" if hi_only else "panel16_mmv_kernel"))
     _count(1)
-
-
-def panel16_sweep(panel16, V16, absmax_v, n_rows, M, W16, work, out_partial):
-    """out_partial[g] = K[rows of group g]^T (K[rows of group g] V) for every 512-row group of a RESIDENT panel, in one
-    pass: K v of a group streams from HBM, K^T w of the same group two groups later from the L2 (odf_panel16_sweep)."""
-    L = _lib.load()
-    S, M_, T_pad = out_partial.shape
-    assert M_ == M and S == int(L.odf_panel16_sweep_slabs(n_rows)) and out_partial.is_contiguous()
-    assert work.dtype == torch.uint8 and work.numel() >= int(L.odf_panel16_sweep_work_bytes(n_rows, M))
-    ev = None
-    if PANEL_EVENTS is not None:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-    check(L.odf_panel16_sweep(ptr(panel16), n_rows, M, ptr(V16), ptr(absmax_v), T_pad, ptr(W16), ptr(work), work.numel(),
-                              ptr(out_partial), S, _stream()), "odf_panel16_sweep")
-    if ev is not None:
-        ev[1].record()
-        PANEL_EVENTS.append((ev[0], ev[1], n_rows, M, T_pad, "panel16_sweep_kernel"))
-    _count(2)
 
 
 def finish_rows(partial, T, out, scale=1.0, addend=None):
@@ -610,19 +591,19 @@ class Sweeper:
     """Pre-allocated buffers for repeated K_nm^T (K_nm V + W) sweeps with T <= 32 columns.
 
     mode "panel16" (default): rows go through in chunks; the fused tile computes K_chunk V and spills
-    its K tiles as fp16 hi/lo planes to a transient panel, then the tensor-core panel kernel forms
+    its K tiles as hi (fp16) / lo (one byte) planes to a transient panel, then the tensor-core panel kernel forms
     K_chunk^T (K_chunk V + W) streaming the panel once at HBM speed.  K is evaluated once per sweep.
     mode "panel": same with an fp32 panel and the fp32-FMA panel kernel.  mode "recompute": the second
     half re-evaluates K in the transposed orientation with the same fused tile (no panel workspace,
     2x tensor work).
 
     mode "resident": the fp16-plane panels of the row chunks stay in HBM for the life of the Sweeper.  Default
-    (RESIDENT_SINGLE_COPY): ONE copy, K_chunk, 4 B per kernel value (40.5 GB for 1 M x 10 k, inside the 180 GB of
+    (RESIDENT_SINGLE_COPY): ONE copy, K_chunk, 3 B per kernel value (30.3 GB for 1 M x 10 k, inside the 180 GB of
     a B200); the first sweep of a fit fills it as a by-product of a forward pass of the fused tile with the spill
     on, every later sweep evaluates no kernel value at all: K v comes from the panel through odf_panel16_mmv (rows
     as the MMA's M dimension) and K^T w through odf_panel16_tmm, two passes over the resident planes at HBM speed.
     mode "auto" = as many row chunks resident as fit (resident_plan), the rest streamed through one transient panel
-    as in "panel16".  ODF_RESIDENT_SINGLE=0 selects the first version (K_chunk and K_chunk^T both resident, 2 x 4 B
+    as in "panel16".  ODF_RESIDENT_SINGLE=0 selects the first version (K_chunk and K_chunk^T both resident, 2 x 3 B
     per value, transposed tile pass for the right-hand side sweep)."""
 
     def __init__(self, rows, cols, sigma, T, mode="panel16", resident_chunks=None):
@@ -698,12 +679,6 @@ class Sweeper:
             self.absmax_v = torch.zeros((32,), dtype=torch.int32, device=dev)
             self.pslabs = [int(L.odf_panel16_splits(r1 - r0, M)) for (r0, r1) in self.chunks]
             self.part3 = torch.empty((sum(self.pslabs), M, Tp), dtype=torch.float32, device=dev)
-            # one-pass sweeps over filled resident panels (odf_panel16_sweep): one slab per 512-row group
-            self.fused = bool(RESIDENT_FUSED) and self.single and self.n_res > 0
-            if self.fused:
-                self.fslabs = [int(L.odf_panel16_sweep_slabs(r1 - r0)) for (r0, r1) in self.chunks[:self.n_res]]
-                self.part3f = torch.empty((sum(self.fslabs) + sum(self.pslabs[self.n_res:]), M, Tp), dtype=torch.float32, device=dev)
-                self.fwork = u8(max(int(L.odf_panel16_sweep_work_bytes(n, M)) for n in sizes))
         elif mode == "panel":
             self.chunk = min(int(PANEL_ROWS), (rows.n + 127) // 128 * 128)
             self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
@@ -801,19 +776,12 @@ class Sweeper:
                 self.Vpad[0, :, :T].copy_(v)
                 finish_w16(self.Vpad, T, self.Vf, self.absmax_v, self.V16)
         slab = 0
-        # filled panels and no addend (every CG iteration): K v and K^T (K v) of a resident chunk in ONE pass over its panel
-        fused = self.fused and not fill and v is not None and w is None and not hi
-        part3 = self.part3f if fused else self.part3
+        part3 = self.part3
         for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
             n = r1 - r0
             resident = i < self.n_res
             panel = self.fwd[i] if resident else self.transient
             tile = fill or not resident
-            if fused and resident:
-                S = self.fslabs[i]
-                panel16_sweep(panel, self.V16, self.absmax_v, n, M, self.W16, self.fwork, part3[slab:slab + S])
-                slab += S
-                continue
             if tile:
                 mmv_partial(view, self.cols, self.v_rhs, self.sigma, self.part1[n], panel16=panel)
             if v is None:
@@ -919,9 +887,6 @@ class Sweeper:
 # EXPERIMENTAL precision tier: resident sweeps stream the hi plane only (K to 11 bits, 2 B per value) once the panels
 # are filled.  ODF_PANEL_HI_ONLY=1.  Off by default: emulated on the CPU only so far (tools/precision_study.py).
 PANEL_HI_ONLY = os.environ.get("ODF_PANEL_HI_ONLY", "0") not in ("0", "")
-# one pass over a filled resident panel per sweep (odf_panel16_sweep: K v from HBM, K^T w of the same rows from the L2)
-# instead of two (odf_panel16_mmv + odf_panel16_tmm).  ODF_RESIDENT_FUSED=0 selects the two-pass sweeps.
-RESIDENT_FUSED = os.environ.get("ODF_RESIDENT_FUSED", "0") not in ("0", "")
 RESIDENT_FRACTION = 0.85   # share of the free device memory the resident panels may take in mode "auto"
 # keep only K_chunk (default) instead of K_chunk and K_chunk^T: K v then comes from the same panel through
 # odf_panel16_mmv, half the memory and no transposed tile pass.  ODF_RESIDENT_SINGLE=0 selects the two-copy variant.

@@ -56,7 +56,7 @@ class _Ev:
 def test_roofline_entries_from_event_records():
     import bench
     peaks = {"hbm_gbs": 6500.0, "bf16_tflops_sustained": 1400.0}
-    traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_v12_traffic.json")))
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
     # 4 panel launches of a 524288 x 10000 panel at 3 ms (2 per kernel) and 2 of the ragged 475712-row one
     pe = []
     t = 0.0
@@ -65,13 +65,13 @@ def test_roofline_entries_from_event_records():
         pe.append((_Ev(t), _Ev(t + 3.0), n, 10000, 32, name))
         t += 3.0
     r = bench.panel_roofline(pe, steps=1, step_ms=36.0, peaks=peaks, traffic_json=traffic)
-    alg = 4.0 * 10112 * (4 * 524288 + 2 * 475776)
+    alg = 3.0 * 10112 * (4 * 524288 + 2 * 475776)
     assert r["bound"] == "hbm" and r["kernel"] == "panel16_kernel + panel16_mmv_kernel" and r["launches_timed"] == 6
     assert abs(r["achieved"] - alg / 18.0 / 1e6) < 1e-6 * r["achieved"] and abs(r["frac"] - r["achieved"] / 6500.0) < 1e-12
     assert abs(r["share_of_step"] - 0.5) < 1e-12 and abs(r["algorithmic_bytes_per_launch"] - alg / 6) < 1
     # traffic: the captured shape launched most often (524288 rows), read + write of that kernel's capture
-    assert r["traffic"] in (21273837000 + 26101000, 21208303000 + 39267000) and "524288 x 10000" in r["traffic_source"]
-    assert 0.99 < r["traffic"] / (4.0 * 10112 * 524288) < 1.01
+    assert r["traffic"] in (15971971000 + 23584000, 15906150000 + 24156000) and "524288 x 10000" in r["traffic_source"]
+    assert 0.99 < r["traffic"] / (3.0 * 10112 * 524288) < 1.01
     assert set(r["per_kernel"]) == {"panel16_kernel", "panel16_mmv_kernel"} and r["per_kernel"]["panel16_kernel"]["launches"] == 3
     # tile: 2 launches of 524288 x 10000 x 1024, T = 30, 24 ms each
     te = [(_Ev(0.0), _Ev(24.0), 524288, 10000, 1024, 30), (_Ev(24.0), _Ev(48.0), 524288, 10000, 1024, 30)]
@@ -79,7 +79,7 @@ def test_roofline_entries_from_event_records():
     flops = 2.0 * 524288 * 10000 * (1024 + 30)
     assert q["bound"] == "tensor" and abs(q["achieved"] - flops / 24.0 / 1e9) < 1e-6 * q["achieved"]
     assert abs(q["executed_tensor_tflops"] - 6.0 * 524288 * 10000 * (1024 + 32) / 24.0 / 1e9) < 1e-6 * q["executed_tensor_tflops"]
-    assert abs(q["share_of_step"] - 0.1) < 1e-12 and q["traffic"] == 18282461000 + 21970094000
+    assert abs(q["share_of_step"] - 0.1) < 1e-12 and q["traffic"] == 24885498000 + 16680812000
     # a shape without a capture reports no traffic
     q2 = bench.tile_roofline([(_Ev(0.0), _Ev(1.0), 4096, 1000, 256, 21)], 1, 10.0, peaks, traffic)
     assert q2["traffic"] is None and q2["traffic_source"] is None

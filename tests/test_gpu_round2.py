@@ -209,53 +209,3 @@ def test_triangular_apply_matches_fp64(odf, M, T):
             rows = torch.full((r1 - r0, T), float("nan"), device="cuda")
             ops.precond_apply_rows(U, r0, r1, B, rows, tr)
             assert torch.equal(rows, out[r0:r1]) or float((rows.double() - ref[r0:r1]).abs().max()) <= 1.01 * 2.0 ** -24 * float(ref.abs().max())
-
-
-@pytest.mark.parametrize("n,M,d,T,chunk", [(100, 60, 32, 1, 131072), (1500, 700, 64, 5, 131072), (3333, 300, 64, 7, 1024),
-                                           (9000, 1100, 128, 30, 4096), (40000, 2500, 128, 21, 131072)])
-def test_one_pass_resident_sweep_matches_two_pass_and_oracle(odf, monkeypatch, n, M, d, T, chunk):
-    """odf_panel16_sweep (csrc/odf_panel16_sweep.cu): K^T (K v) of a filled resident panel in ONE persistent kernel -- K v of
-    a 512-row group from HBM, the fp16 split of w on the fly (per-row-block scales), K^T w of the same group from the L2 --
-    against the two-pass sweep (odf_panel16_mmv + odf_finish_w16 + odf_panel16_tmm) and the fp64 oracle.  Ragged row blocks,
-    groups and chunks, fewer items than SMs, columns of very different magnitude; two runs are bit-identical."""
-    from odf import ops
-    monkeypatch.setattr(ops, "PANEL_ROWS", chunk)
-    monkeypatch.setattr(ops, "RESIDENT_MULT", 1)
-    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
-    X, _, _ = orc.make_synthetic(n, d, 3, seed=16)
-    C = X[torch.randperm(n, generator=torch.Generator().manual_seed(17))[:M]]
-    g = torch.Generator().manual_seed(18)
-    k = odf.GaussianKernel(15.0)
-    cols = k._prep(C.cuda())
-    rows = k._prep(X.cuda(), like=cols)
-    outs = {}
-    for fused in (False, True):
-        monkeypatch.setattr(ops, "RESIDENT_FUSED", fused)
-        sw = ops.Sweeper(rows, cols, 15.0, T, mode="resident")
-        assert sw.fused == fused
-        out = torch.empty((M, T), device="cuda")
-        y = torch.randn(n, T, generator=torch.Generator().manual_seed(19))
-        sw.dmmv(None, y.cuda(), out, 1.0, 1.0 / n)                 # fills the panels
-        res = []
-        gg = torch.Generator().manual_seed(20)
-        for i in range(3):
-            v = torch.randn(M, T, generator=gg) * torch.logspace(-2, 2, T)[None, :]
-            names = []
-            ops.PANEL_EVENTS = []
-            try:
-                sw.dmmv(v.cuda(), None, out, 0.5)
-                names = [e[-1] for e in ops.PANEL_EVENTS]
-            finally:
-                ops.PANEL_EVENTS = None
-            assert set(names) == ({"panel16_sweep_kernel"} if fused else {"panel16_mmv_kernel", "panel16_kernel"})
-            res.append(out.clone())
-            if fused:
-                sw.dmmv(v.cuda(), None, out, 0.5)
-                assert torch.equal(out, res[-1])                  # deterministic
-            ref = 0.5 * orc.dmmv(X, C, v, None, 15.0)
-            err = (out.double().cpu() - ref).abs().max(0).values / ref.abs().max(0).values
-            assert float(err.max()) < 1e-4, (fused, i, float(err.max()))
-        outs[fused] = res
-    for a, b in zip(outs[False], outs[True]):
-        err = (a.double() - b.double()).abs().max(0).values / b.double().abs().max(0).values
-        assert float(err.max()) < 2e-6, float(err.max())
