@@ -356,9 +356,17 @@ class Falkon:
             Xd = torch.empty(X.shape, dtype=torch.float32, device=dev)
             Yd = torch.empty(Y.shape, dtype=torch.float32, device=dev)
             side.wait_stream(main)
+            # labels first (small), then the rows in chunks of the resident sweep's row chunk, one event per chunk: the
+            # panel-filling sweep consumes chunk i (ops.ChunkedPrepared) while chunk i + 1 is still on the bus
+            step = ops._resident_chunk(X.shape[0]) if X.shape[0] > 0 else 1
+            upload_chunks = []
             with torch.cuda.stream(side):
-                Xd.copy_(X, non_blocking=True)
                 Yd.copy_(Y, non_blocking=True)
+                for r0 in range(0, X.shape[0], step):
+                    Xd[r0:r0 + step].copy_(X[r0:r0 + step], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    upload_chunks.append(ev)
                 upload = torch.cuda.Event()
                 upload.record(side)
             Xd.record_stream(side)
@@ -440,8 +448,13 @@ class Falkon:
             if world > 1:
                 dist.all_reduce(pre[1], group=group)
         elif upload is not None:
-            torch.cuda.current_stream(dev).wait_event(upload)        # the rows have arrived by now
-            px = be.Prepared(X, zs[0], zs[1], kind=kind) if n_local > 0 else None
+            if n_local > 0 and len(upload_chunks) > 1:
+                # Y is in front of the row chunks on the copy stream: waiting for the first chunk covers it
+                torch.cuda.current_stream(dev).wait_event(upload_chunks[0])
+                px = ops.ChunkedPrepared(X, step, upload_chunks, zs[0], zs[1], kind=kind)
+            else:
+                torch.cuda.current_stream(dev).wait_event(upload)    # the rows have arrived by now
+                px = be.Prepared(X, zs[0], zs[1], kind=kind) if n_local > 0 else None
         tm.mark()
 
         alpha = torch.empty((M, T), dtype=torch.float32, device=dev)

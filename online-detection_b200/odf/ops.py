@@ -162,6 +162,58 @@ class RowView:
         self.opscale, self.n, self.d, self.kind, self.pitch = prep.opscale, r1 - r0, prep.d, prep.kind, prep.pitch
 
 
+class ChunkedPrepared:
+    """Rows that arrive from the HOST chunk by chunk (Falkon.fit with host-resident X): chunk i is uploaded on a side
+    stream (`ready[i]` is recorded behind its copy) and turned into its split operand form -- with its OWN power-of-two
+    operand scale, the tile takes the scales of rows and centres separately -- the first time a sweep asks for it, on the
+    stream of that sweep.  The panel-filling sweep of a resident fit therefore starts on chunk 0 while chunk 1 is still
+    on the PCIe bus.  `chunk` must be the Sweeper's resident chunk (ops._resident_chunk); any other consumer gets the
+    whole point set through whole()."""
+
+    def __init__(self, Xd, chunk, ready, mean=None, scale=1.0, kind=None):
+        self.X, self.n, self.d = Xd, int(Xd.shape[0]), int(Xd.shape[1])
+        self.chunk = int(chunk)
+        self.bounds = [(r0, min(self.n, r0 + self.chunk)) for r0 in range(0, self.n, self.chunk)]
+        assert len(ready) == len(self.bounds)
+        self.ready, self.mean, self.scale = list(ready), mean, float(scale)
+        self.kind = resolve_kind(kind)
+        self.device = Xd.device
+        self.parts = [None] * len(self.bounds)
+        self._whole = None
+
+    def part(self, i):
+        if self.parts[i] is None:
+            r0, r1 = self.bounds[i]
+            torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+            self.parts[i] = Prepared(self.X[r0:r1], self.mean, self.scale, kind=self.kind)
+            if all(p is not None for p in self.parts):
+                self.X = None                                    # the fp32 copy has served its purpose
+        return self.parts[i]
+
+    def views(self):
+        for i in range(len(self.bounds)):
+            yield self.part(i)
+
+    def whole(self):
+        """One Prepared over all rows (consumers other than the chunk-aligned resident sweep)."""
+        if self._whole is None:
+            if self.X is None:
+                raise RuntimeError("the rows have already been consumed chunk by chunk")
+            st = torch.cuda.current_stream(self.device)
+            for ev in self.ready:
+                st.wait_event(ev)
+            self._whole = Prepared(self.X, self.mean, self.scale, kind=self.kind)
+        return self._whole
+
+
+class _Shape:
+    """n / d / kind of a point set (what alloc_partial needs)."""
+    __slots__ = ("n", "d", "kind")
+
+    def __init__(self, n, d, kind):
+        self.n, self.d, self.kind = int(n), int(d), kind
+
+
 def mmv_partial(rows, cols, rhs, sigma, partial, panel=None, panel16=None):
     """partial[s] = K(rows, cols restricted to split s) @ rhs  — the fused tcgen05 tile.
     With `panel` ([rows.n x pad_rows(cols.n)] fp32) the K tiles are also spilled for panel_tmm; with `panel16`
@@ -608,10 +660,14 @@ class Sweeper:
 
     def __init__(self, rows, cols, sigma, T, mode="panel16", resident_chunks=None):
         auto = mode == "auto"
+        dev = cols.hi.device
         if auto:
             # as many row chunks resident as fit (single-copy variant: the rest is streamed through a transient panel)
-            resident_chunks = resident_plan(rows.n, cols.n, rows.hi.device)
+            resident_chunks = resident_plan(rows.n, cols.n, dev)
             mode = "resident" if (resident_chunks is None or resident_chunks > 0) else "panel16"
+        if isinstance(rows, ChunkedPrepared) and not (mode == "resident" and RESIDENT_SINGLE_COPY and resident_chunks is None
+                                                      and rows.chunk == _resident_chunk(rows.n)):
+            rows = rows.whole()                     # only the chunk-aligned, fully resident sweep consumes chunk by chunk
         try:
             self._setup(rows, cols, sigma, T, mode, resident_chunks)
         except torch.OutOfMemoryError:
@@ -620,13 +676,15 @@ class Sweeper:
             # the plan was too optimistic (fragmentation, another allocation in between): stream instead
             for k in list(self.__dict__):
                 delattr(self, k)
-            if rows.hi.is_cuda:
+            if dev.type == "cuda":
                 torch.cuda.empty_cache()
+            if isinstance(rows, ChunkedPrepared):
+                rows = rows.whole()
             self._setup(rows, cols, sigma, T, "panel16", None)
 
     def _setup(self, rows, cols, sigma, T, mode, resident_chunks):
         L = _lib.load()
-        dev = rows.hi.device
+        dev = cols.hi.device
         self.rows, self.cols, self.sigma, self.T, self.mode = rows, cols, sigma, int(T), mode
         if mode not in ("panel16", "panel", "recompute", "resident"):
             raise ValueError("unknown sweep mode %r" % (mode,))
@@ -650,7 +708,11 @@ class Sweeper:
             M = cols.n
             self.chunk = _resident_chunk(rows.n, resident_chunks is None or not RESIDENT_SINGLE_COPY)
             self.chunks = [(r0, min(rows.n, r0 + self.chunk)) for r0 in range(0, rows.n, self.chunk)]
-            self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
+            if isinstance(rows, ChunkedPrepared):
+                assert rows.bounds == self.chunks
+                self.views = None                   # rows.views(): prepared (behind their upload) when the sweep reaches them
+            else:
+                self.views = [RowView(rows, r0, r1) for (r0, r1) in self.chunks]
             sizes = sorted({r1 - r0 for (r0, r1) in self.chunks})
             u8 = lambda nbytes: torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)  # noqa: E731
             self.single = bool(RESIDENT_SINGLE_COPY)
@@ -661,7 +723,7 @@ class Sweeper:
             self.fwd = [u8(L.odf_panel16_bytes(r1 - r0, M)) for (r0, r1) in self.chunks[:self.n_res]]     # K_chunk
             self.transient = u8(L.odf_panel16_bytes(self.chunk, M)) if self.n_res < len(self.chunks) else None
             self.have_fwd = self.have_tr = False
-            self.part1 = {n: alloc_partial(RowView(rows, 0, n), cols, Tp, dev) for n in sizes}
+            self.part1 = {n: alloc_partial(_Shape(n, rows.d, rows.kind), cols, Tp, dev) for n in sizes}
             if self.single:
                 kv_splits = {n: int(L.odf_panel16_mmv_splits(n, M)) for n in sizes}
             else:
@@ -777,7 +839,8 @@ class Sweeper:
                 finish_w16(self.Vpad, T, self.Vf, self.absmax_v, self.V16)
         slab = 0
         part3 = self.part3
-        for i, ((r0, r1), view) in enumerate(zip(self.chunks, self.views)):
+        views = self.views if self.views is not None else (self.rows.views() if need_tile else [None] * len(self.chunks))
+        for i, ((r0, r1), view) in enumerate(zip(self.chunks, views)):
             n = r1 - r0
             resident = i < self.n_res
             panel = self.fwd[i] if resident else self.transient

@@ -51,8 +51,8 @@ def test_layout_helpers(lib):
         tiles = (m + 127) // 128
         per = (tiles + s - 1) // s
         assert s >= 1 and (tiles + per - 1) // per == s        # no empty split
-    # fp16-plane panel: 4 bytes per (padded) kernel value; row ranges never empty; the CTA-pair tile wants >= 8192 rows
-    assert lib.odf_panel16_bytes(131072, 10000) == 131072 * 10112 * 4 and lib.odf_panel16_bytes(100, 100) == 128 * 128 * 4
+    # K panel: 3 bytes per (padded) kernel value (fp16 hi plane + one-byte residual plane); row ranges never empty; the CTA-pair tile wants >= 8192 rows
+    assert lib.odf_panel16_bytes(131072, 10000) == 131072 * 10112 * 3 and lib.odf_panel16_bytes(100, 100) == 128 * 128 * 3
     for (n, m) in [(131072, 10000), (82496, 10000), (131072, 30000), (300, 200), (64, 5), (9000, 333)]:
         s = lib.odf_panel16_splits(n, m)
         stages = (n + 63) // 64

@@ -209,3 +209,37 @@ def test_triangular_apply_matches_fp64(odf, M, T):
             rows = torch.full((r1 - r0, T), float("nan"), device="cuda")
             ops.precond_apply_rows(U, r0, r1, B, rows, tr)
             assert torch.equal(rows, out[r0:r1]) or float((rows.double() - ref[r0:r1]).abs().max()) <= 1.01 * 2.0 ** -24 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("mode", ["auto", "recompute"])
+def test_chunked_upload_fit_matches_device_fit(odf, monkeypatch, mode):
+    """fit() with host-resident rows spanning several resident row chunks: the rows are uploaded chunk by chunk and every
+    chunk gets its split operand form (own power-of-two operand scale) when the panel-filling sweep reaches it
+    (ops.ChunkedPrepared); a sweep mode that does not consume chunk by chunk gets the whole point set.  Chunk 1 holds rows
+    of 1.25 x the norm of the others."""
+    from odf import ops
+    monkeypatch.setattr(ops, "PANEL_ROWS", 1024)
+    monkeypatch.setattr(ops, "RESIDENT_MULT", 2)
+    X, c, Y = orc.make_synthetic(7000, 128, 3, seed=2)
+    X = X.clone()
+    X[2048:4096] *= 1.25
+    C = X[orc.shared_centres(c, 300, seed=1)]
+    opt = odf.FalkonOptions(sweep_mode=mode)
+    base = odf.InCoreFalkon(kernel=odf.GaussianKernel(15.0), penalty=1e-4, M=300, options=opt)
+    base.fit(X.cuda(), Y.cuda(), centres=C.cuda())
+    ref = orc.falkon_predict(X[:2000].double(), C.double(), orc.falkon_fit(X.double(), Y, C.double(), 15.0, 1e-4, dtype=torch.float64, eps_pc=1e-5, eps_cg=1e-7), 15.0)
+    assert rel(base.predict(X[:2000].cuda()), ref) < 2e-4
+    for Xh, Yh in ((X.pin_memory(), Y.pin_memory()), (X, Y)):
+        made = []
+        orig = ops.ChunkedPrepared.part
+        monkeypatch.setattr(ops.ChunkedPrepared, "part", lambda self, i: (made.append(i), orig(self, i))[1])
+        m = odf.InCoreFalkon(kernel=odf.GaussianKernel(15.0), penalty=1e-4, M=300, options=opt)
+        m.fit(Xh, Yh, centres=C.cuda())
+        monkeypatch.setattr(ops.ChunkedPrepared, "part", orig)
+        assert (sorted(set(made)) == [0, 1, 2, 3]) == (mode == "auto")
+        if mode == "auto":
+            # same arithmetic up to the operand scales of the chunks (alpha itself is ill-conditioned: compare scores)
+            assert rel(m.predict(X[:2000].cuda()), base.predict(X[:2000].cuda())) < 1e-4
+        else:
+            assert torch.equal(m.alpha_, base.alpha_)
+        assert rel(m.predict(X[:2000].cuda()), ref) < 2e-4

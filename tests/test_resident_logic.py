@@ -54,7 +54,7 @@ def emu(monkeypatch, lib):
         for s in range(S):
             partial[s, :, :rhs.T] = (K[:, edges[s]:edges[s + 1]] @ rhs.V[edges[s]:edges[s + 1]]).to(torch.float32)
         if panel16 is not None:
-            assert panel16.numel() >= ((rows.n + 127) // 128 * 128) * ((cols.n + 127) // 128 * 128) * 4
+            assert panel16.numel() >= ((rows.n + 127) // 128 * 128) * ((cols.n + 127) // 128 * 128) * 3
             store["panel"][panel16.data_ptr()] = K
         store["calls"].append(("tile", rows.n, cols.n, panel16 is not None))
 
@@ -170,10 +170,10 @@ def test_resident_sweeper_operator_first(emu):
 
 def test_resident_bytes_and_mode_names(lib):
     from odf import ops
-    # C2 on one GPU: 4 B x pad(rows) x pad(centres) (x 2 orientations in the two-copy variant); 1 000 000 rows pad to
+    # C2 on one GPU: 3 B x pad(rows) x pad(centres) (x 2 orientations in the two-copy variant); 1 000 000 rows pad to
     # 1 000 064 whatever the chunking (chunks are multiples of 128 rows)
     b = ops.resident_bytes(1_000_000, 10_000)
-    assert b == (1 if ops.RESIDENT_SINGLE_COPY else 2) * 4 * 10112 * 1_000_064
+    assert b == (1 if ops.RESIDENT_SINGLE_COPY else 2) * 3 * 10112 * 1_000_064
     with pytest.raises(ValueError):
         ops.Sweeper(_FakePrepared(torch.zeros(4, 2)), _FakePrepared(torch.zeros(2, 2)), 1.0, 1, mode="nope")
 
@@ -184,7 +184,7 @@ def test_resident_single_copy_bookkeeping(emu, monkeypatch, n, M, T):
     K v comes from the same panel (odf_panel16_mmv)."""
     ops, store = emu
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
-    assert ops.resident_bytes(n, M) * 2 == sum(2 * 4 * ((r + 127) // 128 * 128) * ((M + 127) // 128 * 128)
+    assert ops.resident_bytes(n, M) * 2 == sum(2 * 3 * ((r + 127) // 128 * 128) * ((M + 127) // 128 * 128)
                                                for r in [min(256, n - r0) for r0 in range(0, n, 256)])
     g = torch.Generator().manual_seed(n)
     X = torch.randn(n, 12, generator=g, dtype=DT)
@@ -252,12 +252,12 @@ def test_resident_plan(lib, monkeypatch):
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
     assert ops._resident_chunk(1_000_000) == 4 * 131072 and ops._resident_chunk(1_000_000, all_resident=False) == 131072
     assert ops._resident_chunk(1000) == 1024
-    per = 4 * 131072 * 10112
+    per = 3 * 131072 * 10112
     assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) is None               # everything fits
     assert ops.resident_plan(1_000_000, 10_000, None, budget=4.5 * per) == 3             # transient + 3 resident
     assert ops.resident_plan(1_000_000, 10_000, None, budget=1.5 * per) == 0             # stream everything
     monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", False)
-    assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) == 0                  # two copies: 81 GB
+    assert ops.resident_plan(1_000_000, 10_000, None, budget=50e9) == 0                  # two copies: 61 GB
     assert ops.resident_plan(1_000_000, 10_000, None, budget=90e9) is None
 
 
