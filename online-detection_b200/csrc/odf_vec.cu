@@ -43,15 +43,20 @@ rownorm_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ldx,
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = (c + k < d) ? __ldg(xr + c + k) : 0.f;
     }
+    // four squares in fp32 (fma chain), the running sum in fp64: one conversion + one DADD per 4 elements instead of
+    // 8 + 4 -- the fp64 pipe, not HBM, bound the first version (2.1 TB/s, ncu profiles/r2_ncu_vector_kernels.md); the
+    // fp32 partial adds ~4e-7 absolute at |x|^2 = 400, far below the final rounding of the norm to fp32 (2.4e-5)
+    float p4 = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (c + k < d) {
         float x = v[k];
         if (mean) x -= __ldg(mean + c + k);
         x *= scale;
-        acc += static_cast<double>(x) * static_cast<double>(x);
+        p4 = fmaf(x, x, p4);
       }
     }
+    acc += static_cast<double>(p4);
   }
   acc = warp_sum(acc);
   if (lane == 0) {
