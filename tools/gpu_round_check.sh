@@ -1,6 +1,6 @@
 #!/bin/bash
-# One gpurun call: resident-mode parity tests -> bench (both sweep modes) -> full GPU suite -> [experimental paths] -> ncu launch list.
-# Knobs: TAG (file prefix), DO_EXPERIMENTAL=1, DO_NCU=0, DO_NCU_FULL=0, DO_BRINGUP=0, SUITE_TIMEOUT.
+# One gpurun call: resident-mode parity tests -> bench (both sweep modes) -> full GPU suite -> ncu launch list.
+# Knobs: TAG (file prefix), DO_NCU=0, DO_NCU_FULL=0, DO_BRINGUP=0, SUITE_TIMEOUT.
 # Every step is bounded by its own timeout; logs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
@@ -25,18 +25,6 @@ tail -3 gpurun_out/${TAG:-v9}_bench_c2.err
 timeout ${SUITE_TIMEOUT:-480} python -m pytest tests -m gpu -x -q $DESEL > gpurun_out/${TAG:-v9}_pytest_gpu.log 2>&1
 el "gpu suite rc=$?"
 tail -6 gpurun_out/${TAG:-v9}_pytest_gpu.log
-if [ "${DO_EXPERIMENTAL:-0}" = "1" ]; then
-  # paths that are off by default: split GEMM, blocked preconditioner, hi-plane-only panel tier, overlap_rhs
-  ODF_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "split_gemm or blocked or hi_only or overlapped" \
-    > gpurun_out/${TAG:-v9}_experimental.log 2>&1
-  el "experimental tests rc=$?"
-  tail -15 gpurun_out/${TAG:-v9}_experimental.log
-  for V in "ODF_PANEL_HI_ONLY=1" "ODF_OVERLAP_RHS=1"; do
-    env $V timeout 100 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-streaming-compare > gpurun_out/${TAG:-v9}_bench_$V.json 2> gpurun_out/${TAG:-v9}_bench_$V.err
-    el "bench $V rc=$?"
-    tail -c 400 gpurun_out/${TAG:-v9}_bench_$V.json
-  done
-fi
 if [ "${DO_NCU:-1}" = "1" ]; then
   timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG:-v9}_launches.csv \
     python bench.py --steps 1 --warmup 3 --n 131072 --no-e2e --no-cpu-baseline --no-streaming-compare > gpurun_out/${TAG:-v9}_launches_bench.log 2>&1
