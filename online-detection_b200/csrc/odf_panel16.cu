@@ -16,7 +16,8 @@
 // B = W16 [row][hi(s_t W) 0..31 | lo 32..63] (MN-major SWIZZLE_128B, one 128-byte row per panel row, s_t a power of two
 // per column so that s_t max|W[:, t]| < 2^15):
 //     acc1 [128 x 64] += P_hi^T . W16      (columns 0..31: hi.hi      32..63: hi.lo, scaled 2^11)
-//     acc2 [128 x 64] += P_lo^T . W16      (columns 0..31: lo.hi, scaled 2^12;  32..63 unused)
+//     acc2 [128 x 32] += P_lo^T . W16[:, 0..31]   (lo.hi, scaled 2^19; an N = 32 MMA: lo.lo is never formed -- a quarter less
+//                                                  tensor work, which under the 1 kW cap is ~50 MHz of SM clock and 3 % of the pass)
 // fp32 in TMEM.  The tensor core adds with truncation, so an accumulation chain is cut every 512 rows: the epilogue
 // warps drain the (double-buffered) accumulators into registers, combine the three terms and keep the running sums in
 // fp32 round-to-nearest.  Row ranges write separate slabs that odf_finish_rows reduces in index order (deterministic).
@@ -155,7 +156,7 @@ panel16_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             const uint64_t b_w = kSdescMnHi | static_cast<uint64_t>(sd + ((4 * QBOX + kk * 2048) >> 4));
             const uint32_t accum = (first && kk == 0) ? 0u : 1u;
             mma_f16_ss(t_acc, a_hi, b_w, kIdesc, accum);
-            if (!HI_ONLY) mma_f16_ss(t_acc + 64, a_lo, b_w, kIdesc, accum);
+            if (!HI_ONLY) mma_f16_ss(t_acc + 64, a_lo, b_w, kIdescN32, accum);
           }
           tc_commit(BAR(B_EMPTY + stage));
           if (((local + 1) % QFLUSH) == 0 || st == st1 - 1) {
@@ -366,7 +367,7 @@ panel16_mmv_kernel(const __grid_constant__ CUtensorMap tmV, const Panel16VParams
             const uint64_t b_v = kSdescMnHi | static_cast<uint64_t>(sd + ((2 * VA + kk * 2048) >> 4));
             const uint32_t accum = (first && kk == 0) ? 0u : 1u;
             mma_f16_ss(t_acc, a_hi, b_v, kIdescV, accum);
-            if (!HI_ONLY) mma_f16_ss(t_acc + 64, a_lo, b_v, kIdescV, accum);
+            if (!HI_ONLY) mma_f16_ss(t_acc + 64, a_lo, b_v, kIdescVN32, accum);
           }
           tc_commit(BAR(B_EMPTY + stage));
           if (((local + 1) % QFLUSH) == 0 || st == st1 - 1) {

@@ -31,6 +31,8 @@ constexpr uint64_t kSdescMnPlainHiSwapped = (static_cast<uint64_t>(512 >> 4) << 
                                             (static_cast<uint64_t>(1) << 46);
 // kind::f16, fp16 A/B, fp32 accumulate, A and B MN-major (bits 15, 16), N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// the same with N = 32: the lo plane is contracted with the hi half of W16 / V16 only (lo . lo is dropped anyway)
+constexpr uint32_t kIdescN32 = (1u << 4) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 // ---- K . V orientation (rows are the MMA's M dimension, centres its K dimension) ----
 constexpr int VA = 8 * 2048;              // [8 centre groups][128 rows][8 fp16] of one plane
@@ -43,6 +45,7 @@ constexpr uint64_t kSdescKPlainHiSwapped = (static_cast<uint64_t>(128 >> 4) << 1
                                            (static_cast<uint64_t>(1) << 46);
 // kind::f16, fp16 A/B, fp32 accumulate, A K-major, B MN-major (bit 16), N = 64, M = 128
 constexpr uint32_t kIdescV = (1u << 4) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescVN32 = (1u << 4) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"

@@ -295,7 +295,9 @@ def test_panel16_mmv_kernel_matches_fp64_product(odf, n, M, d, T):
     ref = K @ V.double()
     assert float(((out - ref).abs() / (K @ V.double().abs())).max()) < 2e-5
     tile_kv = part1.sum(0)[:, :T].double().cpu()
-    assert float(((out - tile_kv).abs() / tile_kv.abs().max(0).values).max()) < 2e-5
+    # against the tile's own K.V (22-bit K pairs in TMEM): the panel keeps K to 2^-20 ABSOLUTE (fp16 hi + one-byte residual), so
+    # the two differ by ~1e-6 |V|_1-weighted -- 2e-5 of the column maximum at M = 1300 (the 4-byte panel of round 1: 1e-5)
+    assert float(((out - tile_kv).abs() / tile_kv.abs().max(0).values).max()) < 4e-5
 
 
 def test_panel_sweep_in_several_row_chunks(odf, monkeypatch):
