@@ -184,7 +184,8 @@ class ChunkedPrepared:
     def part(self, i):
         if self.parts[i] is None:
             r0, r1 = self.bounds[i]
-            torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+            if self.ready[i] is not None:                        # None: the rows are already there (host-logic tests)
+                torch.cuda.current_stream(self.device).wait_event(self.ready[i])
             self.parts[i] = Prepared(self.X[r0:r1], self.mean, self.scale, kind=self.kind)
             if all(p is not None for p in self.parts):
                 self.X = None                                    # the fp32 copy has served its purpose
@@ -199,9 +200,9 @@ class ChunkedPrepared:
         if self._whole is None:
             if self.X is None:
                 raise RuntimeError("the rows have already been consumed chunk by chunk")
-            st = torch.cuda.current_stream(self.device)
             for ev in self.ready:
-                st.wait_event(ev)
+                if ev is not None:
+                    torch.cuda.current_stream(self.device).wait_event(ev)
             self._whole = Prepared(self.X, self.mean, self.scale, kind=self.kind)
         return self._whole
 

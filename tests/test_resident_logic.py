@@ -23,6 +23,9 @@ class _FakePrepared:
         self.n, self.d, self.kind, self.pitch = X.shape[0], X.shape[1], 1, X.shape[1]
 
 
+_FakePreparedBase = _FakePrepared
+
+
 class _FakeRhs:
     def __init__(self, m, T, device):
         self.m, self.T, self.T_pad, self.V = int(m), int(T), (16 if T <= 16 else 32), None
@@ -311,3 +314,50 @@ def test_hi_only_tier_applies_to_filled_resident_panels_only(emu, monkeypatch):
         store["hi"].clear()
         sw.dmmv(torch.randn(150, 5, generator=g), None, out)
         assert store["hi"] == [("mmv", hi), ("panel", hi)] * 2 + [("panel", False)]
+
+
+@pytest.mark.parametrize("n,M,T,mode", [(700, 150, 5, "resident"), (600, 90, 3, "auto"), (700, 150, 5, "recompute")])
+def test_chunked_rows_are_prepared_when_the_filling_sweep_reaches_them(emu, monkeypatch, n, M, T, mode):
+    """ops.ChunkedPrepared (rows that arrive from the host chunk by chunk): the chunk-aligned, fully resident single-copy
+    sweep prepares chunk i when the panel-filling pass reaches it -- in order, once, never again in later sweeps -- and
+    drops the fp32 copy after the last one; any other consumer (another sweep mode, a chunk size that does not match) gets
+    the whole point set.  Sweeps equal the oracle's dmmv either way."""
+    ops, store = emu
+    monkeypatch.setattr(ops, "RESIDENT_SINGLE_COPY", True)
+    monkeypatch.setattr(ops, "resident_plan", lambda n_rows, M_, dev, budget=None: None)      # everything fits
+    made = []
+
+    class Prep(_FakePreparedBase):
+        def __init__(self, X, mean=None, scale=1.0, kind=None, linear=False):
+            super().__init__(X)
+            made.append(int(X.shape[0]))
+
+    monkeypatch.setattr(ops, "Prepared", Prep)
+    monkeypatch.setattr(ops, "resolve_kind", lambda kind=None: 1)
+    g = torch.Generator().manual_seed(n + T)
+    X = torch.randn(n, 12, generator=g, dtype=DT)
+    C = X[torch.randperm(n, generator=g)[:M]]
+    chunk = ops._resident_chunk(n)
+    n_chunks = -(-n // chunk)
+    rows = ops.ChunkedPrepared(X, chunk, [None] * n_chunks)
+    sw = ops.Sweeper(rows, _FakePrepared(C), 3.0, T, mode=mode)
+    out = torch.empty((M, T), dtype=torch.float32)
+    y = torch.randn(n, T, generator=g)
+    sw.dmmv(None, y, out, 1.0, 1.0 / n)
+    assert (out.to(DT) - orc.dmmv(X, C, None, y.to(DT) / n, 3.0, DT)).abs().max() <= 2e-5 * out.abs().max()
+    if mode == "recompute":
+        assert made == [n] and rows.parts == [None] * n_chunks            # one whole-set preparation, no chunk touched
+    else:
+        assert made == [min(chunk, n - r0) for r0 in range(0, n, chunk)] and rows.X is None
+    for _ in range(2):
+        v = torch.randn(M, T, generator=g)
+        sw.dmmv(v, None, out, 0.5)
+        ref = 0.5 * orc.dmmv(X, C, v.to(DT), None, 3.0, DT)
+        assert (out.to(DT) - ref).abs().max() <= 2e-5 * ref.abs().max()
+    assert len(made) == (1 if mode == "recompute" else n_chunks)          # later sweeps prepare nothing
+    # a chunk size that is not the sweeper's: the whole set
+    rows2 = ops.ChunkedPrepared(X, 128, [None] * (-(-n // 128)))
+    made.clear()
+    sw2 = ops.Sweeper(rows2, _FakePrepared(C), 3.0, T, mode="resident")
+    sw2.dmmv(None, y, out, 1.0, 1.0 / n)
+    assert made == [n] and (out.to(DT) - orc.dmmv(X, C, None, y.to(DT) / n, 3.0, DT)).abs().max() <= 2e-5 * out.abs().max()
