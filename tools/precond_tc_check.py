@@ -86,6 +86,13 @@ def fits():
 
 
 if __name__ == "__main__":
+    # ODF_CHECK="d,sigma,lam" overrides the factor check's data (C3: "256,10,1e-6"); ODF_CHECK_FITS=0 skips the fits
+    cfg = os.environ.get("ODF_CHECK")
+    kw = {}
+    if cfg:
+        d_, s_, l_ = cfg.split(",")
+        kw = {"d": int(d_), "sigma": float(s_), "lam": float(l_)}
     for M in [int(a) for a in sys.argv[1:]] or [2500, 10000]:
-        factors(M)
-    fits()
+        factors(M, **kw)
+    if os.environ.get("ODF_CHECK_FITS", "1") != "0":
+        fits()
