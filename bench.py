@@ -292,12 +292,13 @@ def _score_agreement(got, ref, band=1e-3):
     got, ref = got.double(), ref.double()
     scale = float(ref.abs().max())
     rel = float((got - ref).abs().max() / scale)
+    rms = float((got - ref).pow(2).mean().sqrt() / scale)          # the typical error beside the worst one
     if ref.shape[1] < 2:
-        return {"rel_score_err": rel, "argmax_flips": 0.0, "argmax_flips_outside_band": 0.0}
+        return {"rel_score_err": rel, "rel_score_err_rms": rms, "argmax_flips": 0.0, "argmax_flips_outside_band": 0.0}
     flips = got.argmax(1) != ref.argmax(1)
     top2 = ref.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 2 * band * scale
-    return {"rel_score_err": rel, "argmax_flips": float(flips.double().mean()),
+    return {"rel_score_err": rel, "rel_score_err_rms": rms, "argmax_flips": float(flips.double().mean()),
             "argmax_flips_outside_band": float((flips & clear).double().sum() / max(1, int(clear.sum())))}
 
 
