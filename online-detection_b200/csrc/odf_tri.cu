@@ -6,8 +6,9 @@
 // fp64) and the sums carry no fp32 rounding, so an application is an exactly rounded linear map of its fp32 inputs --
 // the applications were a main source of the arithmetic noise that 20 CG iterations amplify into the scores
 // (profiles/r2_accuracy_probe_200k_4k.log: triangular solves 1.7e-4, explicit inverse through sgemm 3.7e-4 against the fp64
-// oracle).  Bound: M^2 T / 2 fp64 FMAs (1.6e9 at M = 10 k, T = 32: ~90 us at the B200's 64 DFMA / clk / SM) against
-// 200 MB of triangle (31 us of HBM): DFMA-bound, and still half the time of the library call.
+// oracle).  Bound: M^2 T / 2 fp64 FMAs (1.6e9 at M = 10 k, T = 32) against 200 MB of triangle (31 us of HBM): bound by the
+// fp64 rate, which on this part saturates at 17 TFLOP/s (0.19 ms) whichever way it is issued -- the time of the library's
+// fp32 call, with fp64 accumulation and half the bytes.
 //
 // Persistent CTAs (one per SM) deal the 32-row output blocks out snake-wise, largest first (block b of a round goes to CTA b
 // in even rounds and to CTA G-1-b in odd ones): a block's work is proportional to its part of the triangle, so two
