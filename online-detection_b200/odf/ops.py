@@ -33,7 +33,10 @@ def _count(n):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # the raw cudaStream_t of torch's current stream on the current device.  torch.cuda.current_stream() builds a Stream
+    # object and re-checks the device count on every call (~10 us, a good part of the host cost of a launch in the
+    # launch-bound small fits); the two C-level accessors below are what it wraps.
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _req(t, name, ndim=None):
@@ -43,7 +46,7 @@ def _req(t, name, ndim=None):
         raise ValueError("%s must live on a CUDA device (the FALKON hot path has no CPU fallback)" % name)
     if t.dtype != torch.float32:
         raise ValueError("%s must be float32, got %s" % (name, t.dtype))
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != torch._C._cuda_getDevice():
         # libodf launches on the CURRENT device's current stream (one process per GPU): a tensor on another
         # device would be read through a wrong-device launch.  Wrap the call in torch.cuda.device(t.device).
         raise ValueError("%s lives on cuda:%d but the current device is cuda:%d (one device per process; use "
@@ -951,6 +954,7 @@ class Sweeper:
 # EXPERIMENTAL precision tier: resident sweeps stream the hi plane only (K to 11 bits, 2 B per value) once the panels
 # are filled.  ODF_PANEL_HI_ONLY=1.  Off by default: emulated on the CPU only so far (tools/precision_study.py).
 PANEL_HI_ONLY = os.environ.get("ODF_PANEL_HI_ONLY", "0") not in ("0", "")
+RESIDENT_NO_QUERY = 1 << 30  # panels up to this size are taken to fit without querying the free memory
 RESIDENT_FRACTION = 0.85   # share of the free device memory the resident panels may take in mode "auto"
 # keep only K_chunk (default) instead of K_chunk and K_chunk^T: K v then comes from the same panel through
 # odf_panel16_mmv, half the memory and no transposed tile pass.  ODF_RESIDENT_SINGLE=0 selects the two-copy variant.
@@ -983,8 +987,13 @@ def resident_plan(n_rows, M, device, budget=None):
     into RESIDENT_FRACTION of the free device memory; otherwise (single-copy variant) as many as fit beside the
     transient panel the streamed chunks share; 0 = stream everything (mode "panel16")."""
     L = _lib.load()
+    need = resident_bytes(n_rows, M)
+    if budget is None and need <= RESIDENT_NO_QUERY:
+        # small fits (the minibootstrap regime: a few MB of panel, hundreds of refits): cudaMemGetInfo costs ~3 ms on a
+        # 180 GB device, a third of such a fit -- do not ask; an allocation failure falls back to streaming anyway
+        return None
     budget = RESIDENT_FRACTION * _free_bytes(device) if budget is None else budget
-    if resident_bytes(n_rows, M) <= budget:
+    if need <= budget:
         return None                                                 # everything (chunks of _resident_chunk rows)
     if not RESIDENT_SINGLE_COPY:
         return 0
