@@ -60,7 +60,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int TRANSPOSED>
+// NJ = column fragments of 8 right-hand sides a warp accumulates: 4 (T <= 32) or 1 (T <= 8: the one-class fits of the
+// minibootstrap, where the kernel is bound by the latency of a block's slice chain, not by the DMMA rate)
+template <int TRANSPOSED, int NJ>
 __global__ void __launch_bounds__(32 * TW, 1)
 tri_apply_kernel(const float* __restrict__ U, int64_t M, const float* __restrict__ Bm, int64_t ldb, int T,
                  float* __restrict__ out, int64_t ldo, int64_t row0, int64_t row1, int n_blocks) {
@@ -78,11 +80,11 @@ tri_apply_kernel(const float* __restrict__ U, int64_t M, const float* __restrict
     const int64_t cbeg = TRANSPOSED ? 0 : (r0 / TC) * TC;
     const int64_t cend = TRANSPOSED ? (r0 + rn) : M;
     const int n_slices = static_cast<int>((cend - cbeg + TC - 1) / TC);
-    double acc[4][4][2];                     // [row tile i][column tile j]: rows 8 i + lq, columns 8 j + 2 lr, + 1
+    double acc[4][NJ][2];                    // [row tile i][column tile j]: rows 8 i + lq, columns 8 j + 2 lr, + 1
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     // slice sl -> stage sl % TNS (one commit group per slice, empty past the end)
     auto issue = [&](int sl) {
       if (sl < n_slices) {
@@ -120,15 +122,15 @@ tri_apply_kernel(const float* __restrict__ U, int64_t M, const float* __restrict
       const float* Us = tri_smem + (sl % TNS) * TSTAGE;
       const float* Bs = Us + US;
       const int c = 4 * warp + lr;           // this lane's contraction value of the warp's k = 4 step
-      double a[4], b[4];
+      double a[4], b[NJ];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = static_cast<double>(TRANSPOSED ? Us[c * PU1 + 8 * i + lq] : Us[(8 * i + lq) * PU0 + c]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = static_cast<double>(Bs[c * PB + 8 * j + lq]);
+      for (int j = 0; j < NJ; ++j) b[j] = static_cast<double>(Bs[c * PB + 8 * j + lq]);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     cp_async_wait<0>();
     // cross-warp reduction in warp order, 4 warps at a time: red[w][s = 4 i + j][lane] (double2) aliases the ring
@@ -141,7 +143,7 @@ tri_apply_kernel(const float* __restrict__ U, int64_t M, const float* __restrict
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) red[((warp & 3) * 16 + 4 * i + j) * 32 + lane] = make_double2(acc[i][j][0], acc[i][j][1]);
+          for (int j = 0; j < NJ; ++j) red[((warp & 3) * 16 + 4 * i + j) * 32 + lane] = make_double2(acc[i][j][0], acc[i][j][1]);
       }
       __syncthreads();
 #pragma unroll
@@ -155,7 +157,7 @@ tri_apply_kernel(const float* __restrict__ U, int64_t M, const float* __restrict
       // thread -> (s = 4 i + j, lane') of the layout above: row 8 i + lq', columns 8 j + 2 lr', + 1
       const int s = threadIdx.x >> 5, i = s >> 2, j = s & 3;
       const int r = 8 * i + lq, t = 8 * j + 2 * lr;
-      if (r < rn) {
+      if (r < rn && j < NJ) {
         float* o = out + (r0 - row0 + r) * ldo + t;
         if (t < T) o[0] = static_cast<float>(total.x);
         if (t + 1 < T) o[1] = static_cast<float>(total.y);
@@ -177,15 +179,23 @@ int tri_apply(const float* U, int64_t M, const float* Bm, int64_t ldb, int64_t T
   static DeviceOnce attr_once;
   bool& attr_set = attr_once.here();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tri_apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tri_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tri_apply_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tri_apply_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tri_apply_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tri_apply_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(tri_apply_kernel)");
     attr_set = true;
   }
   const int sms = tri_sm_count();
   const int grid = n_blocks < sms ? n_blocks : sms;
-  if (transposed) tri_apply_kernel<1><<<grid, 32 * TW, TRI_SMEM, st>>>(U, M, Bm, ldb, static_cast<int>(T), out, ldo, row0, row1, n_blocks);
-  else tri_apply_kernel<0><<<grid, 32 * TW, TRI_SMEM, st>>>(U, M, Bm, ldb, static_cast<int>(T), out, ldo, row0, row1, n_blocks);
+  const int Ti = static_cast<int>(T);
+  if (T <= 8) {
+    if (transposed) tri_apply_kernel<1, 1><<<grid, 32 * TW, TRI_SMEM, st>>>(U, M, Bm, ldb, Ti, out, ldo, row0, row1, n_blocks);
+    else tri_apply_kernel<0, 1><<<grid, 32 * TW, TRI_SMEM, st>>>(U, M, Bm, ldb, Ti, out, ldo, row0, row1, n_blocks);
+  } else {
+    if (transposed) tri_apply_kernel<1, 4><<<grid, 32 * TW, TRI_SMEM, st>>>(U, M, Bm, ldb, Ti, out, ldo, row0, row1, n_blocks);
+    else tri_apply_kernel<0, 4><<<grid, 32 * TW, TRI_SMEM, st>>>(U, M, Bm, ldb, Ti, out, ldo, row0, row1, n_blocks);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ODF_OK : set_cuda_error(e, "tri_apply_kernel launch");
 }
