@@ -18,4 +18,4 @@ if p: print({k: p.get(k) for k in ('alpha_max_abs_diff_across_ranks','rel_score_
 }
 run c2 29521 --steps 5 --warmup 3 --no-cpu-baseline --no-c1-pair --no-streaming-compare
 run c5 29522 --workload c5 --steps 5 --warmup 3 --no-cpu-baseline
-if [ "$N" = "8" ]; then run c3 29523 --workload c3 --steps 1 --warmup 1 --no-cpu-baseline --no-c1-pair --no-streaming-compare --no-parity; fi
+if [ "$N" = "8" ] && [ "${DO_C3:-1}" = "1" ]; then run c3 29523 --workload c3 --steps 1 --warmup 1 --no-cpu-baseline --no-c1-pair --no-streaming-compare --no-parity; fi
