@@ -243,3 +243,34 @@ def test_chunked_upload_fit_matches_device_fit(odf, monkeypatch, mode):
         else:
             assert torch.equal(m.alpha_, base.alpha_)
         assert rel(m.predict(X[:2000].cuda()), ref) < 2e-4
+
+
+@pytest.mark.parametrize("n,T,S,with_addend", [(5000, 30, 3, True), (700, 1, 1, False), (8192, 16, 2, True), (9000, 30, 3, True), (300, 21, 1, False)])
+def test_finish_w16_arithmetic_restated(odf, n, T, S, with_addend):
+    """odf_finish_w16: slab reduction (index order) + addend, per-column power-of-two scales from max |W|, fp16 hi | lo split --
+    bit for bit the arithmetic restated here in torch (small and large, ragged, T = 1, with and without an addend)."""
+    from odf import ops
+    g = torch.Generator().manual_seed(n + T)
+    T_pad = 16 if T <= 16 else 32
+    part = torch.randn(S, n, T_pad, generator=g) * torch.logspace(-3, 3, T_pad)[None, None, :]
+    add = torch.randn(n, T, generator=g) if with_addend else None
+    Wf = torch.full((n, T_pad), float("nan"), device="cuda")
+    W16 = torch.full(((n + 127) // 128 * 128, 64), float("nan"), dtype=torch.float16, device="cuda")
+    absmax = torch.full((32,), 123, dtype=torch.int32, device="cuda")
+    ops.finish_w16(part.cuda(), T, Wf, absmax, W16, None if add is None else add.cuda())
+    W = torch.zeros(n, T_pad)
+    for s in range(S):
+        W = W + part[s]
+    W = W[:, :T] + (add if add is not None else 0.0)
+    assert torch.equal(Wf[:, :T].cpu(), W)
+    amax = W.abs().max(0).values
+    bits = amax.view(torch.int32)
+    assert torch.equal(absmax[:T].cpu(), bits) and int(absmax[T:].abs().sum()) == 0
+    e = ((bits >> 23) & 0xff) - 127
+    scale = torch.where(amax > 0, torch.pow(2.0, (14 - e).float()), torch.ones_like(amax))
+    v = W * scale[None, :]
+    hi = v.half()
+    lo = ((v - hi.float()) * 2048.0).half()
+    got = W16.cpu()
+    assert torch.equal(got[:n, :T], hi) and torch.equal(got[:n, 32:32 + T], lo)
+    assert float(got[n:].abs().sum()) == 0 and float(got[:, T:32].abs().sum()) == 0 and float(got[:, 32 + T:].abs().sum()) == 0
